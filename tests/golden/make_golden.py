@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the REAL in-tree reference.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+What is real and what is stood in:
+  * real, imported unmodified from /root/reference:
+      Stage3_source/cond_diff_transformer_layer.py   (get_model, forward, conditioning layout)
+      Stage3_source/transformer_training_helper.py   (cond_predict_conditional_prob)
+      Stage3_source/sampling_analysis.py             (predict_next_index, batch_generate_denoised_sampled)
+      Stage3_source/animation_tools.py               (convert_num_to_char)
+  * stood in, because the wheels are not installed and there is no network:
+      linear_attention_transformer / axial_positional_embedding -> oracle/upstream_blocks.py
+      Bio, matplotlib, imageio -> empty stand-ins (only imported, never called on this path)
+
+So the fixtures pin everything the reference keeps in its own tree (conditioning
+layout, time embedding, output permute, softmax axis, OneHotCategorical draw, the
+cross-sample unmask write, return lists); the transformer block itself stays
+"parity unpinned" (oracle/upstream_blocks.py header).
+
+The reference sampler draws from torch's global CPU generator.  Each case seeds it
+with ``torch.manual_seed(noise_seed)`` right before the call; the consumer
+(tests/test_oracle_vs_reference.py) rebuilds the same Exp(1) stream with
+``torch.empty(B*L, C).exponential_(1)`` per step after the same seed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+sys.path.insert(0, ROOT)
+
+from biom3_b200 import synthetic  # noqa: E402
+from oracle import upstream_blocks  # noqa: E402
+
+
+def _install_stand_ins():
+    lat = types.ModuleType('linear_attention_transformer')
+    lat.LinearAttentionTransformer = upstream_blocks.LinearAttentionTransformer
+    sys.modules['linear_attention_transformer'] = lat
+    ax = types.ModuleType('axial_positional_embedding')
+    ax.AxialPositionalEmbedding = upstream_blocks.AxialPositionalEmbedding
+    sys.modules['axial_positional_embedding'] = ax
+    for name in ('Bio', 'Bio.Align', 'matplotlib', 'matplotlib.pyplot', 'imageio'):
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = mock.MagicMock(name=name)
+
+
+def import_reference():
+    _install_stand_ins()
+    sys.path.insert(0, REF)
+    import Stage3_source.cond_diff_transformer_layer as mod
+    import Stage3_source.sampling_analysis as samp
+    import Stage3_source.transformer_training_helper as helper
+    import Stage3_source.animation_tools as ani
+    assert mod.__file__.startswith(REF) and samp.__file__.startswith(REF)
+    return mod, samp, helper, ani
+
+
+CASES = {
+    # name: (arg overrides, batch, n_iters, start_step)
+    'tiny_b3': (dict(diffusion_steps=256, transformer_dim=64, transformer_heads=4, transformer_depth=2,
+                     transformer_local_heads=2, transformer_local_size=64, text_emb_dim=32), 3, 256, 0),
+    'tiny_b1': (dict(diffusion_steps=256, transformer_dim=64, transformer_heads=4, transformer_depth=2,
+                     transformer_local_heads=2, transformer_local_size=64, text_emb_dim=32), 1, 256, 0),
+    'tiny_resume_b2': (dict(diffusion_steps=256, transformer_dim=64, transformer_heads=4, transformer_depth=2,
+                            transformer_local_heads=2, transformer_local_size=64, text_emb_dim=32), 2, 56, 200),
+    'mid_b2': (dict(diffusion_steps=512, transformer_dim=128, transformer_heads=4, transformer_depth=3,
+                    transformer_local_heads=2, transformer_local_size=128, text_emb_dim=512), 2, 512, 0),
+}
+
+
+def run_case(mod, samp, name):
+    over, B, n_iters, start = CASES[name]
+    args = synthetic.stage3_args(**over)
+    L, C = args.diffusion_steps, args.num_classes
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    model = mod.get_model(args, (args.image_size, args.image_size), C)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    z_c = synthetic.synthetic_z_c(1, args.text_emb_dim, seed=12).repeat(B, 1)
+    path = synthetic.synthetic_paths(B, L, seed=13)
+    g = torch.Generator().manual_seed(14)
+    if start > 0:
+        # a partially unmasked start state: positions whose path index < start hold a token
+        toks = torch.randint(1, C, (B, L), generator=g)
+        state0 = torch.where(path < start, toks, torch.zeros_like(toks)).float()
+    else:
+        state0 = torch.zeros(B, L)
+    # forward fixture: random tokens, distinct steps per sample
+    x = torch.randint(0, C, (B, L), generator=g)
+    t = torch.randint(0, L, (B,), generator=g)
+    with torch.no_grad():
+        logits = model(x, t, z_c)
+    # sampler fixture: the real loop, global generator seeded.
+    # On a CPU device ``state.cpu().numpy()`` (sampling_analysis.py:259-260) ALIASES the live
+    # state tensor, so every list entry the reference returns here is the same final array; on
+    # its intended CUDA device each entry is a snapshot.  The fixture records the snapshots the
+    # CUDA run would return: the model input of call i+1 is the state after step i.
+    seen_x, seen_t = [], []
+
+    class Recorder(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x, t, y_c):
+            seen_x.append(x.detach().clone())
+            seen_t.append(t.detach().clone())
+            return self.inner(x=x, t=t, y_c=y_c)
+
+    noise_seed = 15
+    torch.manual_seed(noise_seed)
+    states, times = samp.batch_generate_denoised_sampled(
+        args=args, model=Recorder(model).eval(), extract_digit_samples=state0.clone(),
+        extract_time=torch.full((B,), start).long(), extract_digit_label=z_c, sampling_path=path)
+    assert len(states) == n_iters == len(seen_x), (len(states), n_iters)
+    assert all(s is not None and np.array_equal(s, states[-1]) for s in states)   # the aliasing
+    snaps = [sx.numpy()[:, None, :] for sx in seen_x[1:]] + [states[-1]]
+    traj = np.stack(snaps).astype(np.uint8)           # [T, B, 1, L]
+    tt = np.stack([st.numpy()[:, None] for st in seen_t]).astype(np.int32)   # [T, B, 1]
+    np.savez_compressed(
+        os.path.join(HERE, f'{name}.npz'),
+        x=x.numpy().astype(np.uint8), t=t.numpy().astype(np.int32), z_c=z_c.numpy(),
+        logits=logits.numpy(), path=path.numpy().astype(np.int32), state0=state0.numpy().astype(np.uint8),
+        start=np.int32(start), noise_seed=np.int32(noise_seed), traj=traj, times=tt,
+        weight_seed=np.int32(11),
+        overrides=np.array(repr(over)))
+    print(name, 'logits', tuple(logits.shape), 'traj', traj.shape)
+
+
+def full_config_forward(mod):
+    """stage3_config.json shape, B=2 (distinct steps), forward only: logits fixture (fp32)."""
+    args = synthetic.stage3_args()
+    sd = synthetic.random_state_dict(args, seed=0)
+    model = mod.get_model(args, (32, 32), 29)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    g = torch.Generator().manual_seed(21)
+    B = 2
+    x = torch.randint(0, 29, (B, 1024), generator=g)
+    x[1, 300:] = 0                                    # a partly masked row
+    t = torch.tensor([17, 900])
+    z_c = synthetic.synthetic_z_c(B, 512, seed=1)
+    with torch.no_grad():
+        logits = model(x, t, z_c)
+    np.savez_compressed(os.path.join(HERE, 'full_forward_b2.npz'),
+                        x=x.numpy().astype(np.uint8), t=t.numpy().astype(np.int32), z_c=z_c.numpy(),
+                        logits=logits.numpy().astype(np.float32), weight_seed=np.int32(0))
+    print('full_forward_b2', tuple(logits.shape))
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    mod, samp, helper, ani = import_reference()
+    for name in CASES:
+        run_case(mod, samp, name)
+    full_config_forward(mod)
+    toks = np.arange(29)
+    s = ani.convert_num_to_char(synthetic.TOKENS, toks)
+    with open(os.path.join(HERE, 'convert_num_to_char.txt'), 'w') as f:
+        f.write(s)
+    print('done')
+
+
+if __name__ == '__main__':
+    main()
