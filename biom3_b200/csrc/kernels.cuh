@@ -1,0 +1,434 @@
+// Bandwidth-bound kernels of the ProteoScribe step: embedding + conditioning + LayerNorm, the vocab
+// head, the softmax / renormalise / Exp(1)-race categorical draw, the unmask scatter, and the small
+// fp32 GEMM used once per model load / per prompt for the conditioning MLPs.
+//
+// Reference semantics:
+//   embed + axial pos + per-layer additive conditioning  /root/reference/Stage3_source/cond_diff_transformer_layer.py:152-171
+//   final LayerNorm + vocab head + permute                /root/reference/Stage3_source/cond_diff_transformer_layer.py:173-176
+//   softmax(dim=1) + OneHotCategorical                    /root/reference/Stage3_source/transformer_training_helper.py:443-449
+//   sample every position, argmax, unmask write           /root/reference/Stage3_source/sampling_analysis.py:251-256
+#pragma once
+#include "ptx.cuh"
+
+namespace k {
+
+// Device-resident loop state: the persistent step loop never returns to the host.
+struct DecodeCtl {
+  int step;                    // current time index t (same for every sample during a decode)
+  int start;                   // step the decode started at (index 0 of noise / trajectory)
+  unsigned int done;           // block-completion counter used to advance `step` exactly once
+  int pad;
+  const float* noise;          // external Exp(1) noise [T][B*L][C] or nullptr -> Philox
+  uint8_t* traj;               // trajectory [T][B][L] or nullptr
+  unsigned long long seed;     // Philox seed when noise == nullptr
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int MAXV = 8;   // up to D = 1024 (D / 128 float4 groups per lane)
+
+// LayerNorm of one row held as nv float4 per lane; writes bf16.
+__device__ __forceinline__ void ln_row_store(const float4 (&v)[MAXV], int nv, int D, int lane,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             __nv_bfloat16* __restrict__ dst) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / float(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / float(D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + col));
+      const float o0 = (v[i].x - mean) * rstd * gm.x + bt.x;
+      const float o1 = (v[i].y - mean) * rstd * gm.y + bt.y;
+      const float o2 = (v[i].z - mean) * rstd * gm.z + bt.z;
+      const float o3 = (v[i].w - mean) * rstd * gm.w + bt.w;
+      *reinterpret_cast<uint2*>(dst + col) = make_uint2(ptx::pack_bf16x2(o0, o1), ptx::pack_bf16x2(o2, o3));
+    }
+}
+
+// cvec[b][j][d] = Ttab[t_b][j][d] + Y[b][j][d]
+__global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* __restrict__ Y,
+                                  const int* __restrict__ t_per_sample, const DecodeCtl* __restrict__ ctl,
+                                  float* __restrict__ cvec, int B, int JD) {
+  const int b = blockIdx.y;
+  const int t = t_per_sample ? t_per_sample[b] : ctl->step;
+  const float4* tt = reinterpret_cast<const float4*>(Ttab + size_t(t) * JD);
+  const float4* yy = reinterpret_cast<const float4*>(Y + size_t(b) * JD);
+  float4* cc = reinterpret_cast<float4*>(cvec + size_t(b) * JD);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < JD / 4; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(tt + i), c = __ldg(yy + i);
+    cc[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+}
+
+// u[b,l,:] = E[x] + (ax0[l / W] + ax1[l % W]) + cvec[b][0][:] ; a = LN(u) (first layer's pre-norm)
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
+                const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ u,
+                __nv_bfloat16* __restrict__ a, int rows, int L, int W, int D) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    const int b = row / L, l = row % L;
+    const int tok = state[row];
+    const float* e = emb + size_t(tok) * D;
+    const float* p0 = ax0 + size_t(l / W) * D;
+    const float* p1 = ax1 + size_t(l % W) * D;
+    const float* cv = cvec + size_t(b) * cond_stride;
+    float4 v[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(e + col));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(p0 + col));
+        const float4 x2 = __ldg(reinterpret_cast<const float4*>(p1 + col));
+        const float4 x3 = __ldg(reinterpret_cast<const float4*>(cv + col));
+        v[i] = make_float4((x0.x + (x1.x + x2.x)) + x3.x, (x0.y + (x1.y + x2.y)) + x3.y,
+                           (x0.z + (x1.z + x2.z)) + x3.z, (x0.w + (x1.w + x2.w)) + x3.w);
+        *reinterpret_cast<float4*>(u + size_t(row) * D + col) = v[i];
+      }
+    ln_row_store(v, nv, D, lane, gamma, beta, a + size_t(row) * D);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ a, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    float4 v[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) v[i] = *reinterpret_cast<const float4*>(u + size_t(row) * D + (i * 32 + lane) * 4);
+    ln_row_store(v, nv, D, lane, gamma, beta, a + size_t(row) * D);
+  }
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 -> Exp(1)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// Exp(1) draw for (step, flat position, class): -log(u), u in (0, 1]
+__device__ __forceinline__ float philox_exp1(unsigned long long seed, int step, int pos, int c) {
+  const uint4 r = philox4x32_10(make_uint4(uint32_t(pos), uint32_t(step), uint32_t(c >> 2), 0u),
+                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const float uu = (float(w[c & 3] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  return -__logf(uu) + 1e-30f;
+}
+
+// ---------------------------------------------------------------- categorical draw (one warp, lane = class)
+// p = softmax(logits); p /= sum(p); token = argmax(p / q), ties -> lowest class id.
+// The two sums run sequentially over c = 0..C-1 (the order the fp32 CPU reference accumulates in).
+__device__ __forceinline__ int categorical_draw(float logit, float q, int lane, int C) {
+  const bool valid = lane < C;
+  float mx = valid ? logit : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = valid ? expf(logit - mx) : 0.f;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += __shfl_sync(0xffffffffu, e, c);
+  float p = e / s;
+  float s2 = 0.f;
+  for (int c = 0; c < C; ++c) s2 += __shfl_sync(0xffffffffu, p, c);
+  p = p / s2;
+  float r = valid ? p / q : -INFINITY;
+  int idx = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float r2 = __shfl_xor_sync(0xffffffffu, r, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (r2 > r || (r2 == r && i2 < idx)) { r = r2; idx = i2; }
+  }
+  return idx;
+}
+
+// Final LayerNorm + vocab head for a list of tokens; optionally writes logits [B][C][L] and/or draws
+// and scatters tokens.  SELECTED mode (decode): token list = {(b', loc[b]) : b in group(b')},
+// loc[b] = inv_path[b][step]  -> this IS the reference's B x B unmask write.  ALL mode: every token.
+struct HeadArgs {
+  const float* u;            // [rows][D] fp32 hidden after the last block
+  const float* gamma; const float* beta;     // final LayerNorm
+  const float* w_out;        // [C][D] fp32
+  const float* b_out;        // [C]
+  float* logits_out;         // [B][C][L] or nullptr
+  uint8_t* state;            // [B][L] updated in place when sampling, or nullptr
+  const int* inv_path;       // [B][L] (SELECTED mode)
+  const DecodeCtl* ctl;      // step / noise / seed (sampling)
+  int B, L, D, C, group;     // group = samples per reference batch (SELECTED mode); 0 -> ALL mode
+};
+
+__global__ void __launch_bounds__(256)
+head_kernel(const HeadArgs a) {
+  extern __shared__ float s_w[];                 // [C][D] staged vocab head
+  for (int i = threadIdx.x; i < a.C * a.D / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(a.w_out) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv = a.D / 128;
+  const int ntok = a.group > 0 ? a.B * a.group : a.B * a.L;
+  const int step = a.ctl ? a.ctl->step : 0;
+  for (int ti = blockIdx.x * 8 + (threadIdx.x >> 5); ti < ntok; ti += gridDim.x * 8) {
+    int b, l;
+    if (a.group > 0) {
+      b = ti / a.group;
+      const int src = (b / a.group) * a.group + (ti % a.group);     // sample whose location is written
+      l = a.inv_path[size_t(src) * a.L + step];
+    } else {
+      b = ti / a.L;
+      l = ti % a.L;
+    }
+    const size_t row = size_t(b) * a.L + l;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) {
+        v[i] = *reinterpret_cast<const float4*>(a.u + row * a.D + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    const float mean = warp_sum(s) / float(a.D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) {
+        const float x0 = v[i].x - mean, x1 = v[i].y - mean, x2 = v[i].z - mean, x3 = v[i].w - mean;
+        q += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / float(a.D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + col));
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + col));
+        v[i] = make_float4((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y,
+                           (v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
+      }
+    float my_logit = 0.f;                        // lane c ends up holding logit c
+    for (int c = 0; c < a.C; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + size_t(c) * a.D + (i * 32 + lane) * 4);
+          acc = fmaf(v[i].x, w4.x, acc);
+          acc = fmaf(v[i].y, w4.y, acc);
+          acc = fmaf(v[i].z, w4.z, acc);
+          acc = fmaf(v[i].w, w4.w, acc);
+        }
+      acc = warp_sum(acc);
+      if (lane == c) my_logit = acc + __ldg(a.b_out + c);
+    }
+    if (a.logits_out && lane < a.C) a.logits_out[(size_t(b) * a.C + lane) * a.L + l] = my_logit;
+    if (a.state) {
+      const int pos = int(row);
+      float qn = 1.f;
+      if (lane < a.C) {
+        if (a.ctl->noise) {
+          const size_t BLC = size_t(a.B) * a.L * a.C;
+          qn = __ldg(a.ctl->noise + size_t(step - a.ctl->start) * BLC + size_t(pos) * a.C + lane);
+        } else {
+          qn = philox_exp1(a.ctl->seed, step, pos, lane);
+        }
+      }
+      const int tok = categorical_draw(my_logit, qn, lane, a.C);
+      if (lane == 0) a.state[row] = uint8_t(tok);
+    }
+  }
+}
+
+// K11 as the reference runs it: draw a token at EVERY position.  logits [B][C][L], noise [B*L][C]
+// -> tok int64 [B][L].  One thread per position; bandwidth bound (logits + noise read once).
+__global__ void __launch_bounds__(256)
+sample_all_kernel(const float* __restrict__ logits, const float* __restrict__ noise, long long* __restrict__ tok,
+                  int B, int L, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L, l = i % L;
+  const float* lg = logits + size_t(b) * C * L + l;
+  const float* qn = noise + size_t(i) * C;
+  float x[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = __ldg(lg + size_t(c) * L);
+      mx = fmaxf(mx, x[c]);
+    }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = expf(x[c] - mx);
+      s += x[c];
+    }
+  float s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = x[c] / s;
+      s2 += x[c];
+    }
+  float best = -INFINITY;
+  int bi = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      const float r = (x[c] / s2) / __ldg(qn + c);
+      if (r > best) { best = r; bi = c; }
+    }
+  tok[i] = bi;
+}
+
+// K12: the reference unmask write.  For every sample b' and every sample b of its group:
+// state[b'][loc[b]] = tok[b'][loc[b]], loc[b] = position with path[b][loc] == step.
+__global__ void unmask_kernel(const long long* __restrict__ tok, const int* __restrict__ inv_path,
+                              long long* __restrict__ state, int B, int L, int group, int step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * group) return;
+  const int b = i / group;
+  const int src = (b / group) * group + (i % group);
+  const int l = inv_path[size_t(src) * L + step];
+  state[size_t(b) * L + l] = tok[size_t(b) * L + l];
+}
+
+__global__ void inverse_path_kernel(const long long* __restrict__ path, int* __restrict__ inv, int B, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L;
+  const long long t = path[i];
+  if (t >= 0 && t < L) inv[size_t(b) * L + t] = i % L;
+}
+
+__global__ void i64_to_u8_kernel(const long long* __restrict__ src, uint8_t* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = uint8_t(src[i]);
+}
+__global__ void u8_to_i64_kernel(const uint8_t* __restrict__ src, long long* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void i64_to_i32_kernel(const long long* __restrict__ src, int* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = int(src[i]);
+}
+
+// Last kernel of a step: snapshot the state into the trajectory, then advance `step` exactly once
+// (the last block to finish does it, after every block has read the old value).
+__global__ void advance_kernel(DecodeCtl* ctl, const uint8_t* __restrict__ state, int n) {
+  const int step = ctl->step;
+  if (ctl->traj) {
+    uint8_t* dst = ctl->traj + size_t(step - ctl->start) * n;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += gridDim.x * blockDim.x * 16)
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(state + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->done, 1u) == gridDim.x - 1) {
+      ctl->done = 0;
+      ctl->step = step + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- conditioning MLP pieces (fp32)
+// te[t][i] = sin/cos((t / num_steps * 4000) * exp(-i * ln(1e4) / (half - 1)))   [L][D]
+__global__ void time_embedding_kernel(float* __restrict__ te, int L, int D, float num_steps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * D) return;
+  const int t = i / D, c = i % D, half = D / 2;
+  const float x = float(t) / num_steps * 4000.0f;
+  const float e = logf(10000.0f) / float(half - 1);
+  const int f = c < half ? c : c - half;
+  const float arg = x * expf(float(f) * -e);
+  te[i] = c < half ? sinf(arg) : cosf(arg);
+}
+
+// C[M][N] = act(A[M][K] . W[N][K]^T + bias[N]); act: 0 none, 1 softplus(beta 1, threshold 20).
+// 64 x 64 tile, 16 x 16 threads, 4 x 4 outputs each.  Runs once per model load / per prompt.
+__global__ void __launch_bounds__(256)
+sgemm_bias_act_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                      float* __restrict__ Cm, int M, int N, int K, int act) {
+  __shared__ float sa[16][64 + 1], sb[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      sa[c][r] = (m0 + r < M) ? A[size_t(m0 + r) * K + k0 + c] : 0.f;
+      sb[c][r] = (n0 + r < N) ? W[size_t(n0 + r) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sa[kk][ty * 4 + i]; bv[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        float v = acc[i][j] + bias[n];
+        if (act == 1) v = v > 20.f ? v : log1pf(expf(v));
+        Cm[size_t(m) * N + n] = v;
+      }
+    }
+}
+
+// out[r][j][d] = in[r][d * depth + j]   (the reference's reshape(B,1,D,1,depth)[..., j] layout)
+__global__ void cond_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int D,
+                                      int depth) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t n = size_t(rows) * D * depth;
+  if (i >= n) return;
+  const int d = int(i % D);
+  const int j = int((i / D) % depth);
+  const size_t r = i / (size_t(D) * depth);
+  out[i] = in[r * size_t(D) * depth + size_t(d) * depth + j];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace k

@@ -1,0 +1,694 @@
+// C-ABI implementation: model handle, strict weight loading, per-step forward, persistent decode loop.
+// See include/biom3_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/biom3_b200.h"
+#include "attention.cuh"
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_OK(expr)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(BIOM3_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                      std::to_string(__LINE__) + ")");                               \
+  } while (0)
+
+using bf16 = __nv_bfloat16;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows][cols] -> tiles of [box_rows][64 cols], 128-byte swizzle
+int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(bf16)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return BIOM3_OK;
+}
+
+constexpr int STAGES_256 = 4;
+constexpr int STAGES_128 = 6;
+
+// launch only; the caller checks cudaGetLastError()
+template <int BN, int EPI, int EW>
+void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
+                   cudaStream_t st) {
+  constexpr int STAGES = BN == 256 ? STAGES_256 : STAGES_128;
+  const int smem = gemm::SmemLayout<BN, STAGES>::TOTAL;
+  const int tiles = (p.M / gemm::BM) * (p.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, EW><<<grid, 64 + 32 * EW, smem, st>>>(ta, tb, p);
+}
+
+template <int EPI, int EW>
+void launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
+                 cudaStream_t st) {
+  if (bn == 128) launch_gemm_t<128, EPI, EW>(ta, tb, p, num_sms, st);
+  else launch_gemm_t<256, EPI, EW>(ta, tb, p, num_sms, st);
+}
+
+constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
+
+// opt in to large dynamic shared memory for every kernel once per process, outside any stream capture
+cudaError_t init_kernel_attributes_impl() {
+  cudaError_t e;
+#define SET_GEMM(BN, EPI, EW)                                                                                    \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, (BN == 256 ? STAGES_256 : STAGES_128), EPI, EW>,          \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
+                           gemm::SmemLayout<BN, (BN == 256 ? STAGES_256 : STAGES_128)>::TOTAL);                  \
+  if (e != cudaSuccess) return e;
+  SET_GEMM(256, gemm::EPI_QKV_HEADMAJOR, 4)
+  SET_GEMM(128, gemm::EPI_QKV_HEADMAJOR, 4)
+  SET_GEMM(256, gemm::EPI_BIAS_RESID_F32, 4)
+  SET_GEMM(128, gemm::EPI_BIAS_RESID_F32, 4)
+  SET_GEMM(256, gemm::EPI_BIAS_GELU_BF16, 8)
+  SET_GEMM(128, gemm::EPI_BIAS_GELU_BF16, 8)
+  SET_GEMM(256, gemm::EPI_STORE_BF16, 4)
+  SET_GEMM(128, gemm::EPI_STORE_BF16, 4)
+  SET_GEMM(256, gemm::EPI_STORE_F32, 4)
+  SET_GEMM(128, gemm::EPI_STORE_F32, 4)
+#undef SET_GEMM
+  e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::LOCAL_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
+  return e;
+}
+
+cudaError_t init_kernel_attributes() {
+  static std::once_flag once;
+  static cudaError_t result = cudaSuccess;
+  std::call_once(once, [] { result = init_kernel_attributes_impl(); });
+  return result;
+}
+
+enum Cat { C_QKV, C_OUT, C_FF1, C_FF2, C_LOCAL, C_LINEAR, C_LN, C_EMBED, C_HEAD, C_OTHER, C_COUNT };
+
+struct Profiler {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cat;
+  cudaStream_t st;
+  void begin(int c) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    ev.push_back(a);
+    ev.push_back(b);
+    cat.push_back(c);
+    cudaEventRecord(a, st);
+  }
+  void end() { cudaEventRecord(ev.back(), st); }
+};
+
+}  // namespace
+
+struct biom3_model {
+  biom3_config cfg{};
+  int device = 0, max_batch = 0, num_sms = 0;
+  int bn_wide = 256, bn_narrow = 256;          // tile widths for the N = 3D/4D and N = D GEMMs
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> host_w;
+  // weights
+  bf16 *Wqkv = nullptr, *Wo = nullptr, *W1 = nullptr, *W2 = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *emb = nullptr, *ax0 = nullptr, *ax1 = nullptr, *norm_g = nullptr, *norm_b = nullptr;
+  float *w_out = nullptr, *b_out = nullptr;
+  float *Ttab = nullptr;
+  float *y_w0 = nullptr, *y_b0 = nullptr, *y_w2 = nullptr, *y_b2 = nullptr;
+  // workspace
+  float* u = nullptr;
+  bf16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
+  float *Yh = nullptr, *Ytmp = nullptr, *Y = nullptr, *cvec = nullptr;
+  uint8_t* state = nullptr;
+  int *inv_path = nullptr, *t_i32 = nullptr;
+  k::DecodeCtl* ctl = nullptr;
+  CUtensorMap tm_a{}, tm_att{}, tm_hid{};
+  CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
+  // step graph cache
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_B = -1, graph_group = -1;
+  std::vector<void*> allocs;
+  int launches_per_step = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(biom3_model* m, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(BIOM3_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  m->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return BIOM3_OK;
+}
+
+int get_w(biom3_model* m, const std::string& key, size_t numel, const std::vector<float>** out) {
+  auto it = m->host_w.find(key);
+  if (it == m->host_w.end()) return fail(BIOM3_ERR_STATE, "missing weight: " + key);
+  if (it->second.size() != numel)
+    return fail(BIOM3_ERR_STATE, "size mismatch for " + key + ": got " + std::to_string(it->second.size()) +
+                                     ", expected " + std::to_string(numel));
+  *out = &it->second;
+  return BIOM3_OK;
+}
+
+int upload_f32(biom3_model* m, const std::string& key, size_t numel, float* dst) {
+  const std::vector<float>* v;
+  int r = get_w(m, key, numel, &v);
+  if (r) return r;
+  CU_OK(cudaMemcpy(dst, v->data(), numel * sizeof(float), cudaMemcpyHostToDevice));
+  return BIOM3_OK;
+}
+
+int upload_bf16(biom3_model* m, const std::string& key, size_t numel, bf16* dst) {
+  const std::vector<float>* v;
+  int r = get_w(m, key, numel, &v);
+  if (r) return r;
+  std::vector<bf16> tmp(numel);
+  for (size_t i = 0; i < numel; ++i) tmp[i] = __float2bfloat16_rn((*v)[i]);
+  CU_OK(cudaMemcpy(dst, tmp.data(), numel * sizeof(bf16), cudaMemcpyHostToDevice));
+  return BIOM3_OK;
+}
+
+// C = act(A W^T + b), fp32 (conditioning MLPs only)
+void sgemm(const float* A, const float* W, const float* b, float* C, int M, int N, int K, int act, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  k::sgemm_bias_act_kernel<<<grid, 256, 0, st>>>(A, W, b, C, M, N, K, act);
+}
+
+// y_mlp(y_c) -> Y[b][j][d]
+void run_y_mlp(biom3_model* m, const float* y_c, int B, cudaStream_t st) {
+  const int D = m->cfg.dim, depth = m->cfg.depth, E = m->cfg.text_emb_dim;
+  sgemm(y_c, m->y_w0, m->y_b0, m->Yh, B, 4 * D, E, 1, st);
+  sgemm(m->Yh, m->y_w2, m->y_b2, m->Ytmp, B, D * depth, 4 * D, 0, st);
+  const size_t n = size_t(B) * D * depth;
+  k::cond_transpose_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->Ytmp, m->Y, B, D, depth);
+}
+
+// One per-step forward over the resident state.  sample: draw + unmask (decode); else write logits.
+// t_per_sample != nullptr -> forward API (arbitrary step per sample); else the device step counter.
+cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, float* logits_out, bool sample,
+                     bool advance, cudaStream_t st, Profiler* prof, int* n_launch) {
+  const biom3_config& c = m->cfg;
+  const int D = c.dim, L = c.seq_len, H = c.heads, depth = c.depth, NL = c.local_heads, C = c.num_classes;
+  const int M = B * L;
+  const int JD = depth * D;
+  int launches = 0;
+  cudaError_t err = cudaSuccess;
+#define LAUNCH(cat, ...)                     \
+  do {                                       \
+    if (prof) prof->begin(cat);              \
+    __VA_ARGS__;                             \
+    if (prof) prof->end();                   \
+    ++launches;                              \
+    err = cudaGetLastError();                \
+    if (err != cudaSuccess) return err;      \
+  } while (0)
+
+  const int row_blocks = std::min((M + 7) / 8, m->num_sms * 8);
+  LAUNCH(C_OTHER, k::cond_build_kernel<<<dim3(std::max(1, JD / 4 / 256), B), 256, 0, st>>>(
+                      m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
+  LAUNCH(C_EMBED, k::embed_ln_kernel<<<row_blocks, 256, 0, st>>>(m->state, m->emb, m->ax0, m->ax1, m->cvec, JD,
+                                                                 m->ln1_g, m->ln1_b, m->u, m->a, M, L,
+                                                                 c.local_window, D));
+  const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
+  const float q_scale = 1.0f / sqrtf(float(attn::DH));
+  const int iw = m->bn_wide == 256 ? 1 : 0, in = m->bn_narrow == 256 ? 1 : 0;
+  for (int j = 0; j < depth; ++j) {
+    if (j > 0)
+      LAUNCH(C_LN, k::layernorm_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln1_g + size_t(j) * D,
+                                                                  m->ln1_b + size_t(j) * D, m->a, M, D));
+    gemm::Params p{};
+    p.L = L; p.H = H; p.Bsz = B;
+    // q, k, v projections (no bias) -> head-major bf16
+    p.M = M; p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv; p.bias = nullptr; p.cond = nullptr;
+    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR, 4>(m->bn_wide, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
+    if (NL > 0)
+      LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
+                          m->qkv, m->att, B, H, L, scale_log2e));
+    if (H - NL > 0)
+      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv, m->att, B, H, L, NL,
+                                                                                      q_scale));
+    // u += att . Wo^T + bo
+    p.N = D; p.K = D; p.b_row_offset = j * D; p.out = m->u; p.bias = m->bo + size_t(j) * D;
+    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(m->bn_narrow, m->tm_att, m->tm_wo[in], p, m->num_sms, st));
+    LAUNCH(C_LN, k::layernorm_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D,
+                                                                m->ln2_b + size_t(j) * D, m->a, M, D));
+    // hid = gelu(a . W1^T + b1)
+    p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid; p.bias = m->b1 + size_t(j) * 4 * D;
+    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16, 8>(m->bn_wide, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
+    // u += hid . W2^T + b2 (+ next layer's conditioning vector)
+    p.N = D; p.K = 4 * D; p.b_row_offset = j * D; p.out = m->u; p.bias = m->b2 + size_t(j) * D;
+    p.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
+    p.cond_stride = JD;
+    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(m->bn_narrow, m->tm_hid, m->tm_w2[in], p, m->num_sms, st));
+  }
+  k::HeadArgs ha{};
+  ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
+  ha.logits_out = logits_out; ha.state = sample ? m->state : nullptr; ha.inv_path = m->inv_path; ha.ctl = m->ctl;
+  ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
+  const int ntok = sample ? B * group : M;
+  const int head_blocks = std::min((ntok + 7) / 8, m->num_sms * 2);
+  LAUNCH(C_HEAD, k::head_kernel<<<head_blocks, 256, size_t(C) * D * sizeof(float), st>>>(ha));
+  if (advance) {
+    const int n = M;
+    const int blocks = std::min(std::max(1, n / (256 * 16)), m->num_sms);
+    LAUNCH(C_OTHER, k::advance_kernel<<<blocks, 256, 0, st>>>(m->ctl, m->state, n));
+  }
+#undef LAUNCH
+  if (n_launch) *n_launch = launches;
+  return cudaSuccess;
+}
+
+__global__ void set_ctl_kernel(k::DecodeCtl* ctl, int step, int start, const float* noise, uint8_t* traj,
+                               unsigned long long seed) {
+  ctl->step = step;
+  ctl->start = start;
+  ctl->done = 0;
+  ctl->pad = 0;
+  ctl->noise = noise;
+  ctl->traj = traj;
+  ctl->seed = seed;
+}
+
+int check_ready(biom3_model* m, int B) {
+  if (!m) return fail(BIOM3_ERR_INVALID, "null model");
+  if (!m->finalized) return fail(BIOM3_ERR_STATE, "weights not finalized");
+  if (B < 1 || B > m->max_batch)
+    return fail(BIOM3_ERR_INVALID, "batch " + std::to_string(B) + " outside [1, max_batch=" +
+                                       std::to_string(m->max_batch) + "]");
+  return BIOM3_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* biom3_last_error(void) { return g_err.c_str(); }
+
+int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model** out) {
+  if (!cfg || !out) return fail(BIOM3_ERR_INVALID, "null argument");
+  const biom3_config& c = *cfg;
+  if (c.reversible) return fail(BIOM3_ERR_INVALID, "transformer_reversible=true is not supported");
+  if (c.n_blocks != 1) return fail(BIOM3_ERR_INVALID, "transformer_blocks must be 1");
+  if (c.heads <= 0 || c.dim != c.heads * attn::DH)
+    return fail(BIOM3_ERR_INVALID, "transformer_dim / transformer_heads must be 32");
+  if (c.dim % 256 != 0 || c.dim > 1024) return fail(BIOM3_ERR_INVALID, "transformer_dim must be a multiple of 256, <= 1024");
+  if (c.local_window != attn::WIN) return fail(BIOM3_ERR_INVALID, "transformer_local_size must be 128");
+  if (c.seq_len <= 0 || c.seq_len % c.local_window != 0)
+    return fail(BIOM3_ERR_INVALID, "diffusion_steps must be a positive multiple of the local window");
+  if (c.local_heads < 0 || c.local_heads > c.heads) return fail(BIOM3_ERR_INVALID, "bad transformer_local_heads");
+  if (c.num_classes < 2 || c.num_classes > 32) return fail(BIOM3_ERR_INVALID, "num_classes must be in [2, 32]");
+  if (c.depth < 1 || c.text_emb_dim < 1 || max_batch < 1) return fail(BIOM3_ERR_INVALID, "bad depth/text_emb_dim/max_batch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
+  CU_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(BIOM3_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                    "; this library is built for sm_100a only");
+  biom3_model* m = new biom3_model();
+  m->cfg = c;
+  m->device = device;
+  m->max_batch = max_batch;
+  m->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("BIOM3_BN_WIDE")) m->bn_wide = atoi(e) == 128 ? 128 : 256;
+  if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
+  CU_OK(init_kernel_attributes());
+  CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+  *out = m;
+  return BIOM3_OK;
+}
+
+void biom3_destroy(biom3_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t numel) {
+  if (!m || !key || !data || numel <= 0) return fail(BIOM3_ERR_INVALID, "bad set_weight argument");
+  if (m->finalized) return fail(BIOM3_ERR_STATE, "weights already finalized");
+  m->host_w[key] = std::vector<float>(data, data + numel);
+  return BIOM3_OK;
+}
+
+int biom3_finalize_weights(biom3_model* m) {
+  if (!m) return fail(BIOM3_ERR_INVALID, "null model");
+  if (m->finalized) return fail(BIOM3_ERR_STATE, "weights already finalized");
+  CU_OK(cudaSetDevice(m->device));
+  const biom3_config& c = m->cfg;
+  const size_t D = c.dim, depth = c.depth, L = c.seq_len, C = c.num_classes, E = c.text_emb_dim, W = c.local_window;
+  const size_t Bm = m->max_batch, M = Bm * L;
+  int r;
+#define TRY(x) if ((r = (x)) != BIOM3_OK) return r
+  TRY(dev_alloc(m, &m->Wqkv, depth * 3 * D * D));
+  TRY(dev_alloc(m, &m->Wo, depth * D * D));
+  TRY(dev_alloc(m, &m->W1, depth * 4 * D * D));
+  TRY(dev_alloc(m, &m->W2, depth * 4 * D * D));
+  TRY(dev_alloc(m, &m->ln1_g, depth * D));
+  TRY(dev_alloc(m, &m->ln1_b, depth * D));
+  TRY(dev_alloc(m, &m->ln2_g, depth * D));
+  TRY(dev_alloc(m, &m->ln2_b, depth * D));
+  TRY(dev_alloc(m, &m->bo, depth * D));
+  TRY(dev_alloc(m, &m->b1, depth * 4 * D));
+  TRY(dev_alloc(m, &m->b2, depth * D));
+  TRY(dev_alloc(m, &m->emb, C * D));
+  TRY(dev_alloc(m, &m->ax0, (L / W) * D));
+  TRY(dev_alloc(m, &m->ax1, W * D));
+  TRY(dev_alloc(m, &m->norm_g, D));
+  TRY(dev_alloc(m, &m->norm_b, D));
+  TRY(dev_alloc(m, &m->w_out, C * D));
+  TRY(dev_alloc(m, &m->b_out, C));
+  TRY(dev_alloc(m, &m->Ttab, L * depth * D));
+  TRY(dev_alloc(m, &m->y_w0, 4 * D * E));
+  TRY(dev_alloc(m, &m->y_b0, 4 * D));
+  TRY(dev_alloc(m, &m->y_w2, D * depth * 4 * D));
+  TRY(dev_alloc(m, &m->y_b2, D * depth));
+
+  const std::string T = "transformer.";
+  TRY(upload_f32(m, T + "x_emb_NN.weight", C * D, m->emb));
+  TRY(upload_f32(m, T + "axial_pos_emb.weights_0", (L / W) * D, m->ax0));
+  TRY(upload_f32(m, T + "axial_pos_emb.weights_1", W * D, m->ax1));
+  TRY(upload_f32(m, T + "norm.weight", D, m->norm_g));
+  TRY(upload_f32(m, T + "norm.bias", D, m->norm_b));
+  TRY(upload_f32(m, T + "out.weight", C * D, m->w_out));
+  TRY(upload_f32(m, T + "out.bias", C, m->b_out));
+  TRY(upload_f32(m, T + "y_mlp.0.weight", 4 * D * E, m->y_w0));
+  TRY(upload_f32(m, T + "y_mlp.0.bias", 4 * D, m->y_b0));
+  TRY(upload_f32(m, T + "y_mlp.2.weight", D * depth * 4 * D, m->y_w2));
+  TRY(upload_f32(m, T + "y_mlp.2.bias", D * depth, m->y_b2));
+  for (size_t j = 0; j < depth; ++j) {
+    const std::string P = T + "transformer_blocks.0." + std::to_string(j) + ".layers.layers.0.";
+    TRY(upload_f32(m, P + "0.norm.weight", D, m->ln1_g + j * D));
+    TRY(upload_f32(m, P + "0.norm.bias", D, m->ln1_b + j * D));
+    TRY(upload_bf16(m, P + "0.fn.to_q.weight", D * D, m->Wqkv + (j * 3 + 0) * D * D));
+    TRY(upload_bf16(m, P + "0.fn.to_k.weight", D * D, m->Wqkv + (j * 3 + 1) * D * D));
+    TRY(upload_bf16(m, P + "0.fn.to_v.weight", D * D, m->Wqkv + (j * 3 + 2) * D * D));
+    TRY(upload_bf16(m, P + "0.fn.to_out.weight", D * D, m->Wo + j * D * D));
+    TRY(upload_f32(m, P + "0.fn.to_out.bias", D, m->bo + j * D));
+    TRY(upload_f32(m, P + "1.norm.weight", D, m->ln2_g + j * D));
+    TRY(upload_f32(m, P + "1.norm.bias", D, m->ln2_b + j * D));
+    TRY(upload_bf16(m, P + "1.fn.fn.w1.weight", 4 * D * D, m->W1 + j * 4 * D * D));
+    TRY(upload_f32(m, P + "1.fn.fn.w1.bias", 4 * D, m->b1 + j * 4 * D));
+    TRY(upload_bf16(m, P + "1.fn.fn.w2.weight", 4 * D * D, m->W2 + j * 4 * D * D));
+    TRY(upload_f32(m, P + "1.fn.fn.w2.bias", D, m->b2 + j * D));
+  }
+  // time-conditioning table: depends on the step only -> once per model load
+  {
+    float *te, *h1, *tt, *w0, *b0, *w2, *b2;
+    CU_OK(cudaMalloc(&te, L * D * sizeof(float)));
+    CU_OK(cudaMalloc(&h1, L * 4 * D * sizeof(float)));
+    CU_OK(cudaMalloc(&tt, L * D * depth * sizeof(float)));
+    CU_OK(cudaMalloc(&w0, 4 * D * D * sizeof(float)));
+    CU_OK(cudaMalloc(&b0, 4 * D * sizeof(float)));
+    CU_OK(cudaMalloc(&w2, D * depth * 4 * D * sizeof(float)));
+    CU_OK(cudaMalloc(&b2, D * depth * sizeof(float)));
+    TRY(upload_f32(m, T + "mlp.0.weight", 4 * D * D, w0));
+    TRY(upload_f32(m, T + "mlp.0.bias", 4 * D, b0));
+    TRY(upload_f32(m, T + "mlp.2.weight", D * depth * 4 * D, w2));
+    TRY(upload_f32(m, T + "mlp.2.bias", D * depth, b2));
+    k::time_embedding_kernel<<<unsigned((L * D + 255) / 256), 256>>>(te, int(L), int(D), float(L));
+    sgemm(te, w0, b0, h1, int(L), int(4 * D), int(D), 1, 0);
+    sgemm(h1, w2, b2, tt, int(L), int(D * depth), int(4 * D), 0, 0);
+    const size_t n = L * D * depth;
+    k::cond_transpose_kernel<<<unsigned((n + 255) / 256), 256>>>(tt, m->Ttab, int(L), int(D), int(depth));
+    CU_OK(cudaDeviceSynchronize());
+    cudaFree(te); cudaFree(h1); cudaFree(tt); cudaFree(w0); cudaFree(b0); cudaFree(w2); cudaFree(b2);
+  }
+  // expected number of keys: anything else in the map is an unexpected key (strict load)
+  const size_t expected = 15 + 13 * depth;
+  if (m->host_w.size() != expected)
+    return fail(BIOM3_ERR_STATE, "unexpected keys in state dict: got " + std::to_string(m->host_w.size()) +
+                                     " tensors, expected " + std::to_string(expected));
+  m->host_w.clear();
+
+  // workspace, sized for max_batch
+  TRY(dev_alloc(m, &m->u, M * D));
+  TRY(dev_alloc(m, &m->a, M * D));
+  TRY(dev_alloc(m, &m->qkv, M * 3 * D));
+  TRY(dev_alloc(m, &m->att, M * D));
+  TRY(dev_alloc(m, &m->hid, M * 4 * D));
+  TRY(dev_alloc(m, &m->Yh, Bm * 4 * D));
+  TRY(dev_alloc(m, &m->Ytmp, Bm * D * depth));
+  TRY(dev_alloc(m, &m->Y, Bm * D * depth));
+  TRY(dev_alloc(m, &m->cvec, Bm * D * depth));
+  TRY(dev_alloc(m, &m->state, M));
+  TRY(dev_alloc(m, &m->inv_path, M));
+  TRY(dev_alloc(m, &m->t_i32, Bm));
+  TRY(dev_alloc(m, &m->ctl, 1));
+  CU_OK(cudaMemset(m->ctl, 0, sizeof(k::DecodeCtl)));
+  CU_OK(cudaMemset(m->inv_path, 0, M * sizeof(int)));
+
+  TRY(make_tmap(&m->tm_a, m->a, M, D, 128));
+  TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
+  TRY(make_tmap(&m->tm_hid, m->hid, M, 4 * D, 128));
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t box = i ? 256 : 128;
+    TRY(make_tmap(&m->tm_wqkv[i], m->Wqkv, depth * 3 * D, D, box));
+    TRY(make_tmap(&m->tm_wo[i], m->Wo, depth * D, D, box));
+    TRY(make_tmap(&m->tm_w1[i], m->W1, depth * 4 * D, D, box));
+    TRY(make_tmap(&m->tm_w2[i], m->W2, depth * D, 4 * D, box));
+  }
+#undef TRY
+  m->finalized = true;
+  m->launches_per_step = 2 + int(depth) * 8 - 1 + 2 - (c.local_heads == 0 ? int(depth) : 0) -
+                         (c.heads == c.local_heads ? int(depth) : 0);
+  return BIOM3_OK;
+}
+
+int biom3_launches_per_step(const biom3_model* m) { return m ? m->launches_per_step : 0; }
+
+int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const float* y_c, int B, float* logits,
+                  void* stream) {
+  int r = check_ready(m, B);
+  if (r) return r;
+  if (!x || !t || !y_c || !logits) return fail(BIOM3_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int L = m->cfg.seq_len, n = B * L;
+  k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(x), m->state, n);
+  k::i64_to_i32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), m->t_i32, B);
+  run_y_mlp(m, y_c, B, st);
+  CU_OK(run_step(m, B, 0, m->t_i32, logits, false, false, st, nullptr, nullptr));
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const int64_t* state0, int start_step,
+                 int num_steps, int group, const float* noise, uint64_t seed, int64_t* tokens, uint8_t* traj, int B,
+                 void* stream) {
+  int r = check_ready(m, B);
+  if (r) return r;
+  if (!y_c || !path || !tokens) return fail(BIOM3_ERR_INVALID, "null argument");
+  const int L = m->cfg.seq_len;
+  if (group < 1 || B % group != 0) return fail(BIOM3_ERR_INVALID, "B must be a multiple of group");
+  if (start_step < 0 || num_steps < 0 || start_step + num_steps > L)
+    return fail(BIOM3_ERR_INVALID, "step range outside [0, diffusion_steps]");
+  CU_OK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n = B * L;
+  if (state0)
+    k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(state0), m->state, n);
+  else
+    CU_OK(cudaMemsetAsync(m->state, 0, n, st));
+  k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L);
+  run_y_mlp(m, y_c, B, st);
+  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed);
+  CU_OK(cudaGetLastError());
+
+  if (num_steps > 0) {
+    if (!m->graph_exec || m->graph_B != B || m->graph_group != group) {
+      if (m->graph_exec) {
+        cudaGraphExecDestroy(m->graph_exec);
+        m->graph_exec = nullptr;
+      }
+      cudaGraph_t graph;
+      CU_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e = run_step(m, B, group, nullptr, nullptr, true, true, m->cap_stream, nullptr, nullptr);
+      cudaError_t e2 = cudaStreamEndCapture(m->cap_stream, &graph);
+      if (e != cudaSuccess) return fail(BIOM3_ERR_CUDA, std::string("step capture: ") + cudaGetErrorString(e));
+      CU_OK(e2);
+      CU_OK(cudaGraphInstantiate(&m->graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      m->graph_B = B;
+      m->graph_group = group;
+    }
+    for (int s = 0; s < num_steps; ++s) CU_OK(cudaGraphLaunch(m->graph_exec, st));
+  }
+  k::u8_to_i64_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->state, reinterpret_cast<long long*>(tokens), n);
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out) {
+  int r = check_ready(m, B);
+  if (r) return r;
+  if (!out) return fail(BIOM3_ERR_INVALID, "null argument");
+  if (group < 1 || B % group != 0) return fail(BIOM3_ERR_INVALID, "B must be a multiple of group");
+  CU_OK(cudaSetDevice(m->device));
+  cudaStream_t st = m->cap_stream;
+  // a valid resident state is assumed (call after a decode); run one warm step then a timed one
+  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull);
+  CU_OK(run_step(m, B, group, nullptr, nullptr, true, true, st, nullptr, nullptr));
+  Profiler prof;
+  prof.st = st;
+  int launches = 0;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  cudaEventRecord(t0, st);
+  CU_OK(run_step(m, B, group, nullptr, nullptr, true, true, st, &prof, &launches));
+  cudaEventRecord(t1, st);
+  CU_OK(cudaStreamSynchronize(st));
+  float acc[C_COUNT] = {};
+  for (size_t i = 0; i < prof.cat.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    acc[prof.cat[i]] += ms;
+    cudaEventDestroy(prof.ev[2 * i]);
+    cudaEventDestroy(prof.ev[2 * i + 1]);
+  }
+  cudaEventElapsedTime(&out->total_ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  out->gemm_qkv_ms = acc[C_QKV]; out->gemm_out_ms = acc[C_OUT]; out->gemm_ff1_ms = acc[C_FF1];
+  out->gemm_ff2_ms = acc[C_FF2]; out->local_attn_ms = acc[C_LOCAL]; out->linear_attn_ms = acc[C_LINEAR];
+  out->layernorm_ms = acc[C_LN]; out->embed_ms = acc[C_EMBED]; out->head_ms = acc[C_HEAD];
+  out->other_ms = acc[C_OTHER];
+  out->launches = launches;
+  return BIOM3_OK;
+}
+
+int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t nbytes) {
+  if (!m || !name || !host_dst || !m->finalized) return fail(BIOM3_ERR_INVALID, "bad debug_copy argument");
+  const size_t D = m->cfg.dim, depth = m->cfg.depth, L = m->cfg.seq_len, M = size_t(m->max_batch) * L;
+  const std::string n(name);
+  const void* src = nullptr;
+  size_t sz = 0;
+  if (n == "u") { src = m->u; sz = M * D * 4; }
+  else if (n == "a") { src = m->a; sz = M * D * 2; }
+  else if (n == "qkv") { src = m->qkv; sz = M * 3 * D * 2; }
+  else if (n == "att") { src = m->att; sz = M * D * 2; }
+  else if (n == "hid") { src = m->hid; sz = M * 4 * D * 2; }
+  else if (n == "cvec") { src = m->cvec; sz = size_t(m->max_batch) * depth * D * 4; }
+  else if (n == "Y") { src = m->Y; sz = size_t(m->max_batch) * depth * D * 4; }
+  else if (n == "Ttab") { src = m->Ttab; sz = L * depth * D * 4; }
+  else if (n == "state") { src = m->state; sz = M; }
+  else return fail(BIOM3_ERR_INVALID, "unknown buffer " + n);
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(host_dst, src, std::min(sz, size_t(nbytes)), cudaMemcpyDeviceToHost));
+  return BIOM3_OK;
+}
+
+int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int B, int L, int C, void* stream) {
+  if (!logits || !noise || !tok || B < 1 || L < 1 || C < 2 || C > 32) return fail(BIOM3_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n = B * L;
+  k::sample_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(logits, noise, reinterpret_cast<long long*>(tok), B, L, C);
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B, int L, int group, int step,
+                 void* stream) {
+  if (!tok || !path || !state || B < 1 || L < 1 || group < 1 || B % group != 0 || step < 0 || step >= L)
+    return fail(BIOM3_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int* inv = nullptr;
+  CU_OK(cudaMallocAsync(&inv, size_t(B) * L * sizeof(int), st));
+  const int n = B * L;
+  k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), inv, B, L);
+  k::unmask_kernel<<<(B * group + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(tok), inv,
+                                                              reinterpret_cast<long long*>(state), B, L, group, step);
+  CU_OK(cudaFreeAsync(inv, st));
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
+                    int block_n, void* stream) {
+  if (!A || !W || !out) return fail(BIOM3_ERR_INVALID, "null argument");
+  if (block_n != 128 && block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 128 or 256");
+  if (M % 128 || N % block_n || K % 64) return fail(BIOM3_ERR_INVALID, "M%128, N%block_n, K%64 must be 0");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaDeviceProp prop;
+  int dev = 0;
+  CU_OK(cudaGetDevice(&dev));
+  CU_OK(cudaGetDeviceProperties(&prop, dev));
+  CUtensorMap ta, tb;
+  int r;
+  if ((r = make_tmap(&ta, A, M, K, 128))) return r;
+  if ((r = make_tmap(&tb, W, N, K, block_n))) return r;
+  gemm::Params p{};
+  p.M = M; p.N = N; p.K = K; p.b_row_offset = 0; p.out = out; p.bias = bias; p.cond = nullptr; p.cond_stride = 0;
+  p.L = M; p.H = 1; p.Bsz = 1;
+  const int sms = prop.multiProcessorCount;
+  CU_OK(init_kernel_attributes());
+  switch (epi) {
+    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16, 4>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_BIAS_GELU_BF16:
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      launch_gemm<gemm::EPI_BIAS_GELU_BF16, 8>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_BIAS_RESID_F32:
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32, 4>(block_n, ta, tb, p, sms, st); break;
+    default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
+  }
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""Host-side handle on the CUDA engine: owns a biom3_model*, feeds it weights by reference
+state-dict key, and exposes forward / decode on torch CUDA tensors (torch is plumbing here: device
+memory, streams)."""
+from __future__ import annotations
+
+import ctypes as C
+from argparse import Namespace
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+def config_from_args(args: Namespace) -> _lib.Config:
+    """stage3_config.json Namespace -> biom3_config (include/biom3_b200.h)."""
+    return _lib.Config(
+        seq_len=int(args.diffusion_steps), dim=int(args.transformer_dim), heads=int(args.transformer_heads),
+        depth=int(args.transformer_depth), n_blocks=int(args.transformer_blocks),
+        local_heads=int(args.transformer_local_heads), local_window=int(args.transformer_local_size),
+        num_classes=int(args.num_classes), text_emb_dim=int(args.text_emb_dim),
+        reversible=int(bool(getattr(args, 'transformer_reversible', False))))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, args: Namespace, state_dict: Dict[str, torch.Tensor], device: torch.device, max_batch: int):
+        if not torch.cuda.is_available():
+            raise RuntimeError('biom3_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.cfg = config_from_args(args)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError(f'biom3_b200 engine cannot run on device {device}')
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.max_batch = int(max_batch)
+        self.L = self.cfg.seq_len
+        self.C = self.cfg.num_classes
+        self.E = self.cfg.text_emb_dim
+        h = C.c_void_p()
+        _lib.check(self.lib.biom3_create(C.byref(self.cfg), self.dev_index, self.max_batch, C.byref(h)))
+        self.handle = h
+        try:
+            for key, t in state_dict.items():
+                t = t.detach().to('cpu', torch.float32).contiguous()
+                _lib.check(self.lib.biom3_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+            _lib.check(self.lib.biom3_finalize_weights(self.handle))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle:
+            self.lib.biom3_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches_per_step(self) -> int:
+        return int(self.lib.biom3_launches_per_step(self.handle))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y_c: torch.Tensor) -> torch.Tensor:
+        """x int [B, L], t int [B], y_c [B, E] -> logits fp32 [B, C, L] (reference layout)."""
+        B = x.shape[0]
+        assert x.shape == (B, self.L) and t.numel() == B and y_c.shape == (B, self.E)
+        x = x.to(self.device, torch.int64).contiguous()
+        t = t.reshape(-1).to(self.device, torch.int64).contiguous()
+        y_c = y_c.to(self.device, torch.float32).contiguous()
+        out = torch.empty(B, self.C, self.L, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.biom3_forward(self.handle, _ptr(x), _ptr(t), _ptr(y_c), B, _ptr(out), self._stream()))
+        return out
+
+    def decode(self, y_c: torch.Tensor, path: torch.Tensor, state0: Optional[torch.Tensor] = None,
+               start_step: int = 0, num_steps: Optional[int] = None, group: Optional[int] = None,
+               noise: Optional[torch.Tensor] = None, seed: int = 0, want_traj: bool = False):
+        """All tensors already on the device.  Returns (tokens int64 [B, L], traj uint8 [T, B, L] | None)."""
+        B = path.shape[0]
+        L = self.L
+        if num_steps is None:
+            num_steps = L - start_step
+        if group is None:
+            group = B
+        assert path.shape == (B, L) and path.dtype == torch.int64 and path.is_cuda and path.is_contiguous()
+        assert y_c.shape == (B, self.E) and y_c.dtype == torch.float32 and y_c.is_cuda and y_c.is_contiguous()
+        if state0 is not None:
+            assert state0.shape == (B, L) and state0.dtype == torch.int64 and state0.is_cuda and state0.is_contiguous()
+        if noise is not None:
+            assert noise.dtype == torch.float32 and noise.is_cuda and noise.is_contiguous()
+            assert noise.shape == (num_steps, B * L, self.C), (noise.shape, (num_steps, B * L, self.C))
+        tokens = torch.empty(B, L, device=self.device, dtype=torch.int64)
+        traj = torch.empty(num_steps, B, L, device=self.device, dtype=torch.uint8) if want_traj else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.biom3_decode(
+                self.handle, _ptr(y_c), _ptr(path), _ptr(state0), int(start_step), int(num_steps), int(group),
+                _ptr(noise), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(tokens), _ptr(traj), B, self._stream()))
+        return tokens, traj
+
+    def debug_buffer(self, name: str, shape, dtype: torch.dtype) -> torch.Tensor:
+        """Test hook: host copy of an internal buffer (leading part, sized by shape/dtype)."""
+        out = torch.empty(shape, dtype=dtype)
+        _lib.check(self.lib.biom3_debug_copy(self.handle, name.encode(), C.c_void_p(out.data_ptr()),
+                                             out.numel() * out.element_size()))
+        return out
+
+    def profile_step(self, B: int, group: int) -> Dict[str, float]:
+        prof = _lib.StepProfile()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.biom3_profile_step(self.handle, B, group, C.byref(prof)))
+        return {n: getattr(prof, n) for n, _ in _lib.StepProfile._fields_}
+
+
+def sample_all(logits: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """K11: token at every position.  logits fp32 [B, C, L], noise fp32 [B*L, C] (cuda) -> int64 [B, L]."""
+    lib = _lib.load()
+    B, Cc, L = logits.shape
+    assert logits.is_cuda and noise.is_cuda and noise.shape == (B * L, Cc)
+    logits = logits.contiguous().float()
+    noise = noise.contiguous().float()
+    tok = torch.empty(B, L, device=logits.device, dtype=torch.int64)
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.biom3_sample_all(_ptr(logits), _ptr(noise), _ptr(tok), B, L, Cc,
+                                        C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)))
+    return tok
+
+
+def unmask_(state: torch.Tensor, tok: torch.Tensor, path: torch.Tensor, step: int, group: Optional[int] = None) -> None:
+    """K12 in place: state[b', loc[b]] = tok[b', loc[b]] for all b', b of a group (int64 [B, L], cuda)."""
+    lib = _lib.load()
+    B, L = state.shape
+    group = B if group is None else group
+    assert state.is_cuda and state.dtype == torch.int64 and state.is_contiguous()
+    tok = tok.to(torch.int64).contiguous()
+    path = path.to(state.device, torch.int64).contiguous()
+    with torch.cuda.device(state.device):
+        _lib.check(lib.biom3_unmask(_ptr(tok), _ptr(path), _ptr(state), B, L, group, int(step),
+                                    C.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)))
+
+
+def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h)."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n,
+                                       C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
+    return out

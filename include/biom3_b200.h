@@ -1,0 +1,118 @@
+/* biom3_b200 — C ABI of the B200-native ProteoScribe sampling path.
+ *
+ * Plain C types only: a host binds this with ctypes / cffi / cgo-style FFI.  Every pointer marked
+ * "device" is a CUDA device pointer owned by the caller (e.g. torch.Tensor.data_ptr()); `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  All calls are asynchronous with
+ * respect to the host unless stated; return 0 on success, a negative code on error, message through
+ * biom3_last_error().  Nothing here falls back to the CPU: without a CUDA device every compute entry
+ * point fails.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef BIOM3_B200_H
+#define BIOM3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct biom3_model biom3_model;
+
+/* Subset of stage3_config.json the sampling path reads (stage3_config.json:16,21,28,37,43-45,56,58-60;
+ * read at Stage3_source/cond_diff_transformer_layer.py:94,202-213). */
+typedef struct biom3_config {
+  int32_t seq_len;        /* diffusion_steps == sequence length L (cond_diff_transformer_layer.py:212) */
+  int32_t dim;            /* transformer_dim */
+  int32_t heads;          /* transformer_heads (dim / heads must be 32) */
+  int32_t depth;          /* transformer_depth */
+  int32_t n_blocks;       /* transformer_blocks (must be 1) */
+  int32_t local_heads;    /* transformer_local_heads */
+  int32_t local_window;   /* transformer_local_size (must be 128) */
+  int32_t num_classes;    /* num_classes (<= 32) */
+  int32_t text_emb_dim;   /* text_emb_dim */
+  int32_t reversible;     /* transformer_reversible (must be 0) */
+} biom3_config;
+
+#define BIOM3_OK 0
+#define BIOM3_ERR_INVALID -1
+#define BIOM3_ERR_CUDA -2
+#define BIOM3_ERR_STATE -3
+
+/* Replaces get_model() (Stage3_source/cond_diff_transformer_layer.py:198-256): builds the graph for
+ * `cfg` on CUDA device `device`, with workspace for up to `max_batch` sequences.  Unsupported
+ * variants (reversible, n_blocks != 1, head dim != 32, window != 128, ...) are rejected here. */
+int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model** out);
+void biom3_destroy(biom3_model* m);
+const char* biom3_last_error(void);
+
+/* Replaces model.load_state_dict() (run_ProteoScribe_sample.py:51).  `key` is the reference
+ * state-dict key ("transformer.x_emb_NN.weight", ...); `data` is HOST fp32, `numel` elements.
+ * biom3_finalize_weights() is strict: it fails if a key is missing or has the wrong size.  It casts
+ * GEMM weights to bf16, stacks to_q/to_k/to_v, and precomputes the [L][depth][dim] time-conditioning
+ * table (cond_diff_transformer_layer.py:152-154 depends on the step only). */
+int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t numel);
+int biom3_finalize_weights(biom3_model* m);
+
+/* Replaces DiffTransformer.forward(x, t, y_c) (cond_diff_transformer_layer.py:149-176, 249-251).
+ * x: device int64 [B][L]; t: device int64 [B]; y_c: device fp32 [B][text_emb_dim];
+ * logits: device fp32 [B][num_classes][L] (the reference's permuted layout). */
+int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const float* y_c, int B, float* logits,
+                  void* stream);
+
+/* Replaces batch_generate_denoised_sampled() (Stage3_source/sampling_analysis.py:204-265): the whole
+ * step loop on the device, no host round trip per step.
+ *   y_c      device fp32 [B][text_emb_dim]
+ *   path     device int64 [B][L], a permutation per row (sampling_path)
+ *   state0   device int64 [B][L] start state, or NULL for all-mask (zeros)
+ *   start_step, num_steps: runs steps start_step .. start_step+num_steps-1 (<= L)
+ *   group    samples per reference batch: the reference's unmask write
+ *            (sampling_analysis.py:254-256) couples the samples of one call; B % group == 0
+ *   noise    device fp32 [num_steps][B*L][num_classes] Exp(1) draws (what OneHotCategorical.sample()
+ *            consumes, sampling_analysis.py:251), or NULL to draw on the device (Philox, `seed`)
+ *   tokens   device int64 [B][L] final state (out)
+ *   traj     device uint8 [num_steps][B][L] state after every step (out), or NULL */
+int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const int64_t* state0, int start_step,
+                 int num_steps, int group, const float* noise, uint64_t seed, int64_t* tokens, uint8_t* traj, int B,
+                 void* stream);
+
+/* Replaces `argmax(OneHotCategorical(probs=softmax(logits,1).permute(0,2,1)).sample(), -1)`
+ * (transformer_training_helper.py:444-449 + sampling_analysis.py:251) at every position.
+ * logits device fp32 [B][C][L]; noise device fp32 [B*L][C]; tok device int64 [B][L] (out). */
+int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int B, int L, int C, void* stream);
+
+/* Replaces the unmask write `state[:, 0, loc] = tok[:, loc]` (sampling_analysis.py:254-256).
+ * tok, state device int64 [B][L]; path device int64 [B][L]; step = current time index. */
+int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B, int L, int group, int step,
+                 void* stream);
+
+/* Unit-test hook for the tcgen05 GEMM: C = A . W^T with one of the fused epilogues.
+ * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
+ * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256. */
+int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
+                    int block_n, void* stream);
+
+/* Per-kernel device timings (ms) of the last biom3_profile_step() call; for bench.py's roofline. */
+typedef struct biom3_step_profile {
+  float total_ms;
+  float gemm_qkv_ms, gemm_out_ms, gemm_ff1_ms, gemm_ff2_ms;
+  float local_attn_ms, linear_attn_ms, layernorm_ms, embed_ms, head_ms, other_ms;
+  int32_t launches;
+} biom3_step_profile;
+/* Runs one decode step un-graphed with CUDA events around every launch (synchronous). */
+int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out);
+
+/* Test hook: synchronous device->host copy of an internal buffer after a forward/decode call.
+ * name: "u" fp32 [B*L][D] | "a" bf16 [B*L][D] | "qkv" bf16 [3][B][H][L][32] | "att" bf16 [B*L][D] |
+ * "hid" bf16 [B*L][4D] | "cvec" fp32 [B][depth][D] | "Y" fp32 [B][depth][D] | "Ttab" fp32 [L][depth][D] |
+ * "state" u8 [B*L].  Copies min(nbytes, buffer size). */
+int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t nbytes);
+
+/* Number of kernel launches one decode step issues (for bench.py's gpu_launches). */
+int biom3_launches_per_step(const biom3_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOM3_B200_H */
