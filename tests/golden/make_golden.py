@@ -77,6 +77,11 @@ CASES = {
                      transformer_local_heads=2, transformer_local_size=64, text_emb_dim=32), 1, 256, 0),
     'tiny_resume_b2': (dict(diffusion_steps=256, transformer_dim=64, transformer_heads=4, transformer_depth=2,
                             transformer_local_heads=2, transformer_local_size=64, text_emb_dim=32), 2, 56, 200),
+    # shapes the sm_100a kernels accept (head dim 32, window 128, dim % 256 == 0): compared on the GPU
+    'gpu_small_b3': (dict(diffusion_steps=256, transformer_dim=256, transformer_heads=8, transformer_depth=2,
+                          transformer_local_heads=4, transformer_local_size=128, text_emb_dim=64), 3, 256, 0),
+    'gpu_resume_b2': (dict(diffusion_steps=256, transformer_dim=256, transformer_heads=8, transformer_depth=2,
+                           transformer_local_heads=4, transformer_local_size=128, text_emb_dim=64), 2, 96, 160),
     'mid_b2': (dict(diffusion_steps=512, transformer_dim=128, transformer_heads=4, transformer_depth=3,
                     transformer_local_heads=2, transformer_local_size=128, text_emb_dim=512), 2, 512, 0),
 }
@@ -168,6 +173,12 @@ def main():
     for name in CASES:
         run_case(mod, samp, name)
     full_config_forward(mod)
+    # key schema of the real model at the stage3_config.json shape
+    import json
+    args = synthetic.stage3_args()
+    real = mod.get_model(args, (32, 32), 29)
+    with open(os.path.join(HERE, 'state_dict_keys.json'), 'w') as f:
+        json.dump({k: list(v.shape) for k, v in real.state_dict().items()}, f, indent=0)
     toks = np.arange(29)
     s = ani.convert_num_to_char(synthetic.TOKENS, toks)
     with open(os.path.join(HERE, 'convert_num_to_char.txt'), 'w') as f:

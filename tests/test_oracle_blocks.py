@@ -1,0 +1,79 @@
+"""Independent re-derivations of the un-vendored blocks the oracle restates:
+these do not pin the oracle to the missing wheels (nothing can, offline) but they do catch a
+restatement that contradicts its own specification."""
+import math
+
+import torch
+
+from oracle import upstream_blocks as ub
+from oracle import sampler as osamp
+
+
+def test_local_attention_equals_dense_band_mask():
+    torch.manual_seed(0)
+    b, h, n, e, W = 2, 3, 512, 32, 128
+    q, k, v = (torch.randn(b, h, n, e) for _ in range(3))
+    got = ub.LocalAttention(W)(q, k, v)
+    wi = torch.arange(n) // W
+    allowed = (wi[:, None] - wi[None, :]).abs() <= 1            # query window sees windows w-1..w+1
+    s = torch.einsum('bhie,bhje->bhij', q * e ** -0.5, k).masked_fill(~allowed, float('-inf'))
+    ref = torch.einsum('bhij,bhje->bhie', s.softmax(-1), v)
+    assert (got - ref).abs().max().item() < 2e-6
+
+
+def test_scale_order_switch_is_rounding_only():
+    torch.manual_seed(1)
+    q, k, v = (torch.randn(1, 2, 256, 32) for _ in range(3))
+    a = ub.LocalAttention(128, scale_q_first=True)(q, k, v)
+    b = ub.LocalAttention(128, scale_q_first=False)(q, k, v)
+    assert 0 < (a - b).abs().max().item() < 1e-5 or torch.equal(a, b)
+
+
+def test_linear_attention_definition():
+    torch.manual_seed(2)
+    q, k, v = (torch.randn(1, 1, 64, 32) for _ in range(3))
+    got = ub.linear_attention(q, k, v)[0, 0]
+    qs = torch.softmax(q[0, 0], -1) / math.sqrt(32)
+    ks = torch.softmax(k[0, 0], 0)
+    ref = qs @ (ks.t() @ v[0, 0])
+    assert (got - ref).abs().max().item() < 1e-6
+
+
+def test_axial_embedding_index_rule():
+    ax = ub.AxialPositionalEmbedding(16, (4, 8))
+    pos = ax(torch.zeros(1, 32, 16))[0]
+    for p in (0, 7, 8, 31):
+        assert torch.equal(pos[p], ax.weights_0[0, p // 8, 0] + ax.weights_1[0, 0, p % 8])
+
+
+def test_conditioning_layout_fact():
+    """t.reshape(B,1,D,1,depth)[..., 0, j] == t[:, j::depth]."""
+    t = torch.arange(2 * 6 * 4).float().reshape(2, 24)
+    r = t.reshape(2, 1, 6, 1, 4)
+    for j in range(4):
+        assert torch.equal(r[:, 0, :, 0, j], t[:, j::4])
+
+
+def test_unmask_is_a_bxb_write():
+    """Every sample is written at every sample's current location."""
+    B, L = 3, 8
+    path = torch.stack([torch.tensor([0, 1, 2, 3, 4, 5, 6, 7]), torch.tensor([1, 0, 3, 2, 5, 4, 7, 6]),
+                        torch.tensor([7, 6, 5, 4, 3, 2, 1, 0])])
+    state = torch.zeros(B, 1, L, dtype=torch.long)
+    tok = torch.arange(1, B * L + 1).reshape(B, L)
+    osamp.unmask(state, tok, path, torch.zeros(B, 1).long())
+    locs = {0, 1, 7}                                             # positions whose path value is 0
+    for b in range(B):
+        for l in range(L):
+            assert state[b, 0, l].item() == (tok[b, l].item() if l in locs else 0)
+
+
+def test_categorical_draw_equals_torch_multinomial():
+    """argmax(p_norm / q) with q drawn after the same seed == OneHotCategorical.sample()."""
+    torch.manual_seed(3)
+    logits = torch.randn(2, 29, 64)
+    torch.manual_seed(7)
+    ref = torch.argmax(torch.distributions.OneHotCategorical(
+        probs=torch.softmax(logits, 1).permute(0, 2, 1)).sample(), -1)
+    q = osamp.reference_noise_stream(7, 1, 2, 64, 29)[0]
+    assert torch.equal(osamp.sample_tokens(logits, q), ref)

@@ -12,7 +12,7 @@ from oracle.model import OracleModel
 from oracle import sampler as osamp
 from conftest import GOLDEN
 
-CASES = ['tiny_b3', 'tiny_b1', 'tiny_resume_b2', 'mid_b2']
+CASES = ['tiny_b3', 'tiny_b1', 'tiny_resume_b2', 'mid_b2', 'gpu_small_b3', 'gpu_resume_b2']
 
 
 def load_case(name):
