@@ -150,116 +150,235 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 
 // ------------------------------------------------------------------------------------------------
 // Linear attention (global heads): q <- softmax_d(q) * dh^-0.5 ; k <- softmax over the L tokens ;
-// ctx = k^T v (32 x 32) ; out = q ctx.  One CTA per (global head, sample), 256 threads, fp32 math.
+// ctx = k^T v (32 x 32) ; out = q ctx.  One CTA (4 warps) per (global head, sample).
+//   phase A  each warp streams a quarter of the sequence in 32-row chunks (cp.async, 2 stages) and
+//            accumulates exp(k - running max)^T v on the tensor cores (mma.sync, fp32 accumulators),
+//            rescaling when the running per-feature max moves (the softmax over tokens is shift invariant)
+//   merge    the four partial (max, denominator, ctx) sets are combined in shared memory -> ctx^T bf16
+//   phase B  each warp softmaxes its q rows in registers (quad shuffles) and multiplies by ctx
 // ------------------------------------------------------------------------------------------------
-constexpr int LIN_CHUNK = 128;
+constexpr int LIN_CH = 32;                         // rows per chunk
+constexpr int LIN_STAGE_BYTES = 2 * LIN_CH * 64;   // k + v (or q alone in phase B)
+constexpr int LIN_WARP_BYTES = 2 * LIN_STAGE_BYTES;
+constexpr int LIN_SMEM_BYTES = 4 * LIN_WARP_BYTES + 4 * DH * DH * 4 + 2 * 4 * DH * 4 + DH * 64;
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void lin_load_chunk(uint32_t dst, const __nv_bfloat16* src, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = lane + 32 * i;                   // 128 pieces of 16 B = 32 rows x 64 B
+    ptx::cp_async_16(dst + swz(p >> 2, p & 3), src + p * 8);
+  }
+}
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u);
+  return make_float2(__bfloat162float(b.x), __bfloat162float(b.y));
+}
+
+__global__ void __launch_bounds__(128)
 linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
                         int NL, float q_scale) {
   const int h = NL + blockIdx.x, b = blockIdx.y;
   const size_t head_stride = size_t(L) * DH;
   const size_t plane = size_t(B) * H * head_stride;
-  const __nv_bfloat16* qg = qkv + (size_t(b) * H + h) * head_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int rows_per_warp = L / 4;
+  const int nchunks = rows_per_warp / LIN_CH;
+  const __nv_bfloat16* qg = qkv + (size_t(b) * H + h) * head_stride + size_t(warp) * rows_per_warp * DH;
   const __nv_bfloat16* kg = qg + plane;
   const __nv_bfloat16* vg = kg + plane;
 
-  __shared__ float s_red[8][DH];
-  __shared__ float s_max[DH];
-  __shared__ float s_e[LIN_CHUNK][DH + 1];
-  __shared__ __align__(16) float s_v[LIN_CHUNK][DH];
-  __shared__ __align__(16) float s_ctx[DH][DH];
+  extern __shared__ __align__(128) uint8_t lin_smem[];
+  const uint32_t stage0 = ptx::smem_u32(lin_smem) + warp * LIN_WARP_BYTES;
+  float* pctx = reinterpret_cast<float*>(lin_smem + 4 * LIN_WARP_BYTES);     // [4][32][32]
+  float* pmax = pctx + 4 * DH * DH;                                           // [4][32]
+  float* pden = pmax + 4 * DH;                                                // [4][32]
+  uint8_t* ctxT = reinterpret_cast<uint8_t*>(pden + 4 * DH);                  // [32 e][32 d] bf16, swizzled rows
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // pass 1: per-feature max of k over the sequence (lane = feature d)
-  float mx = -INFINITY;
-  for (int n = warp; n < L; n += 8) mx = fmaxf(mx, __bfloat162float(kg[size_t(n) * DH + lane]));
-  s_red[warp][lane] = mx;
-  __syncthreads();
-  if (warp == 0) {
-    float m = s_red[0][lane];
+  // ---------------------------------------------------------------- phase A
+  float acc[2][4][4];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i][lane]);
-    s_max[lane] = m;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+  float mrun[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+  float den[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+
+  lin_load_chunk(stage0, kg, lane);
+  lin_load_chunk(stage0 + LIN_CH * 64, vg, lane);
+  ptx::cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
+    if (c + 1 < nchunks) {
+      const uint32_t nxt = stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES;
+      lin_load_chunk(nxt, kg + size_t(c + 1) * LIN_CH * DH, lane);
+      lin_load_chunk(nxt + LIN_CH * 64, vg + size_t(c + 1) * LIN_CH * DH, lane);
+      ptx::cp_async_commit();
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
+    }
+    __syncwarp();
+    const uint32_t sk = cur, sv = cur + LIN_CH * 64;
+    uint32_t kr[2][2][4];                          // [k-step][m-tile(d)][a0..a3], raw k as A^T fragments
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+        ptx::ldmatrix_x4_trans(sk + swz(ks * 16 + (lane & 7) + 8 * (lane >> 4), 2 * mt + ((lane >> 3) & 1)),
+                               kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3]);
+    // running per-feature max: this thread owns features 16*mt + g (a0, a2) and 16*mt + 8 + g (a1, a3)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float cm = -INFINITY;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const float2 x0 = bf2_to_f2(kr[ks][mt][hf]), x1 = bf2_to_f2(kr[ks][mt][hf + 2]);
+          cm = fmaxf(cm, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
+        }
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        const float mn = fmaxf(mrun[mt][hf], cm);
+        const float f = __expf(mrun[mt][hf] - mn);
+        mrun[mt][hf] = mn;
+        den[mt][hf] *= f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[mt][nt][2 * hf] *= f;
+          acc[mt][nt][2 * hf + 1] *= f;
+        }
+        float dsum = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            const float2 x = bf2_to_f2(kr[ks][mt][hf + 2 * q2]);
+            const float e0 = __expf(x.x - mn), e1 = __expf(x.y - mn);
+            dsum += e0 + e1;
+            kr[ks][mt][hf + 2 * q2] = ptx::pack_bf16x2(e0, e1);
+          }
+        den[mt][hf] += dsum;
+      }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int ep = 0; ep < 2; ++ep) {
+        uint32_t v0, v1, v2, v3;
+        ptx::ldmatrix_x4_trans(sv + swz(ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4)), v0, v1, v2, v3);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          ptx::mma_bf16_16816(acc[mt][2 * ep], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v0, v1);
+          ptx::mma_bf16_16816(acc[mt][2 * ep + 1], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v2, v3);
+        }
+      }
+    __syncwarp();
+  }
+  // partial results of this warp -> shared
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float dn = den[mt][hf];
+      dn += __shfl_xor_sync(0xffffffffu, dn, 1);
+      dn += __shfl_xor_sync(0xffffffffu, dn, 2);
+      const int d = 16 * mt + 8 * hf + g;
+      if (t == 0) {
+        pmax[warp * DH + d] = mrun[mt][hf];
+        pden[warp * DH + d] = dn;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* dst = pctx + (size_t(warp) * DH + d) * DH + 8 * nt + 2 * t;
+        dst[0] = acc[mt][nt][2 * hf];
+        dst[1] = acc[mt][nt][2 * hf + 1];
+      }
+    }
+  __syncthreads();
+  // ---------------------------------------------------------------- merge -> ctx^T (bf16), q scale folded in
+  for (int idx = threadIdx.x; idx < DH * DH; idx += 128) {
+    const int d = idx >> 5, e = idx & 31;
+    const float m0 = pmax[d], m1 = pmax[DH + d], m2 = pmax[2 * DH + d], m3 = pmax[3 * DH + d];
+    const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    const float f0 = __expf(m0 - mm), f1 = __expf(m1 - mm), f2 = __expf(m2 - mm), f3 = __expf(m3 - mm);
+    const float num = pctx[(0 * DH + d) * DH + e] * f0 + pctx[(1 * DH + d) * DH + e] * f1 +
+                      pctx[(2 * DH + d) * DH + e] * f2 + pctx[(3 * DH + d) * DH + e] * f3;
+    const float dn = pden[d] * f0 + pden[DH + d] * f1 + pden[2 * DH + d] * f2 + pden[3 * DH + d] * f3;
+    *reinterpret_cast<__nv_bfloat16*>(ctxT + swz(e, d >> 3) + (d & 7) * 2) = __float2bfloat16_rn(num / dn * q_scale);
   }
   __syncthreads();
-
-  // pass 2: ctx_un[d][e] = sum_n exp(k[n][d] - max[d]) v[n][e];  den[d] = sum_n exp(...)
-  const int d = tid >> 3, e0 = (tid & 7) * 4;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, den = 0.f;
-  for (int c0 = 0; c0 < L; c0 += LIN_CHUNK) {
-    for (int i = tid; i < LIN_CHUNK * DH; i += 256) {
-      const int r = i >> 5, c = i & 31;
-      s_e[r][c] = __expf(__bfloat162float(kg[size_t(c0 + r) * DH + c]) - s_max[c]);
-      s_v[r][c] = __bfloat162float(vg[size_t(c0 + r) * DH + c]);
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < LIN_CHUNK; ++r) {
-      const float ev = s_e[r][d];
-      const float4 vv = *reinterpret_cast<const float4*>(&s_v[r][e0]);
-      acc0 = fmaf(ev, vv.x, acc0);
-      acc1 = fmaf(ev, vv.y, acc1);
-      acc2 = fmaf(ev, vv.z, acc2);
-      acc3 = fmaf(ev, vv.w, acc3);
-      den += ev;
-    }
-    __syncthreads();
-  }
-  const float inv = q_scale / den;       // fold the q scale (dh^-0.5) into ctx
-  s_ctx[d][e0] = acc0 * inv;
-  s_ctx[d][e0 + 1] = acc1 * inv;
-  s_ctx[d][e0 + 2] = acc2 * inv;
-  s_ctx[d][e0 + 3] = acc3 * inv;
-  __syncthreads();
-
-  // pass 3: out[n][:] = softmax_d(q[n][:]) . ctx   (one token per thread per iteration)
+  // ---------------------------------------------------------------- phase B
+  uint32_t cb[4][4];                               // ctx as B fragments: [n-tile(e)][b0 ks0, b1 ks0, b0 ks1, b1 ks1]
+  const uint32_t sc = ptx::smem_u32(ctxT);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+    ptx::ldmatrix_x4(sc + swz(8 * nt + (lane & 7), lane >> 3), cb[nt][0], cb[nt][1], cb[nt][2], cb[nt][3]);
   const int D = H * DH;
-  for (int n = tid; n < L; n += 256) {
-    float qv[DH];
-    const uint4* q4 = reinterpret_cast<const uint4*>(qg + size_t(n) * DH);
+  lin_load_chunk(stage0, qg, lane);
+  ptx::cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
+    if (c + 1 < nchunks) {
+      lin_load_chunk(stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES, qg + size_t(c + 1) * LIN_CH * DH, lane);
+      ptx::cp_async_commit();
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
+    }
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 u = __ldg(q4 + i);
-      const uint32_t w32[4] = {u.x, u.y, u.z, u.w};
+    for (int mt = 0; mt < 2; ++mt) {               // 16 query rows each
+      uint32_t qa[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&w32[j]);
-        qv[i * 8 + j * 2] = __bfloat162float(bb.x);
-        qv[i * 8 + j * 2 + 1] = __bfloat162float(bb.y);
+      for (int ks = 0; ks < 2; ++ks)
+        ptx::ldmatrix_x4(cur + swz(mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)), qa[ks][0],
+                         qa[ks][1], qa[ks][2], qa[ks][3]);
+      // rows g (regs 0, 2) and g + 8 (regs 1, 3): softmax over the 32 features held by the quad
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float2 x[4];
+        x[0] = bf2_to_f2(qa[0][hf]); x[1] = bf2_to_f2(qa[0][hf + 2]);
+        x[2] = bf2_to_f2(qa[1][hf]); x[3] = bf2_to_f2(qa[1][hf + 2]);
+        float mx = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)),
+                         fmaxf(fmaxf(x[2].x, x[2].y), fmaxf(x[3].x, x[3].y)));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[i].x = __expf(x[i].x - mx);
+          x[i].y = __expf(x[i].y - mx);
+          s += x[i].x + x[i].y;
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float inv = 1.f / s;
+        qa[0][hf] = ptx::pack_bf16x2(x[0].x * inv, x[0].y * inv);
+        qa[0][hf + 2] = ptx::pack_bf16x2(x[1].x * inv, x[1].y * inv);
+        qa[1][hf] = ptx::pack_bf16x2(x[2].x * inv, x[2].y * inv);
+        qa[1][hf + 2] = ptx::pack_bf16x2(x[3].x * inv, x[3].y * inv);
+      }
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+        ptx::mma_bf16_16816(o[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], cb[nt][0], cb[nt][1]);
+        ptx::mma_bf16_16816(o[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], cb[nt][2], cb[nt][3]);
+      }
+      const size_t row0 = size_t(b) * L + size_t(warp) * rows_per_warp + size_t(c) * LIN_CH + mt * 16 + g;
+      __nv_bfloat16* o0 = out + row0 * D + h * DH + 2 * t;
+      __nv_bfloat16* o1 = o0 + size_t(8) * D;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<uint32_t*>(o0 + nt * 8) = ptx::pack_bf16x2(o[nt][0], o[nt][1]);
+        *reinterpret_cast<uint32_t*>(o1 + nt * 8) = ptx::pack_bf16x2(o[nt][2], o[nt][3]);
       }
     }
-    float qm = qv[0];
-#pragma unroll
-    for (int i = 1; i < DH; ++i) qm = fmaxf(qm, qv[i]);
-    float qs = 0.f;
-#pragma unroll
-    for (int i = 0; i < DH; ++i) {
-      qv[i] = __expf(qv[i] - qm);
-      qs += qv[i];
-    }
-    const float qinv = 1.f / qs;
-    float ov[DH];
-#pragma unroll
-    for (int e = 0; e < DH; ++e) ov[e] = 0.f;
-#pragma unroll
-    for (int dd = 0; dd < DH; ++dd) {
-      const float pq = qv[dd] * qinv;
-#pragma unroll
-      for (int e = 0; e < DH; e += 4) {
-        const float4 cv = *reinterpret_cast<const float4*>(&s_ctx[dd][e]);
-        ov[e] = fmaf(pq, cv.x, ov[e]);
-        ov[e + 1] = fmaf(pq, cv.y, ov[e + 1]);
-        ov[e + 2] = fmaf(pq, cv.z, ov[e + 2]);
-        ov[e + 3] = fmaf(pq, cv.w, ov[e + 3]);
-      }
-    }
-    uint4* o4 = reinterpret_cast<uint4*>(out + (size_t(b) * L + n) * D + h * DH);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o4[i] = make_uint4(ptx::pack_bf16x2(ov[8 * i], ov[8 * i + 1]), ptx::pack_bf16x2(ov[8 * i + 2], ov[8 * i + 3]),
-                         ptx::pack_bf16x2(ov[8 * i + 4], ov[8 * i + 5]), ptx::pack_bf16x2(ov[8 * i + 6], ov[8 * i + 7]));
+    __syncwarp();
   }
 }
 

@@ -2,12 +2,17 @@
 //
 //   warp 0        TMA producer: cp.async.bulk.tensor (128B swizzle) into a STAGES-deep smem ring
 //   warp 1        tcgen05.mma issuer (one elected thread), fp32 accumulators in TMEM, double buffered
-//   warps 2..     epilogue: tcgen05.ld TMEM -> registers -> fused bias / GELU / residual -> global
+//   warps 2..9    epilogue: tcgen05.ld TMEM -> registers (thread = row) -> fused math -> per-warp smem
+//                 transpose (XOR swizzled, conflict free) -> fully coalesced global loads / stores
 //
 // Tiles are 128 x BN x 64; one CTA per SM walks tiles n-fastest so the A tile is re-read from L2.
-// The reference runs these contractions as separate cuBLAS calls plus element-wise kernels
-// (to_q/to_k/to_v, to_out, w1 + GELU, w2 in linear-attention-transformer, called from
-// /root/reference/Stage3_source/cond_diff_transformer_layer.py:171).
+//
+// Fusions (the reference runs each as separate library / element-wise kernels; block structure from
+// linear-attention-transformer, called at /root/reference/Stage3_source/cond_diff_transformer_layer.py:171):
+//   * pre-norm LayerNorm is folded into the consumer GEMM:  LN(u) W^T = rstd (u (g*W)^T - mean * sum_k g_k W_nk)
+//     + sum_k b_k W_nk.  The producer epilogue emits a raw bf16 copy of the residual stream plus per-row
+//     partial (sum, sum of squares); the consumer epilogue applies mean / rstd per row.  No LayerNorm kernel.
+//   * bias, erf-GELU, fp32 residual update and the next layer's additive conditioning vector.
 #pragma once
 #include "ptx.cuh"
 
@@ -16,11 +21,13 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int STG_BYTES = 4096;  // per epilogue warp: one 32 x 32 fp32 (or bf16) block
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
   EPI_QKV_HEADMAJOR = 1,   // C bf16 as [3][B][H][L][32]  (column n = which*D + h*32 + d)
-  EPI_BIAS_GELU_BF16 = 2,  // C bf16 row-major, gelu_erf(acc + bias[n])
+  EPI_BIAS_GELU_BF16 = 2,  // C bf16 row-major, gelu_erf(x + bias[n])
   EPI_BIAS_RESID_F32 = 3,  // R fp32 row-major [M, N]: R += acc + bias[n] (+ cond[b(m)][n]), in place
   EPI_STORE_F32 = 4,       // C fp32 row-major (unit tests)
 };
@@ -35,6 +42,14 @@ struct Params {
   int L;                   // tokens per sample (rows per batch entry)
   int H;                   // heads (EPI_QKV_HEADMAJOR)
   int Bsz;                 // batch (EPI_QKV_HEADMAJOR)
+  // consumer side of the folded LayerNorm (bf16-output epilogues): x = rstd*(acc - mean*ln_s[n]) + ln_t[n]
+  const float* ln_stats;   // [M][ln_parts][2] partial (sum, sumsq) over the K features, or nullptr
+  const float* ln_s;       // [N]
+  const float* ln_t;       // [N]
+  int ln_parts;
+  // producer side (EPI_BIAS_RESID_F32): raw bf16 copy of the updated rows + their partial statistics
+  __nv_bfloat16* out_bf16; // [M][N] or nullptr
+  float* stats_out;        // [M][(N/BN)*2][2] or nullptr
 };
 
 template <int BN, int STAGES>
@@ -42,19 +57,37 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = STG_OFFSET + EPI_WARPS * STG_BYTES + 1024;   // + alignment slack
 };
 
+// erf-GELU, x * Phi(x), evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))): the three coefficients are a
+// least-squares fit to the exact erf form (max abs error 3.0e-5 on [-8, 8], below the bf16 rounding of the
+// stored result); one MUFU.TANH + 6 FP32 ops instead of erff()'s ~30, so the FF1 epilogue keeps up with the MMAs.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);      // beyond +-8 the tanh argument saturates anyway
+  const float x2 = xc * xc;
+  const float poly = fmaf(fmaf(-3.58732362e-4f, x2, 3.70503451e-2f), x2, 7.97458471e-1f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(xc * poly));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
 }
 
-template <int BN, int STAGES, int EPI, int EPI_WARPS>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
-  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
   using SL = SmemLayout<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulator stages
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
@@ -138,82 +171,162 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (8 warps)
     const uint32_t ew = warp - 2;
     const uint32_t quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
-    constexpr int COL_SPLIT = EPI_WARPS / 4;           // 1 or 2 warps share a lane quarter
-    const uint32_t col_half = (COL_SPLIT == 2) ? (ew >> 2) : 0;
-    constexpr int COLS_PER_WARP = BN / COL_SPLIT;
+    const uint32_t col_half = ew >> 2;                 // two warps share a lane quarter, half the columns each
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int NCH = COLS_PER_WARP / 32;
+    const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
-      ptx::mbar_wait(&acc_full[as], aphase);
-      ptx::tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const int bidx = row / p.L;
+      const int n_tile = tile % n_tiles;
+      const int rbase = m0 + quarter * 32;                 // first of this warp's 32 rows
+      const int nbase = n_tile * BN + col_half * COLS_PER_WARP;
+      const int bidx = rbase / p.L;                        // 32-row blocks never straddle samples (L % 128 == 0)
       const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
+
+      if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_STORE_F32) {
+        // fp32 path.  Read phase mapping: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte
+        // column group lane%8): every global access is 4 full 128-byte lines per warp instruction.
+        const int rr = lane >> 3, ch = lane & 7;
+        float rs[8], rq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
+        float* gbase = reinterpret_cast<float*>(p.out) + size_t(rbase + rr) * p.N + nbase + 4 * ch;
+        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row + c, r);
-        ptx::tmem_ld_wait();
-        const int n = n0 + col_half * COLS_PER_WARP + c;   // first of 32 consecutive output columns
-        if constexpr (EPI == EPI_STORE_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + size_t(row) * p.N + n);
+        for (int c = 0; c < NCH; ++c) {
+          float4 res[8];
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(gbase + size_t(4 * j) * p.N + c * 32);
+          }
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, r);
+          ptx::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-        } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + size_t(row) * p.N + n);
-          const float4* bias = reinterpret_cast<const float4*>(p.bias + n);
-          const float4* cond = p.cond ? reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + n)
-                                      : nullptr;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 o = dst[i];
-            const float4 b = __ldg(bias + i);
-            o.x += __uint_as_float(r[4 * i]) + b.x;
-            o.y += __uint_as_float(r[4 * i + 1]) + b.y;
-            o.z += __uint_as_float(r[4 * i + 2]) + b.z;
-            o.w += __uint_as_float(r[4 * i + 3]) + b.w;
-            if (cond) {
-              const float4 cv = __ldg(cond + i);
-              o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
+            st_shared_v4(stg + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          __syncwarp();
+          float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            add = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c * 32 + 4 * ch));
+            if (p.cond) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase + c * 32 + 4 * ch));
+              add.x += cv.x; add.y += cv.y; add.z += cv.z; add.w += cv.w;
             }
-            dst[i] = o;
           }
-        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + rr;
+            const uint4 a4 = ld_shared_v4(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+            float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
+            if constexpr (EPI == EPI_BIAS_RESID_F32) {
+              o.x += res[j].x + add.x; o.y += res[j].y + add.y; o.z += res[j].z + add.z; o.w += res[j].w + add.w;
+            }
+            *reinterpret_cast<float4*>(gbase + size_t(4 * j) * p.N + c * 32) = o;
+            if constexpr (EPI == EPI_BIAS_RESID_F32) {
+              if (p.out_bf16)
+                *reinterpret_cast<uint2*>(p.out_bf16 + size_t(rbase + row) * p.N + nbase + c * 32 + 4 * ch) =
+                    make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+              rs[j] += (o.x + o.y) + (o.z + o.w);
+              rq[j] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+            }
+          }
+          __syncwarp();
+        }
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+          if (p.stats_out) {
+            const int parts = n_tiles * 2, part = n_tile * 2 + col_half;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float s = rs[j], q = rq[j];
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+              }
+              if (ch == 0)
+                *reinterpret_cast<float2*>(p.stats_out + (size_t(rbase + 4 * j + rr) * parts + part) * 2) = make_float2(s, q);
+            }
+          }
+        }
+      } else {
+        // bf16 path: thread = row while the fused math runs, then a 32 x 64-byte block is transposed
+        // through smem so each warp store instruction writes 8 rows x 64 contiguous bytes.
+        float mean = 0.f, rstd = 1.f;
+        if (p.ln_stats) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + size_t(rbase + lane) * p.ln_parts;
+          float s = 0.f, q = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v = sp[i];
+            s += v.x;
+            q += v.y;
+          }
+          mean = s / float(p.K);
+          rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
+        }
+        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int n = nbase + c * 32;                    // first of 32 consecutive output columns
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, r);
+          ptx::tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          __nv_bfloat16* dst;
-          if constexpr (EPI == EPI_QKV_HEADMAJOR) {
-            const int D = p.N / 3;
-            const int which = n / D, h = (n % D) >> 5, l = row % p.L;
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                  ((((size_t(which) * p.Bsz + bidx) * p.H + h) * p.L + l) << 5);
-          } else {
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + size_t(row) * p.N + n;
-          }
-          if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-            const float4* bias = reinterpret_cast<const float4*>(p.bias + n);
+          if (p.ln_stats) {
+            const float nm = -mean * rstd;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(bias + i);
-              v[4 * i] = gelu_erf(v[4 * i] + b.x);
-              v[4 * i + 1] = gelu_erf(v[4 * i + 1] + b.y);
-              v[4 * i + 2] = gelu_erf(v[4 * i + 2] + b.z);
-              v[4 * i + 3] = gelu_erf(v[4 * i + 3] + b.w);
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + n) + i);
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.ln_t + n) + i);
+              v[4 * i] = fmaf(v[4 * i], rstd, fmaf(nm, s4.x, t4.x));
+              v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nm, s4.y, t4.y));
+              v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nm, s4.z, t4.z));
+              v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, fmaf(nm, s4.w, t4.w));
+            }
+          } else if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            d4[i] = make_uint4(ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                               ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            st_shared_v4(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]),
+                         ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
+                         ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          __syncwarp();
+          __nv_bfloat16* dst;
+          size_t row_stride;                               // elements between consecutive rows of the block
+          if constexpr (EPI == EPI_QKV_HEADMAJOR) {
+            const int D = p.N / 3;
+            const int which = n / D, h = (n % D) >> 5, l0 = rbase % p.L;
+            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((((size_t(which) * p.Bsz + bidx) * p.H + h) * p.L + l0) << 5);
+            row_stride = 32;
+          } else {
+            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + size_t(rbase) * p.N + n;
+            row_stride = p.N;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
+            const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
+            *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
+          }
+          __syncwarp();
         }
       }
       // accumulator stage drained: hand it back to the MMA warp
@@ -225,7 +338,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace gemm

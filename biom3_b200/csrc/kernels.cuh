@@ -77,12 +77,13 @@ __global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* _
   }
 }
 
-// u[b,l,:] = E[x] + (ax0[l / W] + ax1[l % W]) + cvec[b][0][:] ; a = LN(u) (first layer's pre-norm)
+// u[b,l,:] = E[x] + (ax0[l / W] + ax1[l % W]) + cvec[b][0][:].  Writes the fp32 residual stream, its raw
+// bf16 copy (A operand of the first QKV GEMM) and the row's (sum, sum of squares) for the folded LayerNorm
+// (slot 0 of `parts`; the other slots are zeroed).
 __global__ void __launch_bounds__(256)
-embed_ln_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
-                const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ u,
-                __nv_bfloat16* __restrict__ a, int rows, int L, int W, int D) {
+embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
+             const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride, float* __restrict__ u,
+             __nv_bfloat16* __restrict__ ub, float* __restrict__ stats, int parts, int rows, int L, int W, int D) {
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
@@ -92,7 +93,7 @@ embed_ln_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb
     const float* p0 = ax0 + size_t(l / W) * D;
     const float* p1 = ax1 + size_t(l % W) * D;
     const float* cv = cvec + size_t(b) * cond_stride;
-    float4 v[MAXV];
+    float s = 0.f, q = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
@@ -101,11 +102,17 @@ embed_ln_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb
         const float4 x1 = __ldg(reinterpret_cast<const float4*>(p0 + col));
         const float4 x2 = __ldg(reinterpret_cast<const float4*>(p1 + col));
         const float4 x3 = __ldg(reinterpret_cast<const float4*>(cv + col));
-        v[i] = make_float4((x0.x + (x1.x + x2.x)) + x3.x, (x0.y + (x1.y + x2.y)) + x3.y,
-                           (x0.z + (x1.z + x2.z)) + x3.z, (x0.w + (x1.w + x2.w)) + x3.w);
-        *reinterpret_cast<float4*>(u + size_t(row) * D + col) = v[i];
+        const float4 v = make_float4((x0.x + (x1.x + x2.x)) + x3.x, (x0.y + (x1.y + x2.y)) + x3.y,
+                                     (x0.z + (x1.z + x2.z)) + x3.z, (x0.w + (x1.w + x2.w)) + x3.w);
+        *reinterpret_cast<float4*>(u + size_t(row) * D + col) = v;
+        *reinterpret_cast<uint2*>(ub + size_t(row) * D + col) = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+        s += (v.x + v.y) + (v.z + v.w);
+        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       }
-    ln_row_store(v, nv, D, lane, gamma, beta, a + size_t(row) * D);
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane < parts)
+      *reinterpret_cast<float2*>(stats + (size_t(row) * parts + lane) * 2) = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
   }
 }
 

@@ -71,21 +71,21 @@ constexpr int STAGES_256 = 4;
 constexpr int STAGES_128 = 6;
 
 // launch only; the caller checks cudaGetLastError()
-template <int BN, int EPI, int EW>
+template <int BN, int EPI>
 void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
                    cudaStream_t st) {
   constexpr int STAGES = BN == 256 ? STAGES_256 : STAGES_128;
   const int smem = gemm::SmemLayout<BN, STAGES>::TOTAL;
   const int tiles = (p.M / gemm::BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, EW><<<grid, 64 + 32 * EW, smem, st>>>(ta, tb, p);
+  gemm::gemm_bf16_tcgen05<BN, STAGES, EPI><<<grid, 64 + 32 * gemm::EPI_WARPS, smem, st>>>(ta, tb, p);
 }
 
-template <int EPI, int EW>
+template <int EPI>
 void launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
                  cudaStream_t st) {
-  if (bn == 128) launch_gemm_t<128, EPI, EW>(ta, tb, p, num_sms, st);
-  else launch_gemm_t<256, EPI, EW>(ta, tb, p, num_sms, st);
+  if (bn == 128) launch_gemm_t<128, EPI>(ta, tb, p, num_sms, st);
+  else launch_gemm_t<256, EPI>(ta, tb, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -93,24 +93,27 @@ constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024
 // opt in to large dynamic shared memory for every kernel once per process, outside any stream capture
 cudaError_t init_kernel_attributes_impl() {
   cudaError_t e;
-#define SET_GEMM(BN, EPI, EW)                                                                                    \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, (BN == 256 ? STAGES_256 : STAGES_128), EPI, EW>,          \
+#define SET_GEMM(BN, EPI)                                                                                        \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, (BN == 256 ? STAGES_256 : STAGES_128), EPI>,          \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
                            gemm::SmemLayout<BN, (BN == 256 ? STAGES_256 : STAGES_128)>::TOTAL);                  \
   if (e != cudaSuccess) return e;
-  SET_GEMM(256, gemm::EPI_QKV_HEADMAJOR, 4)
-  SET_GEMM(128, gemm::EPI_QKV_HEADMAJOR, 4)
-  SET_GEMM(256, gemm::EPI_BIAS_RESID_F32, 4)
-  SET_GEMM(128, gemm::EPI_BIAS_RESID_F32, 4)
-  SET_GEMM(256, gemm::EPI_BIAS_GELU_BF16, 8)
-  SET_GEMM(128, gemm::EPI_BIAS_GELU_BF16, 8)
-  SET_GEMM(256, gemm::EPI_STORE_BF16, 4)
-  SET_GEMM(128, gemm::EPI_STORE_BF16, 4)
-  SET_GEMM(256, gemm::EPI_STORE_F32, 4)
-  SET_GEMM(128, gemm::EPI_STORE_F32, 4)
+  SET_GEMM(256, gemm::EPI_QKV_HEADMAJOR)
+  SET_GEMM(128, gemm::EPI_QKV_HEADMAJOR)
+  SET_GEMM(256, gemm::EPI_BIAS_RESID_F32)
+  SET_GEMM(128, gemm::EPI_BIAS_RESID_F32)
+  SET_GEMM(256, gemm::EPI_BIAS_GELU_BF16)
+  SET_GEMM(128, gemm::EPI_BIAS_GELU_BF16)
+  SET_GEMM(256, gemm::EPI_STORE_BF16)
+  SET_GEMM(128, gemm::EPI_STORE_BF16)
+  SET_GEMM(256, gemm::EPI_STORE_F32)
+  SET_GEMM(128, gemm::EPI_STORE_F32)
 #undef SET_GEMM
   e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LOCAL_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
   return e;
@@ -151,7 +154,9 @@ struct biom3_model {
   std::map<std::string, std::vector<float>> host_w;
   // weights
   bf16 *Wqkv = nullptr, *Wo = nullptr, *W1 = nullptr, *W2 = nullptr;
-  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float *ln_s_qkv = nullptr, *ln_t_qkv = nullptr, *ln_s_ff = nullptr, *ln_t_ff = nullptr;   // folded LayerNorms
+  float* stats = nullptr;                       // [M][ln_parts][2] row partial (sum, sumsq)
+  int ln_parts = 2;
   float *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *emb = nullptr, *ax0 = nullptr, *ax1 = nullptr, *norm_g = nullptr, *norm_b = nullptr;
   float *w_out = nullptr, *b_out = nullptr;
@@ -214,6 +219,36 @@ int upload_bf16(biom3_model* m, const std::string& key, size_t numel, bf16* dst)
   return BIOM3_OK;
 }
 
+// LayerNorm folded into the following linear layer (see gemm_tcgen05.cuh): uploads W' = gamma (.) W as bf16
+// [N][K], s[n] = sum_k bf16(W'[n][k]) and t[n] = sum_k beta[k] W[n][k] (+ bias[n] if bias_key is non-empty).
+int upload_folded(biom3_model* m, const std::string& g_key, const std::string& b_key, const std::string& w_key,
+                  const std::string& bias_key, size_t N, size_t K, bf16* w_dst, float* s_dst, float* t_dst) {
+  const std::vector<float>*g, *b, *w, *bias = nullptr;
+  int r;
+  if ((r = get_w(m, g_key, K, &g))) return r;
+  if ((r = get_w(m, b_key, K, &b))) return r;
+  if ((r = get_w(m, w_key, N * K, &w))) return r;
+  if (!bias_key.empty() && (r = get_w(m, bias_key, N, &bias))) return r;
+  std::vector<bf16> wf(N * K);
+  std::vector<float> s(N), t(N);
+  for (size_t n = 0; n < N; ++n) {
+    double sa = 0.0, ta = 0.0;
+    for (size_t kk = 0; kk < K; ++kk) {
+      const float wv = (*w)[n * K + kk];
+      const bf16 q = __float2bfloat16_rn((*g)[kk] * wv);
+      wf[n * K + kk] = q;
+      sa += double(__bfloat162float(q));
+      ta += double((*b)[kk]) * double(wv);
+    }
+    s[n] = float(sa);
+    t[n] = float(ta + (bias ? double((*bias)[n]) : 0.0));
+  }
+  CU_OK(cudaMemcpy(w_dst, wf.data(), N * K * sizeof(bf16), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(s_dst, s.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(t_dst, t.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+  return BIOM3_OK;
+}
+
 // C = act(A W^T + b), fp32 (conditioning MLPs only)
 void sgemm(const float* A, const float* W, const float* b, float* C, int M, int N, int K, int act, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
@@ -252,40 +287,40 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const int row_blocks = std::min((M + 7) / 8, m->num_sms * 8);
   LAUNCH(C_OTHER, k::cond_build_kernel<<<dim3(std::max(1, JD / 4 / 256), B), 256, 0, st>>>(
                       m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
-  LAUNCH(C_EMBED, k::embed_ln_kernel<<<row_blocks, 256, 0, st>>>(m->state, m->emb, m->ax0, m->ax1, m->cvec, JD,
-                                                                 m->ln1_g, m->ln1_b, m->u, m->a, M, L,
-                                                                 c.local_window, D));
+  LAUNCH(C_EMBED, k::embed_kernel<<<row_blocks, 256, 0, st>>>(m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a,
+                                                              m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const int iw = m->bn_wide == 256 ? 1 : 0, in = m->bn_narrow == 256 ? 1 : 0;
   for (int j = 0; j < depth; ++j) {
-    if (j > 0)
-      LAUNCH(C_LN, k::layernorm_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln1_g + size_t(j) * D,
-                                                                  m->ln1_b + size_t(j) * D, m->a, M, D));
     gemm::Params p{};
-    p.L = L; p.H = H; p.Bsz = B;
-    // q, k, v projections (no bias) -> head-major bf16
-    p.M = M; p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv; p.bias = nullptr; p.cond = nullptr;
-    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR, 4>(m->bn_wide, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
+    p.L = L; p.H = H; p.Bsz = B; p.M = M;
+    // q, k, v = LN1(u) Wqkv^T (no bias; LayerNorm folded) -> head-major bf16
+    p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
+    p.ln_stats = m->stats; p.ln_parts = m->ln_parts;
+    p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
+    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
     if (NL > 0)
       LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
                           m->qkv, m->att, B, H, L, scale_log2e));
     if (H - NL > 0)
-      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv, m->att, B, H, L, NL,
+      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(m->qkv, m->att, B, H, L, NL,
                                                                                       q_scale));
-    // u += att . Wo^T + bo
-    p.N = D; p.K = D; p.b_row_offset = j * D; p.out = m->u; p.bias = m->bo + size_t(j) * D;
-    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(m->bn_narrow, m->tm_att, m->tm_wo[in], p, m->num_sms, st));
-    LAUNCH(C_LN, k::layernorm_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D,
-                                                                m->ln2_b + size_t(j) * D, m->a, M, D));
-    // hid = gelu(a . W1^T + b1)
-    p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid; p.bias = m->b1 + size_t(j) * 4 * D;
-    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16, 8>(m->bn_wide, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
+    // u += att . Wo^T + bo ; also emits bf16(u) and its row statistics for the next folded LayerNorm
+    gemm::Params r{};
+    r.L = L; r.H = H; r.Bsz = B; r.M = M;
+    r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
+    r.out_bf16 = m->a; r.stats_out = m->stats;
+    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, m->tm_att, m->tm_wo[in], r, m->num_sms, st));
+    // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t)
+    p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
+    p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
+    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
     // u += hid . W2^T + b2 (+ next layer's conditioning vector)
-    p.N = D; p.K = 4 * D; p.b_row_offset = j * D; p.out = m->u; p.bias = m->b2 + size_t(j) * D;
-    p.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
-    p.cond_stride = JD;
-    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(m->bn_narrow, m->tm_hid, m->tm_w2[in], p, m->num_sms, st));
+    r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
+    r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
+    r.cond_stride = JD;
+    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, m->tm_hid, m->tm_w2[in], r, m->num_sms, st));
   }
   k::HeadArgs ha{};
   ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
@@ -396,10 +431,10 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(dev_alloc(m, &m->Wo, depth * D * D));
   TRY(dev_alloc(m, &m->W1, depth * 4 * D * D));
   TRY(dev_alloc(m, &m->W2, depth * 4 * D * D));
-  TRY(dev_alloc(m, &m->ln1_g, depth * D));
-  TRY(dev_alloc(m, &m->ln1_b, depth * D));
-  TRY(dev_alloc(m, &m->ln2_g, depth * D));
-  TRY(dev_alloc(m, &m->ln2_b, depth * D));
+  TRY(dev_alloc(m, &m->ln_s_qkv, depth * 3 * D));
+  TRY(dev_alloc(m, &m->ln_t_qkv, depth * 3 * D));
+  TRY(dev_alloc(m, &m->ln_s_ff, depth * 4 * D));
+  TRY(dev_alloc(m, &m->ln_t_ff, depth * 4 * D));
   TRY(dev_alloc(m, &m->bo, depth * D));
   TRY(dev_alloc(m, &m->b1, depth * 4 * D));
   TRY(dev_alloc(m, &m->b2, depth * D));
@@ -430,17 +465,17 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(upload_f32(m, T + "y_mlp.2.bias", D * depth, m->y_b2));
   for (size_t j = 0; j < depth; ++j) {
     const std::string P = T + "transformer_blocks.0." + std::to_string(j) + ".layers.layers.0.";
-    TRY(upload_f32(m, P + "0.norm.weight", D, m->ln1_g + j * D));
-    TRY(upload_f32(m, P + "0.norm.bias", D, m->ln1_b + j * D));
-    TRY(upload_bf16(m, P + "0.fn.to_q.weight", D * D, m->Wqkv + (j * 3 + 0) * D * D));
-    TRY(upload_bf16(m, P + "0.fn.to_k.weight", D * D, m->Wqkv + (j * 3 + 1) * D * D));
-    TRY(upload_bf16(m, P + "0.fn.to_v.weight", D * D, m->Wqkv + (j * 3 + 2) * D * D));
+    // Folded LayerNorms: W' = gamma (.) W in bf16, s_n = sum_k bf16(W'_nk), t_n = sum_k beta_k W_nk (+ bias)
+    TRY(upload_folded(m, P + "0.norm.weight", P + "0.norm.bias", P + "0.fn.to_q.weight", "", D, D,
+                      m->Wqkv + (j * 3 + 0) * D * D, m->ln_s_qkv + (j * 3 + 0) * D, m->ln_t_qkv + (j * 3 + 0) * D));
+    TRY(upload_folded(m, P + "0.norm.weight", P + "0.norm.bias", P + "0.fn.to_k.weight", "", D, D,
+                      m->Wqkv + (j * 3 + 1) * D * D, m->ln_s_qkv + (j * 3 + 1) * D, m->ln_t_qkv + (j * 3 + 1) * D));
+    TRY(upload_folded(m, P + "0.norm.weight", P + "0.norm.bias", P + "0.fn.to_v.weight", "", D, D,
+                      m->Wqkv + (j * 3 + 2) * D * D, m->ln_s_qkv + (j * 3 + 2) * D, m->ln_t_qkv + (j * 3 + 2) * D));
     TRY(upload_bf16(m, P + "0.fn.to_out.weight", D * D, m->Wo + j * D * D));
     TRY(upload_f32(m, P + "0.fn.to_out.bias", D, m->bo + j * D));
-    TRY(upload_f32(m, P + "1.norm.weight", D, m->ln2_g + j * D));
-    TRY(upload_f32(m, P + "1.norm.bias", D, m->ln2_b + j * D));
-    TRY(upload_bf16(m, P + "1.fn.fn.w1.weight", 4 * D * D, m->W1 + j * 4 * D * D));
-    TRY(upload_f32(m, P + "1.fn.fn.w1.bias", 4 * D, m->b1 + j * 4 * D));
+    TRY(upload_folded(m, P + "1.norm.weight", P + "1.norm.bias", P + "1.fn.fn.w1.weight", P + "1.fn.fn.w1.bias", 4 * D, D,
+                      m->W1 + j * 4 * D * D, m->ln_s_ff + j * 4 * D, m->ln_t_ff + j * 4 * D));
     TRY(upload_bf16(m, P + "1.fn.fn.w2.weight", 4 * D * D, m->W2 + j * 4 * D * D));
     TRY(upload_f32(m, P + "1.fn.fn.w2.bias", D, m->b2 + j * D));
   }
@@ -483,6 +518,8 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(dev_alloc(m, &m->Ytmp, Bm * D * depth));
   TRY(dev_alloc(m, &m->Y, Bm * D * depth));
   TRY(dev_alloc(m, &m->cvec, Bm * D * depth));
+  m->ln_parts = int(D) / m->bn_narrow * 2;
+  TRY(dev_alloc(m, &m->stats, M * size_t(m->ln_parts) * 2));
   TRY(dev_alloc(m, &m->state, M));
   TRY(dev_alloc(m, &m->inv_path, M));
   TRY(dev_alloc(m, &m->t_i32, Bm));
@@ -502,7 +539,7 @@ int biom3_finalize_weights(biom3_model* m) {
   }
 #undef TRY
   m->finalized = true;
-  m->launches_per_step = 2 + int(depth) * 8 - 1 + 2 - (c.local_heads == 0 ? int(depth) : 0) -
+  m->launches_per_step = 2 + int(depth) * 6 + 2 - (c.local_heads == 0 ? int(depth) : 0) -
                          (c.heads == c.local_heads ? int(depth) : 0);
   return BIOM3_OK;
 }
@@ -677,14 +714,14 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   const int sms = prop.multiProcessorCount;
   CU_OK(init_kernel_attributes());
   switch (epi) {
-    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16, 4>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, ta, tb, p, sms, st); break;
     case gemm::EPI_BIAS_GELU_BF16:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_GELU_BF16, 8>(block_n, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, ta, tb, p, sms, st); break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_RESID_F32, 4>(block_n, ta, tb, p, sms, st); break;
-    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32, 4>(block_n, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, ta, tb, p, sms, st); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -153,14 +153,14 @@ def stage_stages():
         print(f'   local window {w} rel_err:', rel_err(att[:, w * 128:(w + 1) * 128, :NL * 32], att_ref[:, w * 128:(w + 1) * 128, :NL * 32]))
     u1 = u0 + F.linear(att_ref, sd[p + '0.fn.to_out.weight'], sd[p + '0.fn.to_out.bias'])
     a2 = F.layer_norm(u1, (D,), sd[p + '1.norm.weight'], sd[p + '1.norm.bias'], 1e-5)
-    a2d = eng.debug_buffer('a', (B, L, D), torch.bfloat16).float()
-    print('LN2 out rel_err:', rel_err(a2d, a2))
     hid_ref = F.gelu(F.linear(a2, sd[p + '1.fn.fn.w1.weight'], sd[p + '1.fn.fn.w1.bias']))
     hid = eng.debug_buffer('hid', (B, L, 4 * D), torch.bfloat16).float()
     print('hid rel_err:', rel_err(hid, hid_ref))
     u2 = u1 + F.linear(hid_ref, sd[p + '1.fn.fn.w2.weight'], sd[p + '1.fn.fn.w2.bias'])
     ud = eng.debug_buffer('u', (B, L, D), torch.float32)
     print('u final rel_err:', rel_err(ud, u2))
+    ab = eng.debug_buffer('a', (B, L, D), torch.bfloat16).float()
+    print('bf16 copy of u rel_err:', rel_err(ab, u2))
     ref = orc(x, t, z)
     print('logits rel_err:', rel_err(logits, ref), ' max|ref|', ref.abs().max().item())
 
