@@ -60,7 +60,7 @@ def load() -> C.CDLL:
     lib.biom3_sample_all.restype = i32
     lib.biom3_unmask.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.biom3_unmask.restype = i32
-    lib.biom3_gemm_test.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.biom3_gemm_test.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.biom3_gemm_test.restype = i32
     lib.biom3_profile_step.argtypes = [vp, i32, i32, C.POINTER(StepProfile)]
     lib.biom3_profile_step.restype = i32

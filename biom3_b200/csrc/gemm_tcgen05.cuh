@@ -5,7 +5,13 @@
 //   warps 2..9    epilogue: tcgen05.ld TMEM -> registers (thread = row) -> fused math -> per-warp smem
 //                 transpose (XOR swizzled, conflict free) -> fully coalesced global loads / stores
 //
-// Tiles are 128 x BN x 64; one CTA per SM walks tiles n-fastest so the A tile is re-read from L2.
+// Two tilings of the same kernel:
+//   CG2 = false   one CTA per 128 x BN tile (cta_group::1).  Any M % 128 == 0.
+//   CG2 = true    a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile: each CTA stages its own 128 rows
+//                 of A and HALF of the weight tile, the leader issues 256-row MMAs that read both CTAs' shared
+//                 memory, each CTA keeps its 128 x BN accumulator in its own TMEM.  The mainloop of the 1-CTA
+//                 version is bound by the SM's L2->smem ingest (~43 B/clk measured, 48 KB per 512 MMA cycles);
+//                 the pair needs 32 KB per CTA for the same MMA work.
 //
 // Fusions (the reference runs each as separate library / element-wise kernels; block structure from
 // linear-attention-transformer, called at /root/reference/Stage3_source/cond_diff_transformer_layer.py:171):
@@ -18,11 +24,12 @@
 
 namespace gemm {
 
-constexpr int BM = 128;
+constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int STG_BYTES = 4096;  // per epilogue warp: one 32 x 32 fp32 (or bf16) block
+constexpr int CV_BYTES = 1024;   // per epilogue warp: the two per-column epilogue vectors of its 128 columns
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
@@ -50,15 +57,18 @@ struct Params {
   // producer side (EPI_BIAS_RESID_F32): raw bf16 copy of the updated rows + their partial statistics
   __nv_bfloat16* out_bf16; // [M][N] or nullptr
   float* stats_out;        // [M][(N/BN)*2][2] or nullptr
+  int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CG2>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = CG2 ? BN / 2 : BN;         // weight rows staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = STG_OFFSET + EPI_WARPS * STG_BYTES + 1024;   // + alignment slack
+  static constexpr int CV_OFFSET = STG_OFFSET + EPI_WARPS * STG_BYTES;
+  static constexpr int TOTAL = CV_OFFSET + EPI_WARPS * CV_BYTES + 1024;   // + alignment slack
 };
 
 // erf-GELU, x * Phi(x), evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))): the three coefficients are a
@@ -83,14 +93,15 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool CG2>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
-  using SL = SmemLayout<BN, STAGES>;
+  using SL = SmemLayout<BN, STAGES, CG2>;
   constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulator stages
-  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(CG2 ? 2 * BM : BM, BN);
+  constexpr int TILE_M = CG2 ? 2 * BM : BM;        // rows of one scheduled tile
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
@@ -100,8 +111,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
+  const uint32_t cta_rank = CG2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = CG2 ? int(blockIdx.x >> 1) : int(blockIdx.x);        // tile-walking unit (CTA or CTA pair)
+  const int n_workers = CG2 ? int(gridDim.x >> 1) : int(gridDim.x);
   const int n_tiles = p.N / BN;
-  const int num_tiles = (p.M / BM) * n_tiles;
+  const int num_tiles = (p.M / TILE_M) * n_tiles;
   const int k_blocks = p.K / BK;
 
   if (threadIdx.x == 0) {
@@ -113,42 +128,54 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], EPI_WARPS);
+      ptx::mbar_init(&acc_empty[s], CG2 ? 2 * EPI_WARPS : EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (CG2) {
+      ptx::tmem_alloc_cg2(&tmem_base_slot, TMEM_COLS);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(&tmem_base_slot, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM;
-        const int n0 = (tile % n_tiles) * BN + p.b_row_offset;
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
+        const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
+        const int n0 = (tile % n_tiles) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
-          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if constexpr (CG2) {
+            // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::STAGE_BYTES);
+            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only when paired)
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         ptx::mbar_wait(&acc_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
@@ -162,48 +189,95 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+            if constexpr (CG2) ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+            else ptx::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
           }
-          ptx::umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-          if (kb == k_blocks - 1) ptx::umma_commit(&acc_full[as]);
+          if constexpr (CG2) {
+            ptx::umma_commit_cg2(&empty_bar[stage], 3);     // frees the slot in BOTH CTAs
+            if (kb == k_blocks - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
+          } else {
+            ptx::umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+            if (kb == k_blocks - 1) ptx::umma_commit(&acc_full[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------ epilogue (8 warps, every CTA)
     const uint32_t ew = warp - 2;
     const uint32_t quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
     const uint32_t col_half = ew >> 2;                 // two warps share a lane quarter, half the columns each
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int NCH = COLS_PER_WARP / 32;
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
+    const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // [0,512): scale vector, [512,1024): shift vector
+    const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
+    auto tile_gbase = [&](int tile) -> float* {        // this lane's first fp32 element of a tile (row rr, group ch)
+      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
+      return reinterpret_cast<float*>(p.out) + size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN +
+             col_half * COLS_PER_WARP + 4 * ch;
+    };
+    float4 res[2][8];                                  // residual rows, double buffered one chunk ahead
+    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+      if (worker < num_tiles) {
+        const float* g0 = tile_gbase(worker);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[0][j] = *reinterpret_cast<const float4*>(g0 + size_t(4 * j) * p.N);
+      }
+    }
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BM;
+      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
       const int n_tile = tile % n_tiles;
       const int rbase = m0 + quarter * 32;                 // first of this warp's 32 rows
       const int nbase = n_tile * BN + col_half * COLS_PER_WARP;
       const int bidx = rbase / p.L;                        // 32-row blocks never straddle samples (L % 128 == 0)
       const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
 
-      if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_STORE_F32) {
-        // fp32 path.  Read phase mapping: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte
-        // column group lane%8): every global access is 4 full 128-byte lines per warp instruction.
-        const int rr = lane >> 3, ch = lane & 7;
+      if (p.debug_skip == 1 || p.debug_skip == 2) {
+        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::tc_fence_after();
+        if (p.debug_skip == 1) {
+          uint32_t r[32];
+          for (int c = 0; c < NCH; ++c) {
+            ptx::tmem_ld_32x32(t_row + c * 32, r);
+            ptx::tmem_ld_wait();
+          }
+          if (r[lane] == 0x7fc12345u) reinterpret_cast<float*>(p.out)[0] = 1.f;   // keep the loads alive
+        }
+      } else if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_STORE_F32) {
+        // fp32 path.  Read phase: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte column
+        // group lane%8): every global access is 4 full 128-byte lines per warp instruction.  The residual of
+        // the NEXT chunk (or of the next tile's first chunk) is always in flight while this one is processed.
         float rs[8], rq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
-        float* gbase = reinterpret_cast<float*>(p.out) + size_t(rbase + rr) * p.N + nbase + 4 * ch;
+        float* gbase = tile_gbase(tile);
+        const int next_tile = tile + n_workers;
+        const float* gnext = next_tile < num_tiles ? tile_gbase(next_tile) : nullptr;
+        float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            addv[c] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c * 32 + 4 * ch));
+            if (p.cond) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase + c * 32 + 4 * ch));
+              addv[c].x += cv.x; addv[c].y += cv.y; addv[c].z += cv.z; addv[c].w += cv.w;
+            }
+          }
+        }
         ptx::mbar_wait(&acc_full[as], aphase);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          float4 res[8];
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(gbase + size_t(4 * j) * p.N + c * 32);
+        for (int c = 0; c < NCH; ++c) {
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            const float* gn = (c + 1 < NCH) ? gbase + (c + 1) * 32 : gnext;
+            if (gn) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(gn + size_t(4 * j) * p.N);
+            }
           }
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
@@ -213,20 +287,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             st_shared_v4(stg + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           __syncwarp();
           float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            add = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c * 32 + 4 * ch));
-            if (p.cond) {
-              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase + c * 32 + 4 * ch));
-              add.x += cv.x; add.y += cv.y; add.z += cv.z; add.w += cv.w;
-            }
-          }
+          if constexpr (EPI == EPI_BIAS_RESID_F32) add = addv[c];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int row = 4 * j + rr;
             const uint4 a4 = ld_shared_v4(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
             if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              o.x += res[j].x + add.x; o.y += res[j].y + add.y; o.z += res[j].z + add.z; o.w += res[j].w + add.w;
+              const float4 rv = res[c & 1][j];
+              o.x += rv.x + add.x; o.y += rv.y + add.y; o.z += rv.z + add.z; o.w += rv.w + add.w;
             }
             *reinterpret_cast<float4*>(gbase + size_t(4 * j) * p.N + c * 32) = o;
             if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -258,50 +327,75 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       } else {
         // bf16 path: thread = row while the fused math runs, then a 32 x 64-byte block is transposed
         // through smem so each warp store instruction writes 8 rows x 64 contiguous bytes.
+        // Per-column epilogue vectors (x = acc * rstd + (-mean * rstd) * cs[n] + ct[n]; cs/ct = folded-LayerNorm
+        // s/t, or 0/bias) are staged once per tile in warp-private smem BEFORE the accumulator wait: with ~225 KB of
+        // the SM's 256 KB carved out as shared memory there is next to no L1 left for them.
+        constexpr bool kHasVec = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR);
         float mean = 0.f, rstd = 1.f;
-        if (p.ln_stats) {
-          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + size_t(rbase + lane) * p.ln_parts;
-          float s = 0.f, q = 0.f;
-          for (int i = 0; i < p.ln_parts; ++i) {
-            const float2 v = sp[i];
-            s += v.x;
-            q += v.y;
+        const bool use_vec = kHasVec && (p.ln_stats != nullptr || p.bias != nullptr);
+        if (use_vec) {
+          const float* tsrc = p.ln_stats ? p.ln_t : p.bias;
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(tsrc + nbase) + lane);
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.ln_stats) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + nbase) + lane);
+          __syncwarp();
+          st_shared_v4(cvs + lane * 16, __float_as_uint(s4.x), __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
+          st_shared_v4(cvs + 512 + lane * 16, __float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
+          if (p.ln_stats) {
+            const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + size_t(rbase + lane) * p.ln_parts;
+            float sm = 0.f, q = 0.f;
+            for (int i = 0; i < p.ln_parts; ++i) {
+              const float2 v = sp[i];
+              sm += v.x;
+              q += v.y;
+            }
+            mean = sm / float(p.K);
+            rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
           }
-          mean = s / float(p.K);
-          rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
+          __syncwarp();
+        }
+        const float nm = -mean * rstd;
+        // output addressing, hoisted out of the chunk loop (a warp's 128 columns never straddle q/k/v or a sample)
+        __nv_bfloat16* dst0;
+        size_t row_stride, chunk_stride;                   // elements between rows of a block / between chunks
+        if constexpr (EPI == EPI_QKV_HEADMAJOR) {
+          const int D = p.N / 3;
+          const int which = nbase / D, h0 = (nbase % D) >> 5, l0 = rbase % p.L;
+          dst0 = reinterpret_cast<__nv_bfloat16*>(p.out) + ((((size_t(which) * p.Bsz + bidx) * p.H + h0) * p.L + l0) << 5);
+          row_stride = 32;
+          chunk_stride = size_t(p.L) << 5;
+        } else {
+          dst0 = reinterpret_cast<__nv_bfloat16*>(p.out) + size_t(p.debug_skip == 6 ? (rbase & 1023) : rbase) * p.N + nbase;
+          row_stride = p.N;
+          chunk_stride = 32;
         }
         ptx::mbar_wait(&acc_full[as], aphase);
         ptx::tc_fence_after();
-#pragma unroll 1
+        uint32_t r[2][32];                                 // TMEM loads run one chunk ahead of the math
+        ptx::tmem_ld_32x32(t_row, r[0]);
+#pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int n = nbase + c * 32;                    // first of 32 consecutive output columns
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
+          if (c + 1 < NCH) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.ln_stats) {
-            const float nm = -mean * rstd;
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
+          if (use_vec) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + n) + i);
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.ln_t + n) + i);
-              v[4 * i] = fmaf(v[4 * i], rstd, fmaf(nm, s4.x, t4.x));
-              v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nm, s4.y, t4.y));
-              v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nm, s4.z, t4.z));
-              v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, fmaf(nm, s4.w, t4.w));
-            }
-          } else if (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              const uint4 su = ld_shared_v4(cvs + c * 128 + i * 16);
+              const uint4 tu = ld_shared_v4(cvs + 512 + c * 128 + i * 16);
+              v[4 * i] = fmaf(v[4 * i], rstd, fmaf(nm, __uint_as_float(su.x), __uint_as_float(tu.x)));
+              v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nm, __uint_as_float(su.y), __uint_as_float(tu.y)));
+              v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nm, __uint_as_float(su.z), __uint_as_float(tu.z)));
+              v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, fmaf(nm, __uint_as_float(su.w), __uint_as_float(tu.w)));
             }
           }
           if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+            if (p.debug_skip != 5) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -309,38 +403,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                          ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
                          ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           __syncwarp();
-          __nv_bfloat16* dst;
-          size_t row_stride;                               // elements between consecutive rows of the block
-          if constexpr (EPI == EPI_QKV_HEADMAJOR) {
-            const int D = p.N / 3;
-            const int which = n / D, h = (n % D) >> 5, l0 = rbase % p.L;
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((((size_t(which) * p.Bsz + bidx) * p.H + h) * p.L + l0) << 5);
-            row_stride = 32;
-          } else {
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + size_t(rbase) * p.N + n;
-            row_stride = p.N;
-          }
+          __nv_bfloat16* dst = dst0 + size_t(c) * chunk_stride;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
             const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
-            *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
+            if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
           }
           __syncwarp();
         }
       }
-      // accumulator stage drained: hand it back to the MMA warp
+      // accumulator stage drained: hand it back to the MMA warp (which lives in the leader CTA)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+      if (lane == 0) {
+        if (CG2 && !leader) ptx::mbar_arrive_remote(&acc_empty[as], 0);
+        else ptx::mbar_arrive(&acc_empty[as]);
+      }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG2) ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

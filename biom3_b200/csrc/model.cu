@@ -67,25 +67,45 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, u
   return BIOM3_OK;
 }
 
-constexpr int STAGES_256 = 4;
-constexpr int STAGES_128 = 6;
+template <int BN, bool CG2>
+constexpr int gemm_stages() { return CG2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : 5); }
 
 // launch only; the caller checks cudaGetLastError()
-template <int BN, int EPI>
+template <int BN, int EPI, bool CG2>
 void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
                    cudaStream_t st) {
-  constexpr int STAGES = BN == 256 ? STAGES_256 : STAGES_128;
-  const int smem = gemm::SmemLayout<BN, STAGES>::TOTAL;
-  const int tiles = (p.M / gemm::BM) * (p.N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm::gemm_bf16_tcgen05<BN, STAGES, EPI><<<grid, 64 + 32 * gemm::EPI_WARPS, smem, st>>>(ta, tb, p);
+  constexpr int STAGES = gemm_stages<BN, CG2>();
+  const int smem = gemm::SmemLayout<BN, STAGES, CG2>::TOTAL;
+  const int tiles = (p.M / (CG2 ? 256 : 128)) * (p.N / BN);
+  const int workers = CG2 ? num_sms / 2 : num_sms;
+  const int grid = (tiles < workers ? tiles : workers) * (CG2 ? 2 : 1);
+  if constexpr (CG2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(64 + 32 * gemm::EPI_WARPS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, p);
+  } else {
+    gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false><<<grid, 64 + 32 * gemm::EPI_WARPS, smem, st>>>(ta, tb, p);
+  }
 }
 
+// bn: 128 or 256 columns per tile.  pair: CTA-pair (cta_group::2) tiling, needs bn == 256 and M % 256 == 0;
+// `tb` must then be the 128-row-box weight map (each CTA stages half of the 256 weight rows).
 template <int EPI>
-void launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
+void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
                  cudaStream_t st) {
-  if (bn == 128) launch_gemm_t<128, EPI>(ta, tb, p, num_sms, st);
-  else launch_gemm_t<256, EPI>(ta, tb, p, num_sms, st);
+  if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, p, num_sms, st);
+  else if (pair) launch_gemm_t<256, EPI, true>(ta, tb, p, num_sms, st);
+  else launch_gemm_t<256, EPI, false>(ta, tb, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -93,21 +113,18 @@ constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024
 // opt in to large dynamic shared memory for every kernel once per process, outside any stream capture
 cudaError_t init_kernel_attributes_impl() {
   cudaError_t e;
-#define SET_GEMM(BN, EPI)                                                                                        \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, (BN == 256 ? STAGES_256 : STAGES_128), EPI>,          \
+#define SET_GEMM1(BN, EPI, CG2)                                                                                  \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, gemm_stages<BN, CG2>(), EPI, CG2>,                        \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<BN, (BN == 256 ? STAGES_256 : STAGES_128)>::TOTAL);                  \
+                           gemm::SmemLayout<BN, gemm_stages<BN, CG2>(), CG2>::TOTAL);                            \
   if (e != cudaSuccess) return e;
-  SET_GEMM(256, gemm::EPI_QKV_HEADMAJOR)
-  SET_GEMM(128, gemm::EPI_QKV_HEADMAJOR)
-  SET_GEMM(256, gemm::EPI_BIAS_RESID_F32)
-  SET_GEMM(128, gemm::EPI_BIAS_RESID_F32)
-  SET_GEMM(256, gemm::EPI_BIAS_GELU_BF16)
-  SET_GEMM(128, gemm::EPI_BIAS_GELU_BF16)
-  SET_GEMM(256, gemm::EPI_STORE_BF16)
-  SET_GEMM(128, gemm::EPI_STORE_BF16)
-  SET_GEMM(256, gemm::EPI_STORE_F32)
-  SET_GEMM(128, gemm::EPI_STORE_F32)
+#define SET_GEMM(EPI) SET_GEMM1(256, EPI, false) SET_GEMM1(128, EPI, false) SET_GEMM1(256, EPI, true)
+  SET_GEMM(gemm::EPI_QKV_HEADMAJOR)
+  SET_GEMM(gemm::EPI_BIAS_RESID_F32)
+  SET_GEMM(gemm::EPI_BIAS_GELU_BF16)
+  SET_GEMM(gemm::EPI_STORE_BF16)
+  SET_GEMM(gemm::EPI_STORE_F32)
+#undef SET_GEMM1
 #undef SET_GEMM
   e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LOCAL_SMEM_BYTES);
@@ -150,6 +167,7 @@ struct biom3_model {
   biom3_config cfg{};
   int device = 0, max_batch = 0, num_sms = 0;
   int bn_wide = 256, bn_narrow = 256;          // tile widths for the N = 3D/4D and N = D GEMMs
+  bool use_pair = true;                         // CTA-pair (cta_group::2) GEMM tiling when M % 256 == 0
   bool finalized = false;
   std::map<std::string, std::vector<float>> host_w;
   // weights
@@ -291,7 +309,8 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
                                                               m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
-  const int iw = m->bn_wide == 256 ? 1 : 0, in = m->bn_narrow == 256 ? 1 : 0;
+  const bool pw = m->use_pair && m->bn_wide == 256 && M % 256 == 0, pn = m->use_pair && m->bn_narrow == 256 && M % 256 == 0;
+  const int iw = (m->bn_wide == 256 && !pw) ? 1 : 0, in = (m->bn_narrow == 256 && !pn) ? 1 : 0;   // weight map: 256- or 128-row box
   for (int j = 0; j < depth; ++j) {
     gemm::Params p{};
     p.L = L; p.H = H; p.Bsz = B; p.M = M;
@@ -299,7 +318,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
     p.ln_stats = m->stats; p.ln_parts = m->ln_parts;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
-    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
+    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
     if (NL > 0)
       LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
                           m->qkv, m->att, B, H, L, scale_log2e));
@@ -311,16 +330,16 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
     r.out_bf16 = m->a; r.stats_out = m->stats;
-    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, m->tm_att, m->tm_wo[in], r, m->num_sms, st));
+    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], r, m->num_sms, st));
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t)
     p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
     p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
+    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
     // u += hid . W2^T + b2 (+ next layer's conditioning vector)
     r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
     r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
     r.cond_stride = JD;
-    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, m->tm_hid, m->tm_w2[in], r, m->num_sms, st));
+    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], r, m->num_sms, st));
   }
   k::HeadArgs ha{};
   ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
@@ -395,6 +414,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("BIOM3_BN_WIDE")) m->bn_wide = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
+  if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   *out = m;
@@ -695,33 +715,39 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
 }
 
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
-                    int block_n, void* stream) {
+                    int block_n, int pair, void* stream) {
   if (!A || !W || !out) return fail(BIOM3_ERR_INVALID, "null argument");
   if (block_n != 128 && block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 128 or 256");
   if (M % 128 || N % block_n || K % 64) return fail(BIOM3_ERR_INVALID, "M%128, N%block_n, K%64 must be 0");
+  if (pair && (block_n != 256 || M % 256)) return fail(BIOM3_ERR_INVALID, "pair tiling needs block_n == 256 and M % 256 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaDeviceProp prop;
-  int dev = 0;
-  CU_OK(cudaGetDevice(&dev));
-  CU_OK(cudaGetDeviceProperties(&prop, dev));
+  static cudaDeviceProp prop;
+  static bool have_prop = false;
+  if (!have_prop) {
+    int dev = 0;
+    CU_OK(cudaGetDevice(&dev));
+    CU_OK(cudaGetDeviceProperties(&prop, dev));
+    have_prop = true;
+  }
   CUtensorMap ta, tb;
   int r;
   if ((r = make_tmap(&ta, A, M, K, 128))) return r;
-  if ((r = make_tmap(&tb, W, N, K, block_n))) return r;
+  if ((r = make_tmap(&tb, W, N, K, pair ? block_n / 2 : block_n))) return r;
   gemm::Params p{};
   p.M = M; p.N = N; p.K = K; p.b_row_offset = 0; p.out = out; p.bias = bias; p.cond = nullptr; p.cond_stride = 0;
   p.L = M; p.H = 1; p.Bsz = 1;
   const int sms = prop.multiProcessorCount;
+  if (const char* e = getenv("BIOM3_EPI_SKIP")) p.debug_skip = atoi(e);
   CU_OK(init_kernel_attributes());
   switch (epi) {
-    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, p, sms, st); break;
     case gemm::EPI_BIAS_GELU_BF16:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, p, sms, st); break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, ta, tb, p, sms, st); break;
-    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, p, sms, st); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -149,7 +149,7 @@ def unmask_(state: torch.Tensor, tok: torch.Tensor, path: torch.Tensor, step: in
 
 
 def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, pair: bool = False) -> torch.Tensor:
     """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h)."""
     lib = _lib.load()
     M, K = A.shape
@@ -157,6 +157,6 @@ def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ep
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
     with torch.cuda.device(A.device):
-        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n,
+        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
     return out

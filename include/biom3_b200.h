@@ -89,9 +89,10 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
 
 /* Unit-test hook for the tcgen05 GEMM: C = A . W^T with one of the fused epilogues.
  * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
- * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256. */
+ * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256.  pair != 0: CTA-pair (cta_group::2)
+ * tiling, 256 x 256 tiles (needs block_n == 256, M % 256 == 0). */
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
-                    int block_n, void* stream);
+                    int block_n, int pair, void* stream);
 
 /* Per-kernel device timings (ms) of the last biom3_profile_step() call; for bench.py's roofline. */
 typedef struct biom3_step_profile {

@@ -36,20 +36,22 @@ def make(over, B, seed=11, perturb=True):
 
 
 # ---------------------------------------------------------------- GEMM (tcgen05) vs torch fp32
-@pytest.mark.parametrize('M,N,K,bn', [(128, 256, 64, 256), (128, 128, 64, 128), (384, 768, 256, 256),
-                                      (1024, 1536, 512, 256), (2048, 512, 2048, 128), (20096, 512, 512, 256)])
-def test_gemm_plain(M, N, K, bn):
+@pytest.mark.parametrize('M,N,K,bn,pair', [(128, 256, 64, 256, False), (128, 128, 64, 128, False), (384, 768, 256, 256, False),
+                                           (1024, 1536, 512, 256, False), (2048, 512, 2048, 128, False),
+                                           (20096, 512, 512, 256, False), (256, 256, 64, 256, True), (512, 768, 256, 256, True),
+                                           (1024, 1536, 512, 256, True), (37888, 512, 2048, 256, True)])
+def test_gemm_plain(M, N, K, bn, pair):
     from biom3_b200 import engine
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
     W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
     ref = A.float() @ W.float().t()
-    out = engine.gemm_test(A, W, None, 4, bn)
+    out = engine.gemm_test(A, W, None, 4, bn, pair=pair)
     assert rel_err(out, ref) < 1e-5          # same bf16 inputs, fp32 accumulation on both sides
 
 
-@pytest.mark.parametrize('bn', [128, 256])
-def test_gemm_epilogues(bn):
+@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
+def test_gemm_epilogues(bn, pair):
     from biom3_b200 import engine
     g = torch.Generator().manual_seed(7)
     M, N, K = 1024, 512, 512
@@ -58,10 +60,10 @@ def test_gemm_epilogues(bn):
     bias = torch.randn(N, generator=g).cuda()
     resid = torch.randn(M, N, generator=g).cuda()
     ref = A.float() @ W.float().t()
-    assert rel_err(engine.gemm_test(A, W, None, 0, bn).float(), ref) < 4e-3           # bf16 store
+    assert rel_err(engine.gemm_test(A, W, None, 0, bn, pair=pair).float(), ref) < 4e-3           # bf16 store
     gelu = torch.nn.functional.gelu(ref + bias)
-    assert rel_err(engine.gemm_test(A, W, bias, 2, bn).float(), gelu) < 4e-3          # bias + erf-GELU
-    out = engine.gemm_test(A, W, bias, 3, bn, out=resid.clone())
+    assert rel_err(engine.gemm_test(A, W, bias, 2, bn, pair=pair).float(), gelu) < 4e-3          # bias + erf-GELU
+    out = engine.gemm_test(A, W, bias, 3, bn, out=resid.clone(), pair=pair)
     assert rel_err(out, resid + ref + bias) < 1e-5                                     # in-place residual
 
 
