@@ -20,6 +20,13 @@ constexpr int WIN = 128;   // local window (fixed; checked at create time)
 // ------------------------------------------------------------------------------------------------
 constexpr int LOCAL_SMEM_BYTES = 7 * WIN * 64;   // Q (1 window) + K (3) + V (3), 64 B per row
 
+// two base-2 exponentials per MUFU op, bf16 in / bf16 out (packed)
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __global__ void __launch_bounds__(256)
@@ -73,7 +80,8 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float ol[4] = {0.f, 0.f, 0.f, 0.f};   // row sums, accumulated by the tensor core (every column holds the sum)
+  float m0 = -INFINITY, m1 = -INFINITY;
 
   for (int kc = 0; kc < nkeys; kc += 64) {
     float s[8][4];
@@ -99,29 +107,20 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     const float corr0 = exp2f((m0 - mn0) * scale_log2e), corr1 = exp2f((m1 - mn1) * scale_log2e);
     m0 = mn0; m1 = mn1;
     const float ms0 = mn0 * scale_log2e, ms1 = mn1 * scale_log2e;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(fmaf(s[nt][0], scale_log2e, -ms0));
-      s[nt][1] = exp2f(fmaf(s[nt][1], scale_log2e, -ms0));
-      s[nt][2] = exp2f(fmaf(s[nt][2], scale_log2e, -ms1));
-      s[nt][3] = exp2f(fmaf(s[nt][3], scale_log2e, -ms1));
-      rs0 += s[nt][0] + s[nt][1];
-      rs1 += s[nt][2] + s[nt][3];
-    }
-    l0 = l0 * corr0 + rs0;
-    l1 = l1 * corr1 + rs1;
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
       o[dt][0] *= corr0; o[dt][1] *= corr0;
       o[dt][2] *= corr1; o[dt][3] *= corr1;
     }
+    ol[0] *= corr0; ol[1] *= corr0; ol[2] *= corr1; ol[3] *= corr1;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {        // 16 keys per step
-      const uint32_t a0 = ptx::pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      const uint32_t a1 = ptx::pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      const uint32_t a2 = ptx::pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      const uint32_t a3 = ptx::pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      // P = 2^(s*c - m*c): the arguments are packed to bf16x2 first and exponentiated two per MUFU op
+      // (ex2.approx.bf16x2); the argument rounding error is <= 2^-9 |arg|, i.e. it only grows where P vanishes.
+      const uint32_t a0 = ex2_bf16x2(ptx::pack_bf16x2(fmaf(s[2 * kk][0], scale_log2e, -ms0), fmaf(s[2 * kk][1], scale_log2e, -ms0)));
+      const uint32_t a1 = ex2_bf16x2(ptx::pack_bf16x2(fmaf(s[2 * kk][2], scale_log2e, -ms1), fmaf(s[2 * kk][3], scale_log2e, -ms1)));
+      const uint32_t a2 = ex2_bf16x2(ptx::pack_bf16x2(fmaf(s[2 * kk + 1][0], scale_log2e, -ms0), fmaf(s[2 * kk + 1][1], scale_log2e, -ms0)));
+      const uint32_t a3 = ex2_bf16x2(ptx::pack_bf16x2(fmaf(s[2 * kk + 1][2], scale_log2e, -ms1), fmaf(s[2 * kk + 1][3], scale_log2e, -ms1)));
       const int krow = kc + kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
       for (int dp = 0; dp < 2; ++dp) {      // two d-chunks (16 features) per ldmatrix.x4
@@ -130,13 +129,11 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
         ptx::mma_bf16_16816(o[dp * 2], a0, a1, a2, a3, v0, v1);
         ptx::mma_bf16_16816(o[dp * 2 + 1], a0, a1, a2, a3, v2, v3);
       }
+      // row sums of the SAME bf16 P the numerator uses: one more MMA against an all-ones B fragment
+      ptx::mma_bf16_16816(ol, a0, a1, a2, a3, 0x3F803F80u, 0x3F803F80u);
     }
   }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const float inv0 = 1.f / ol[0], inv1 = 1.f / ol[2];
   const int D = H * DH;
   const size_t row0 = size_t(b) * L + size_t(w) * WIN + q0 + g;
   __nv_bfloat16* o0 = out + row0 * D + h * DH + 2 * t;

@@ -27,9 +27,13 @@ namespace gemm {
 constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
-constexpr int STG_BYTES = 4096;  // per epilogue warp: one 32 x 32 fp32 (or bf16) block
-constexpr int CV_BYTES = 1024;   // per epilogue warp: the two per-column epilogue vectors of its 128 columns
+constexpr int STG_TOTAL = 32768;  // epilogue staging: one 32 x 32 block per warp (fp32: 8 warps x 4 KB, bf16: 16 warps x 2 KB)
+constexpr int CV_TOTAL = 8192;    // the two per-column epilogue vectors of every warp's column range
+
+// Epilogue warps per CTA.  The fp32 residual epilogues use 8 (two per TMEM lane quarter, 128 columns each, 168
+// registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
+// smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
+__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 3 || epi == 4) ? 8 : 16; }
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
@@ -57,6 +61,7 @@ struct Params {
   // producer side (EPI_BIAS_RESID_F32): raw bf16 copy of the updated rows + their partial statistics
   __nv_bfloat16* out_bf16; // [M][N] or nullptr
   float* stats_out;        // [M][(N/BN)*2][2] or nullptr
+  int tma_store;           // bf16 epilogues: 1 = store 32 x 32 blocks with TMA (tmap_c, 64B swizzle) instead of st.global
   int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
 
@@ -67,8 +72,8 @@ struct SmemLayout {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int CV_OFFSET = STG_OFFSET + EPI_WARPS * STG_BYTES;
-  static constexpr int TOTAL = CV_OFFSET + EPI_WARPS * CV_BYTES + 1024;   // + alignment slack
+  static constexpr int CV_OFFSET = STG_OFFSET + STG_TOTAL;
+  static constexpr int TOTAL = CV_OFFSET + CV_TOTAL + 1024;   // + alignment slack
 };
 
 // erf-GELU, x * Phi(x), evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))): the three coefficients are a
@@ -94,11 +99,15 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 
 template <int BN, int STAGES, int EPI, bool CG2>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const Params p) {
+                  const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
   using SL = SmemLayout<BN, STAGES, CG2>;
+  constexpr int EPI_WARPS = epi_warps(EPI);
+  constexpr int STG_BYTES = STG_TOTAL / EPI_WARPS;
+  constexpr int CV_BYTES = CV_TOTAL / EPI_WARPS;
+  constexpr int CV_HALF = CV_BYTES / 2;             // bytes of one per-column vector of a warp
   constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulator stages
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(CG2 ? 2 * BM : BM, BN);
   constexpr int TILE_M = CG2 ? 2 * BM : BM;        // rows of one scheduled tile
@@ -207,11 +216,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ epilogue (8 warps, every CTA)
     const uint32_t ew = warp - 2;
     const uint32_t quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
-    const uint32_t col_half = ew >> 2;                 // two warps share a lane quarter, half the columns each
-    constexpr int COLS_PER_WARP = BN / 2;
+    const uint32_t col_half = ew >> 2;                 // 2 or 4 warps share a lane quarter and split the columns
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
     constexpr int NCH = COLS_PER_WARP / 32;
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
-    const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // [0,512): scale vector, [512,1024): shift vector
+    const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
     auto tile_gbase = [&](int tile) -> float* {        // this lane's first fp32 element of a tile (row rr, group ch)
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
@@ -335,12 +344,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const bool use_vec = kHasVec && (p.ln_stats != nullptr || p.bias != nullptr);
         if (use_vec) {
           const float* tsrc = p.ln_stats ? p.ln_t : p.bias;
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(tsrc + nbase) + lane);
+          const int vl = lane < COLS_PER_WARP / 4 ? lane : 0;      // lanes that carry a float4 of the vectors
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(tsrc + nbase) + vl);
           float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.ln_stats) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + nbase) + lane);
+          if (p.ln_stats) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + nbase) + vl);
           __syncwarp();
-          st_shared_v4(cvs + lane * 16, __float_as_uint(s4.x), __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
-          st_shared_v4(cvs + 512 + lane * 16, __float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
+          if (lane < COLS_PER_WARP / 4) {
+            st_shared_v4(cvs + lane * 16, __float_as_uint(s4.x), __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
+            st_shared_v4(cvs + CV_HALF + lane * 16, __float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
+          }
           if (p.ln_stats) {
             const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + size_t(rbase + lane) * p.ln_parts;
             float sm = 0.f, q = 0.f;
@@ -369,6 +381,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           row_stride = p.N;
           chunk_stride = 32;
         }
+        int tma_c0 = nbase, tma_c1 = rbase;                // TMA-store coordinates (column, row) of chunk 0
+        if constexpr (EPI == EPI_QKV_HEADMAJOR) {
+          const int D = p.N / 3;
+          tma_c0 = 0;
+          tma_c1 = (((nbase / D) * p.Bsz + bidx) * p.H + ((nbase % D) >> 5)) * p.L + rbase % p.L;
+        }
         ptx::mbar_wait(&acc_full[as], aphase);
         ptx::tc_fence_after();
         uint32_t r[2][32];                                 // TMEM loads run one chunk ahead of the math
@@ -384,7 +402,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 su = ld_shared_v4(cvs + c * 128 + i * 16);
-              const uint4 tu = ld_shared_v4(cvs + 512 + c * 128 + i * 16);
+              const uint4 tu = ld_shared_v4(cvs + CV_HALF + c * 128 + i * 16);
               v[4 * i] = fmaf(v[4 * i], rstd, fmaf(nm, __uint_as_float(su.x), __uint_as_float(tu.x)));
               v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nm, __uint_as_float(su.y), __uint_as_float(tu.y)));
               v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nm, __uint_as_float(su.z), __uint_as_float(tu.z)));
@@ -403,12 +421,28 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                          ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
                          ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           __syncwarp();
-          __nv_bfloat16* dst = dst0 + size_t(c) * chunk_stride;
+          if (p.tma_store) {
+            // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one lane stores
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
+                                tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
+              ptx::tma_store_commit();
+              ptx::tma_store_wait_read();               // staging reusable once the engine has read it
+            }
+          } else {
+            __nv_bfloat16* dst = dst0 + size_t(c) * chunk_stride;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
-            const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
-            if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
+            for (int j = 0; j < 4; ++j) {
+              const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
+              const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
+              __nv_bfloat16* gp = dst + size_t(row) * row_stride + pc * 8;
+              if (p.debug_skip == 7) asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              else if (p.debug_skip == 8) asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              else if (p.debug_skip == 9) asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              else if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(gp) = val;
+            }
           }
           __syncwarp();
         }

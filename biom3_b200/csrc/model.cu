@@ -53,6 +53,21 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 row-major [rows][cols] -> tiles of [box_rows][64 cols], 128-byte swizzle
+// bf16 row-major [rows][cols] -> store boxes of [32 rows][32 cols] (64 bytes), 64-byte swizzle
+int make_store_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(bf16)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled (store) failed: " + std::to_string(int(r)));
+  return BIOM3_OK;
+}
+
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -72,8 +87,8 @@ constexpr int gemm_stages() { return CG2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 
 
 // launch only; the caller checks cudaGetLastError()
 template <int BN, int EPI, bool CG2>
-void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
-                   cudaStream_t st) {
+void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p,
+                   int num_sms, cudaStream_t st) {
   constexpr int STAGES = gemm_stages<BN, CG2>();
   const int smem = gemm::SmemLayout<BN, STAGES, CG2>::TOTAL;
   const int tiles = (p.M / (CG2 ? 256 : 128)) * (p.N / BN);
@@ -82,7 +97,7 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Par
   if constexpr (CG2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(64 + 32 * gemm::EPI_WARPS);
+    cfg.blockDim = dim3(64 + 32 * gemm::epi_warps(EPI));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -92,20 +107,20 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Par
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, p);
+    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, p);
   } else {
-    gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false><<<grid, 64 + 32 * gemm::EPI_WARPS, smem, st>>>(ta, tb, p);
+    gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false><<<grid, 64 + 32 * gemm::epi_warps(EPI), smem, st>>>(ta, tb, tc, p);
   }
 }
 
 // bn: 128 or 256 columns per tile.  pair: CTA-pair (cta_group::2) tiling, needs bn == 256 and M % 256 == 0;
 // `tb` must then be the 128-row-box weight map (each CTA stages half of the 256 weight rows).
 template <int EPI>
-void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int num_sms,
-                 cudaStream_t st) {
-  if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, p, num_sms, st);
-  else if (pair) launch_gemm_t<256, EPI, true>(ta, tb, p, num_sms, st);
-  else launch_gemm_t<256, EPI, false>(ta, tb, p, num_sms, st);
+void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                 const gemm::Params& p, int num_sms, cudaStream_t st) {
+  if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, tc, p, num_sms, st);
+  else if (pair) launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
+  else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -188,6 +203,8 @@ struct biom3_model {
   int *inv_path = nullptr, *t_i32 = nullptr;
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
+  CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
+  bool tma_store = true;
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
   cudaStream_t cap_stream = nullptr;
@@ -316,9 +333,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.L = L; p.H = H; p.Bsz = B; p.M = M;
     // q, k, v = LN1(u) Wqkv^T (no bias; LayerNorm folded) -> head-major bf16
     p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
-    p.ln_stats = m->stats; p.ln_parts = m->ln_parts;
+    p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store ? 1 : 0;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
-    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], p, m->num_sms, st));
+    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
     if (NL > 0)
       LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
                           m->qkv, m->att, B, H, L, scale_log2e));
@@ -330,16 +347,16 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
     r.out_bf16 = m->a; r.stats_out = m->stats;
-    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], r, m->num_sms, st));
+    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t)
     p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
     p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], p, m->num_sms, st));
+    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
     // u += hid . W2^T + b2 (+ next layer's conditioning vector)
     r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
     r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
     r.cond_stride = JD;
-    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], r, m->num_sms, st));
+    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
   }
   k::HeadArgs ha{};
   ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
@@ -415,6 +432,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_WIDE")) m->bn_wide = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   *out = m;
@@ -550,6 +568,8 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(make_tmap(&m->tm_a, m->a, M, D, 128));
   TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
   TRY(make_tmap(&m->tm_hid, m->hid, M, 4 * D, 128));
+  TRY(make_store_tmap(&m->tm_st_qkv, m->qkv, M * 3 * D / 32, 32));
+  TRY(make_store_tmap(&m->tm_st_hid, m->hid, M, 4 * D));
   for (int i = 0; i < 2; ++i) {
     const uint32_t box = i ? 256 : 128;
     TRY(make_tmap(&m->tm_wqkv[i], m->Wqkv, depth * 3 * D, D, box));
@@ -738,16 +758,23 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   p.L = M; p.H = 1; p.Bsz = 1;
   const int sms = prop.multiProcessorCount;
   if (const char* e = getenv("BIOM3_EPI_SKIP")) p.debug_skip = atoi(e);
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_BIAS_GELU_BF16) {
+    if ((r = make_store_tmap(&tc, out, M, N))) return r;
+    p.tma_store = 1;
+    if (const char* e = getenv("BIOM3_TMA_STORE")) p.tma_store = atoi(e) != 0;
+  }
   CU_OK(init_kernel_attributes());
   switch (epi) {
-    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, p, sms, st); break;
+    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_BIAS_GELU_BF16:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, p, sms, st); break;
-    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());
