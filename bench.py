@@ -184,7 +184,9 @@ def run_cuda_arm(a):
 
     args = synthetic.stage3_args(batch_size_sample=BATCH, num_replicas=BATCH * world)
     args.device = str(dev)
-    model = mod.get_model(args, (32, 32), C)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the reference-compatible get_model prints; keep stdout = one JSON line
+        model = mod.get_model(args, (32, 32), C)
     model.load_state_dict(synthetic.random_state_dict(args, seed=0))
     model.eval().to(dev)
     eng = model.engine(BATCH)
