@@ -416,6 +416,7 @@ sgemm_bias_act_kernel(const float* __restrict__ A, const float* __restrict__ W, 
       if (m < M && n < N) {
         float v = acc[i][j] + bias[n];
         if (act == 1) v = v > 20.f ? v : log1pf(expf(v));
+        else if (act == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // exact erf-GELU
         Cm[size_t(m) * N + n] = v;
       }
     }

@@ -709,6 +709,43 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
   return BIOM3_OK;
 }
 
+int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
+                      const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream) {
+  if (!z_t || !w0_v || !b0 || !w1_v || !b1 || !z_c || P < 1 || in_dim < 1 || hid_dim < 1 || out_dim < 1)
+    return fail(BIOM3_ERR_INVALID, "bad facilitator argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // weight_norm(dim=None): W = g * V / ||V||_F with a scalar g -> fold into the weights once
+  auto fold = [](const float* v, float g, size_t n) {
+    double ss = 0.0;
+    for (size_t i = 0; i < n; ++i) ss += double(v[i]) * double(v[i]);
+    const float scale = float(double(g) / std::sqrt(ss));
+    std::vector<float> w(n);
+    for (size_t i = 0; i < n; ++i) w[i] = v[i] * scale;
+    return w;
+  };
+  const std::vector<float> w0 = fold(w0_v, w0_g, size_t(hid_dim) * in_dim);
+  const std::vector<float> w1 = fold(w1_v, w1_g, size_t(out_dim) * hid_dim);
+  float *d_w0, *d_b0, *d_w1, *d_b1, *d_h;
+  CU_OK(cudaMalloc(&d_w0, w0.size() * sizeof(float)));
+  CU_OK(cudaMalloc(&d_b0, hid_dim * sizeof(float)));
+  CU_OK(cudaMalloc(&d_w1, w1.size() * sizeof(float)));
+  CU_OK(cudaMalloc(&d_b1, out_dim * sizeof(float)));
+  CU_OK(cudaMalloc(&d_h, size_t(P) * hid_dim * sizeof(float)));
+  CU_OK(cudaMemcpyAsync(d_w0, w0.data(), w0.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(d_b0, b0, hid_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(d_w1, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(d_b1, b1, out_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  sgemm(z_t, d_w0, d_b0, d_h, P, hid_dim, in_dim, 2, st);       // Linear + exact erf-GELU (dropout p = 0 at eval)
+  sgemm(d_h, d_w1, d_b1, z_c, P, out_dim, hid_dim, 0, st);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaStreamSynchronize(st));                              // host vectors and temporaries die with this call
+  cudaFree(d_w0); cudaFree(d_b0); cudaFree(d_w1); cudaFree(d_b1); cudaFree(d_h);
+  return BIOM3_OK;
+}
+
 int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int B, int L, int C, void* stream) {
   if (!logits || !noise || !tok || B < 1 || L < 1 || C < 2 || C > 32) return fail(BIOM3_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

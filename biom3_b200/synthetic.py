@@ -134,3 +134,15 @@ def synthetic_noise(steps: int, batch: int, seq_len: int, num_classes: int,
     (/root/reference/Stage3_source/sampling_analysis.py:251)."""
     g = torch.Generator().manual_seed(seed)
     return torch.empty(steps, batch * seq_len, num_classes).exponential_(1.0, generator=g)
+
+
+def facilitator_state_dict(emb_dim: int = 512, hid_dim: int = 1024, seed: int = 31) -> Dict[str, torch.Tensor]:
+    """Seeded Facilitator weights with the reference keys (weight_norm(Linear, dim=None):
+    main.{0,3}.{bias, weight_g (scalar), weight_v}); weight_g is deliberately != ||weight_v|| so the fold matters."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, (o, i) in (('main.0', (hid_dim, emb_dim)), ('main.3', (emb_dim, hid_dim))):
+        sd[name + '.bias'] = torch.randn(o, generator=g) * 0.3
+        sd[name + '.weight_g'] = torch.randn((), generator=g) * 0.3 + 2.0
+        sd[name + '.weight_v'] = torch.randn(o, i, generator=g) * 0.05
+    return sd

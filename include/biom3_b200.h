@@ -110,6 +110,14 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
  * "state" u8 [B*L].  Copies min(nbytes, buffer size). */
 int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t nbytes);
 
+/* Replaces Facilitator.forward (Stage1_source/model.py:473-493; called at run_Facilitator_sample.py:79-83):
+ * z_c = W1 . gelu_erf(W0 . z_t + b0) + b1 with weight_norm(dim=None) folded, W = g * V / ||V||_F.
+ * z_t device fp32 [P][in_dim]; z_c device fp32 [P][out_dim] (out); weight_v / bias pointers are HOST fp32
+ * (state-dict tensors main.0.weight_v [hid][in], main.0.weight_g (scalar), main.0.bias, main.3.*).
+ * Synchronous (the stream is synchronised before returning). */
+int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
+                      const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream);
+
 /* Number of kernel launches one decode step issues (for bench.py's gpu_launches). */
 int biom3_launches_per_step(const biom3_model* m);
 

@@ -51,7 +51,7 @@ def _install_stand_ins():
     ax = types.ModuleType('axial_positional_embedding')
     ax.AxialPositionalEmbedding = upstream_blocks.AxialPositionalEmbedding
     sys.modules['axial_positional_embedding'] = ax
-    for name in ('Bio', 'Bio.Align', 'matplotlib', 'matplotlib.pyplot', 'imageio'):
+    for name in ('Bio', 'Bio.Align', 'matplotlib', 'matplotlib.pyplot', 'imageio', 'esm'):
         try:
             __import__(name)
         except Exception:
@@ -167,12 +167,29 @@ def full_config_forward(mod):
     print('full_forward_b2', tuple(logits.shape))
 
 
+def facilitator_case():
+    """The REAL Facilitator class (Stage1_source/model.py:473-493; `esm` stood in, never called), trained-looking
+    weights (weight_g != ||V||), z_t ~ N(0, 1.45^2) (README reports |z_t| ~ 33 at dim 512)."""
+    import Stage1_source.model as s1
+    assert s1.__file__.startswith(REF)
+    model = s1.Facilitator(in_dim=512, hid_dim=1024, out_dim=512, dropout=0.0)
+    sd = synthetic.facilitator_state_dict(512, 1024, seed=31)
+    model.load_state_dict(sd)                       # strict: the real class accepts our key schema
+    model.eval()
+    z_t = torch.randn(16, 512, generator=torch.Generator().manual_seed(32)) * 1.45
+    with torch.no_grad():
+        z_c = model(z_t)
+    np.savez_compressed(os.path.join(HERE, 'facilitator_p16.npz'), z_t=z_t.numpy(), z_c=z_c.numpy(), weight_seed=np.int32(31))
+    print('facilitator_p16', tuple(z_c.shape), sorted(sd.keys()))
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     mod, samp, helper, ani = import_reference()
     for name in CASES:
         run_case(mod, samp, name)
     full_config_forward(mod)
+    facilitator_case()
     # key schema of the real model at the stage3_config.json shape
     import json
     args = synthetic.stage3_args()

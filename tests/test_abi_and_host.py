@@ -133,3 +133,16 @@ def test_unit_plan_matches_reference_loop_nest():
     assert len(bd.plan_units(16, 32, 32)) == 16 and len(bd.plan_units(1, 512, 64)) == 8
     got = sorted(sum((bd.units_for_rank(16, r, 8) for r in range(8)), []))
     assert got == list(range(16))
+
+
+def test_facilitator_mirror_keys():
+    """Same state-dict keys/shapes as weight_norm(nn.Linear, dim=None) in the reference Facilitator."""
+    from biom3_b200.Stage1_source.model import Facilitator
+    m = Facilitator(512, 1024, 512, dropout=0.0)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {'main.0.bias': (1024,), 'main.0.weight_g': (), 'main.0.weight_v': (1024, 512),
+                   'main.3.bias': (512,), 'main.3.weight_g': (), 'main.3.weight_v': (512, 1024)}
+    m.load_state_dict(synthetic.facilitator_state_dict())
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU path'):
+            m(torch.zeros(2, 512))

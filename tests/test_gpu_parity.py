@@ -283,3 +283,42 @@ def test_dropin_sampler_signature_and_return_contract():
     ref_p = torch.softmax(torch.from_numpy(z['logits']), 1)
     assert (probs - ref_p).abs().max().item() < 2e-3
     assert dist_.sample().shape == (B, L, 29)
+
+
+# ---------------------------------------------------------------- Facilitator (configs[3] front end)
+def test_facilitator_vs_reference_fixture():
+    """z_c from the REAL reference Facilitator class (fixture) vs biom3_facilitator; fp32, 1e-4."""
+    from biom3_b200.Stage1_source.model import Facilitator
+    z = np.load(os.path.join(GOLDEN, 'facilitator_p16.npz'))
+    model = Facilitator(512, 1024, 512, dropout=0.0)
+    model.load_state_dict(synthetic.facilitator_state_dict(512, 1024, seed=int(z['weight_seed'])))
+    got = model(torch.from_numpy(z['z_t']).cuda()).cpu()
+    assert got.shape == (16, 512)
+    assert rel_err(got, torch.from_numpy(z['z_c'])) < 1e-4
+
+
+def test_full_config_short_decode_vs_oracle():
+    """stage3_config.json shape (16 layers, d 512, L 1024), B = 2, first 10 denoising steps, explicit noise:
+    token trajectory identical to the CPU oracle (the oracle's own race margins are reported on failure)."""
+    from biom3_b200.engine import Engine
+    from oracle.model import OracleModel
+    from oracle import sampler as osamp
+    B, L, C, T = 2, 1024, 29, 10
+    args = synthetic.stage3_args()
+    sd = synthetic.random_state_dict(args, seed=0)
+    eng = Engine(args, sd, torch.device('cuda'), B)
+    orc = OracleModel(args, sd)
+    z = synthetic.synthetic_z_c(1, 512, seed=1).repeat(B, 1)
+    path = synthetic.synthetic_paths(B, L, seed=2)
+    noise = synthetic.synthetic_noise(T, B, L, C, seed=3)
+    margins = []
+
+    def hook(i, logits):
+        p = torch.softmax(logits, 1).permute(0, 2, 1).reshape(B * L, C) / noise[i]
+        top2 = p.topk(2, -1).values
+        margins.append(((top2[:, 0] - top2[:, 1]) / top2[:, 0]).reshape(B, L).numpy())
+
+    states, _ = osamp.decode(orc, torch.zeros(B, L), torch.zeros(B).long(), z, path, noise, L, max_iters=T, logits_hook=hook)
+    tokens, traj = eng.decode(z.cuda(), path.cuda(), num_steps=T, noise=noise.cuda(), want_traj=True)
+    _assert_traj(traj.cpu().numpy().astype(np.int64), np.stack(states)[:, :, 0], margins)
+    assert np.array_equal(tokens.cpu().numpy(), states[-1][:, 0])
