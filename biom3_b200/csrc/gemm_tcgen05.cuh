@@ -415,12 +415,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
           }
+          if (p.tma_store) {
+            // the previous chunk's TMA store must have finished READING the staging block before it is rewritten
+            if (lane == 0) ptx::tma_store_wait_read();
+            __syncwarp();
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             st_shared_v4(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]),
                          ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
                          ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          __syncwarp();
           if (p.tma_store) {
             // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one lane stores
             ptx::fence_proxy_async();
@@ -429,19 +433,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
                                 tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
               ptx::tma_store_commit();
-              ptx::tma_store_wait_read();               // staging reusable once the engine has read it
             }
           } else {
+            __syncwarp();
             __nv_bfloat16* dst = dst0 + size_t(c) * chunk_stride;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
               const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
-              __nv_bfloat16* gp = dst + size_t(row) * row_stride + pc * 8;
-              if (p.debug_skip == 7) asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-              else if (p.debug_skip == 8) asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-              else if (p.debug_skip == 9) asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-              else if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(gp) = val;
+              if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
             }
           }
           __syncwarp();
@@ -457,6 +457,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
   ptx::tc_fence_before();
   __syncwarp();
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();
