@@ -46,6 +46,7 @@ enum Epi : int {
 struct Params {
   int M, N, K;
   int b_row_offset;        // first row of this layer's weight inside the stacked weight tensor map
+  int a_row_offset;        // first row of this launch's A rows inside the A tensor map (row-slab launches)
   void* out;               // bf16 or fp32, see Epi
   const float* bias;       // [N] or nullptr
   const float* cond;       // [B][cond_stride] fp32 or nullptr (added per sample, EPI_BIAS_RESID_F32)
@@ -169,11 +170,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if constexpr (CG2) {
             // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::STAGE_BYTES);
-            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], kb * BK, m0 + p.a_row_offset);
             ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0 + p.a_row_offset);
             ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

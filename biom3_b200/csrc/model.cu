@@ -205,6 +205,7 @@ struct biom3_model {
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
+  int mlp_slabs = 1;                            // FF1/FF2 row slabs per layer (hid slab reused, L2 resident)
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
   cudaStream_t cap_stream = nullptr;
@@ -348,15 +349,25 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
     r.out_bf16 = m->a; r.stats_out = m->stats;
     LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
-    // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t)
-    p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
-    p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
-    // u += hid . W2^T + b2 (+ next layer's conditioning vector)
-    r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
-    r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
-    r.cond_stride = JD;
-    LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+    // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t), then
+    // u += hid . W2^T + b2 (+ next layer's conditioning vector).  Optionally in row slabs that reuse one hid
+    // slab buffer, so the 4D-wide hidden activation lives in L2 between the two GEMMs instead of HBM.
+    const int slabs = (m->mlp_slabs > 1 && B % m->mlp_slabs == 0 && (M / m->mlp_slabs) % 256 == 0) ? m->mlp_slabs : 1;
+    const int Ms = M / slabs, Bs = B / slabs;
+    for (int sl = 0; sl < slabs; ++sl) {
+      const size_t row0 = size_t(sl) * Ms;
+      p.M = Ms; p.a_row_offset = int(row0);
+      p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
+      p.ln_stats = m->stats + row0 * m->ln_parts * 2;
+      p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
+      LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
+      r.M = Ms; r.a_row_offset = 0;
+      r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
+      r.out = m->u + row0 * D; r.out_bf16 = m->a + row0 * D; r.stats_out = m->stats + row0 * m->ln_parts * 2;
+      r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D + size_t(sl) * Bs * JD : nullptr;
+      r.cond_stride = JD;
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+    }
   }
   k::HeadArgs ha{};
   ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
@@ -433,6 +444,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   *out = m;

@@ -322,3 +322,35 @@ def test_full_config_short_decode_vs_oracle():
     tokens, traj = eng.decode(z.cuda(), path.cuda(), num_steps=T, noise=noise.cuda(), want_traj=True)
     _assert_traj(traj.cpu().numpy().astype(np.int64), np.stack(states)[:, :, 0], margins)
     assert np.array_equal(tokens.cpu().numpy(), states[-1][:, 0])
+
+
+def test_forward_odd_row_count_uses_single_cta_tiles():
+    """L = 128, B = 3 -> 384 rows: not a multiple of 256, so the GEMMs fall back from CTA pairs to 128-row tiles."""
+    over = dict(SMALL, diffusion_steps=128)
+    B = 3
+    args, sd, eng, orc = make(over, B)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(0, 29, (B, 128), generator=g)
+    t = torch.tensor([0, 64, 127])
+    z = synthetic.synthetic_z_c(B, 64, seed=4)
+    got = eng.forward(x.cuda(), t.cuda(), z.cuda()).cpu()
+    assert rel_err(got, orc(x, t, z)) < LOGIT_TOL
+
+
+def test_batch_of_one_decode_matches_oracle():
+    """B = 1 is the intended single-position unmask (no cross-sample coupling)."""
+    from oracle import sampler as osamp
+    B, L, C = 1, 256, 29
+    args, sd, eng, orc = make(SMALL, B, seed=5)
+    z = synthetic.synthetic_z_c(1, 64, seed=4)
+    path = synthetic.synthetic_paths(B, L, seed=6)
+    noise = synthetic.synthetic_noise(L, B, L, C, seed=7)
+    states, _ = osamp.decode(orc, torch.zeros(B, L), torch.zeros(B).long(), z, path, noise, L)
+    tokens, traj = eng.decode(z.cuda(), path.cuda(), noise=noise.cuda(), want_traj=True)
+    _assert_traj(traj.cpu().numpy().astype(np.int64), np.stack(states)[:, :, 0])
+    # exactly one position changes per step
+    tr = traj.cpu().numpy()
+    prev = np.zeros((B, L), dtype=np.uint8)
+    for t in range(L):
+        assert int((tr[t] != prev).sum()) <= 1
+        prev = tr[t]
