@@ -31,8 +31,10 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(ro
 
 __global__ void __launch_bounds__(256)
 local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
-                       float scale_log2e) {
-  const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+                       float scale_log2e, int reverse) {
+  // reverse: walk (sample, window) last-to-first so the QKV rows written last (still in L2) are read first
+  const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,
+            b = reverse ? int(gridDim.z) - 1 - int(blockIdx.z) : int(blockIdx.z);
   const int nw = L / WIN;
   const int w_lo = max(w - 1, 0), w_hi = min(w + 1, nw - 1);
   const int nkeys = (w_hi - w_lo + 1) * WIN;
@@ -180,8 +182,8 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
 
 __global__ void __launch_bounds__(128)
 linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
-                        int NL, float q_scale) {
-  const int h = NL + blockIdx.x, b = blockIdx.y;
+                        int NL, float q_scale, int reverse) {
+  const int h = NL + blockIdx.x, b = reverse ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
   const size_t head_stride = size_t(L) * DH;
   const size_t plane = size_t(B) * H * head_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

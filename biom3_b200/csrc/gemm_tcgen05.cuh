@@ -46,6 +46,7 @@ enum Epi : int {
 struct Params {
   int M, N, K;
   int b_row_offset;        // first row of this layer's weight inside the stacked weight tensor map
+  int reverse;             // 1 = walk the tiles last-to-first (consume the previous kernel's freshest, still L2-resident, output first)
   int a_row_offset;        // first row of this launch's A rows inside the A tensor map (row-slab launches)
   void* out;               // bf16 or fp32, see Epi
   const float* bias;       // [N] or nullptr
@@ -160,7 +161,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += n_workers) {
+      for (int t = worker; t < num_tiles; t += n_workers) {
+        const int tile = p.reverse ? num_tiles - 1 - t : t;
         const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
         const int n0 = (tile % n_tiles) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -223,7 +225,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
     const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
-    auto tile_gbase = [&](int tile) -> float* {        // this lane's first fp32 element of a tile (row rr, group ch)
+    auto tile_gbase = [&](int t) -> float* {           // this lane's first fp32 element of a tile (row rr, group ch)
+      const int tile = p.reverse ? num_tiles - 1 - t : t;
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
       return reinterpret_cast<float*>(p.out) + size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN +
              col_half * COLS_PER_WARP + 4 * ch;
@@ -237,7 +240,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
     uint32_t it = 0;
-    for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
+    for (int t = worker; t < num_tiles; t += n_workers, ++it) {
+      const int tile = p.reverse ? num_tiles - 1 - t : t;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
       const int n_tile = tile % n_tiles;
@@ -264,9 +268,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         float rs[8], rq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
-        float* gbase = tile_gbase(tile);
-        const int next_tile = tile + n_workers;
-        const float* gnext = next_tile < num_tiles ? tile_gbase(next_tile) : nullptr;
+        float* gbase = tile_gbase(t);
+        const int next_t = t + n_workers;
+        const float* gnext = next_t < num_tiles ? tile_gbase(next_t) : nullptr;
         float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll

@@ -205,6 +205,7 @@ struct biom3_model {
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
+  bool serpentine = true;                       // alternate the row walking direction kernel to kernel (L2 reuse)
   int mlp_slabs = 1;                            // FF1/FF2 row slabs per layer (hid slab reused, L2 resident)
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
@@ -329,6 +330,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const bool pw = m->use_pair && m->bn_wide == 256 && M % 256 == 0, pn = m->use_pair && m->bn_narrow == 256 && M % 256 == 0;
   const int iw = (m->bn_wide == 256 && !pw) ? 1 : 0, in = (m->bn_narrow == 256 && !pn) ? 1 : 0;   // weight map: 256- or 128-row box
+  int dir = 0;                                  // row walking direction of the next launch (see Params::reverse)
+  auto next_dir = [&]() { const int d = dir; if (m->serpentine) dir ^= 1; return d; };
+  next_dir();                                   // the embed kernel walked forward
   for (int j = 0; j < depth; ++j) {
     gemm::Params p{};
     p.L = L; p.H = H; p.Bsz = B; p.M = M;
@@ -336,18 +340,20 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
     p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store ? 1 : 0;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
+    p.reverse = next_dir();
     LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
+    const int adir = next_dir();                // both attention kernels read the same QKV output
     if (NL > 0)
       LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
-                          m->qkv, m->att, B, H, L, scale_log2e));
+                          m->qkv, m->att, B, H, L, scale_log2e, adir));
     if (H - NL > 0)
       LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(m->qkv, m->att, B, H, L, NL,
-                                                                                      q_scale));
+                                                                                      q_scale, adir));
     // u += att . Wo^T + bo ; also emits bf16(u) and its row statistics for the next folded LayerNorm
     gemm::Params r{};
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
-    r.out_bf16 = m->a; r.stats_out = m->stats;
+    r.out_bf16 = m->a; r.stats_out = m->stats; r.reverse = next_dir();
     LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t), then
     // u += hid . W2^T + b2 (+ next layer's conditioning vector).  Optionally in row slabs that reuse one hid
@@ -356,12 +362,12 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     const int Ms = M / slabs, Bs = B / slabs;
     for (int sl = 0; sl < slabs; ++sl) {
       const size_t row0 = size_t(sl) * Ms;
-      p.M = Ms; p.a_row_offset = int(row0);
+      p.M = Ms; p.a_row_offset = int(row0); p.reverse = next_dir();
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
       p.ln_stats = m->stats + row0 * m->ln_parts * 2;
       p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
       LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
-      r.M = Ms; r.a_row_offset = 0;
+      r.M = Ms; r.a_row_offset = 0; r.reverse = next_dir();
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.out = m->u + row0 * D; r.out_bf16 = m->a + row0 * D; r.stats_out = m->stats + row0 * m->ln_parts * 2;
       r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D + size_t(sl) * Bs * JD : nullptr;
@@ -444,6 +450,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
