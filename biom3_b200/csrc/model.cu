@@ -210,6 +210,9 @@ struct biom3_model {
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t side_stream = nullptr;           // linear attention runs here, concurrently with local attention
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool attn_overlap = false;                    // measured: no gain (the two kernels do not co-reside), kept as a switch
   cudaGraphExec_t graph_exec = nullptr;
   int graph_B = -1, graph_group = -1;
   std::vector<void*> allocs;
@@ -343,12 +346,25 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.reverse = next_dir();
     LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
     const int adir = next_dir();                // both attention kernels read the same QKV output
+    // The two attention kernels read the same QKV output and write disjoint column ranges of `att`.  Outside the
+    // profiler they are forked onto two streams (two branches of the step graph): the linear heads are latency /
+    // HBM bound, the local heads MMA / MUFU bound, so the SMs can interleave their CTAs.
+    const bool fork = m->attn_overlap && !prof && NL > 0 && H - NL > 0;
+    if (fork) {
+      cudaEventRecord(m->ev_fork, st);
+      cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0);
+    }
+    cudaStream_t lst = fork ? m->side_stream : st;
+    if (H - NL > 0)
+      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, lst>>>(m->qkv, m->att, B, H, L, NL,
+                                                                                       q_scale, adir));
     if (NL > 0)
       LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
                           m->qkv, m->att, B, H, L, scale_log2e, adir));
-    if (H - NL > 0)
-      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(m->qkv, m->att, B, H, L, NL,
-                                                                                      q_scale, adir));
+    if (fork) {
+      cudaEventRecord(m->ev_join, m->side_stream);
+      cudaStreamWaitEvent(st, m->ev_join, 0);
+    }
     // u += att . Wo^T + bo ; also emits bf16(u) and its row statistics for the next folded LayerNorm
     gemm::Params r{};
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
@@ -454,6 +470,10 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+  CU_OK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+  CU_OK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  CU_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  if (const char* e = getenv("BIOM3_ATTN_OVERLAP")) m->attn_overlap = atoi(e) != 0;
   *out = m;
   return BIOM3_OK;
 }
@@ -464,6 +484,9 @@ void biom3_destroy(biom3_model* m) {
   cudaDeviceSynchronize();
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->side_stream) cudaStreamDestroy(m->side_stream);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
 }
