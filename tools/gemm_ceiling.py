@@ -31,6 +31,6 @@ if __name__ == '__main__':
     if len(sys.argv) > 1:
         run()
     else:
-        for skip in (sys.argv[1:] or ['0', '1', '2']) if False else ['0']:
+        for skip in ['0', '1', '2', '3']:
             print(f'BIOM3_EPI_SKIP={skip}', flush=True)
             subprocess.run([sys.executable, os.path.abspath(__file__), 'run'], env=dict(os.environ, BIOM3_EPI_SKIP=skip))
