@@ -4,6 +4,8 @@
 //
 // Input layout (written by the QKV GEMM epilogue): qkv bf16 [3][B][H][L][32]; output bf16 [B*L][H*32].
 #pragma once
+#include <cuda.h>
+
 #include "ptx.cuh"
 
 namespace attn {
@@ -385,6 +387,189 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     }
     __syncwarp();
   }
+}
+
+
+// ================================================================================================
+// Local attention on the 5th-generation tensor cores (tcgen05), one CTA (4 warps) per (window, head, sample).
+//   TMA (64B swizzle) stages Q [128 x 32], K_w and V_w [128 x 32] of the 1-3 visible key windows.
+//   per key window j:  S_j = Q K_j^T   (tcgen05.mma 128 x 128 x 32, fp32 in TMEM, operands K-major SW64)
+//                      softmax numerators, thread = query row: two sweeps over S_j in TMEM (max, then
+//                      exp2 / row sum / bf16 pack), P_j written to smem as a K-major SW128 operand
+//                      O_j = P_j V_j   (tcgen05.mma 128 x 32 x 128; V is consumed as stored, [key][d] rows of
+//                      64 bytes = the MN-major SW64 canonical layout)
+//                      o <- o * corr + O_j in registers (online softmax across windows)
+// TMEM: 128 columns S + 32 columns O -> 256 allocated, two CTAs per SM.
+// ================================================================================================
+constexpr int TC_TILE = WIN * 64;                              // one 128 x 32 bf16 tile (64-byte rows)
+constexpr int TC_SMEM_BYTES = 7 * TC_TILE + 2 * WIN * 128 + 1024;   // Q + 3 K + 3 V + P (two 128 x 64 SW128 blocks) + align
+
+// smem matrix descriptor, 64-byte rows with the 64-byte swizzle (SBO = 8 rows x 64 B); used both for the
+// K-major Q / K tiles and for V as an MN-major B operand (SBO = stride between 8-key groups)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(256)
+local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
+                          int L, float scale_log2e, int reverse) {
+  // 8 warps: two threads per query row.  Thread (row = tid & 127, half = tid >> 7) owns keys [64*half, +64) of each
+  // 128-key window (one K-major SW128 block of P) and output features [16*half, +16).
+  const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,
+            b = reverse ? int(gridDim.z) - 1 - int(blockIdx.z) : int(blockIdx.z);
+  const int nw = L / WIN;
+  const int w_lo = max(w - 1, 0), w_hi = min(w + 1, nw - 1);
+  const int nwin = w_hi - w_lo + 1;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+
+  extern __shared__ uint8_t tc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TC_TILE;
+  uint8_t* sV = smem + 4 * TC_TILE;
+  const uint32_t sP = ptx::smem_u32(smem + 7 * TC_TILE);
+  __shared__ uint64_t bar_load, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xmax[2][2][WIN];          // [window parity][half][row]: partial row maxima
+  __shared__ float xsum[2][WIN];             // [half][row]: partial row sums (end of kernel)
+
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_qkv);
+    ptx::mbar_init(&bar_load, 1);
+    ptx::mbar_init(&bar_s, 1);
+    ptx::mbar_init(&bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_s = tmem + ((uint32_t(warp & 3) * 32u) << 16) + half * 64;   // S columns [64*half, +64)
+  const uint32_t t_o = tmem + ((uint32_t(warp & 3) * 32u) << 16) + 128 + half * 16;   // O columns [16*half, +16)
+
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+  auto issue_s = [&](int j) {                 // S = Q K_j^T : two k-steps of 16 features
+    const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ));
+    const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sK + j * TC_TILE));
+    ptx::umma_bf16(tmem, dq, dk, IDESC_S, 0);
+    ptx::umma_bf16(tmem, dq + 2, dk + 2, IDESC_S, 1);
+    ptx::umma_commit(&bar_s);
+  };
+  auto issue_o = [&](int j) {                 // O_j = P_j V_j : eight k-steps of 16 keys
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t dp = ptx::umma_desc_sw128(sP + (ks >> 2) * (WIN * 128) + (ks & 3) * 32);
+      const uint64_t dv = umma_desc_sw64(ptx::smem_u32(sV + j * TC_TILE) + ks * 16 * 64);
+      ptx::umma_bf16(tmem + 128, dp, dv, IDESC_O, ks != 0);
+    }
+    ptx::umma_commit(&bar_o);
+  };
+
+  if (tid == 0) {
+    const int plane = B * H * L;
+    const int rq = (b * H + h) * L;
+    ptx::mbar_arrive_expect_tx(&bar_load, (1 + 2 * nwin) * TC_TILE);
+    ptx::tma_load_2d(sQ, &tm_qkv, &bar_load, 0, rq + w * WIN);
+    for (int j = 0; j < nwin; ++j) {
+      ptx::tma_load_2d(sK + j * TC_TILE, &tm_qkv, &bar_load, 0, plane + rq + (w_lo + j) * WIN);
+      ptx::tma_load_2d(sV + j * TC_TILE, &tm_qkv, &bar_load, 0, 2 * plane + rq + (w_lo + j) * WIN);
+    }
+  }
+  ptx::mbar_wait(&bar_load, 0);
+  if (tid == 0) {
+    ptx::tc_fence_after();
+    issue_s(0);
+  }
+
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+  float m = -INFINITY, l = 0.f;
+
+  for (int j = 0; j < nwin; ++j) {
+    ptx::mbar_wait(&bar_s, j & 1);
+    ptx::tc_fence_after();
+    // sweep 1: this thread's 64 scores -> partial row maximum, exchanged with the other half through smem
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld_32x32(t_s, r0);
+    ptx::tmem_ld_32x32(t_s + 32, r1);
+    ptx::tmem_ld_wait();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+    xmax[j & 1][half][row] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, xmax[j & 1][half ^ 1][row]);
+    const float mn = fmaxf(m, mx);
+    const float corr = fast_ex2((m - mn) * scale_log2e);
+    const float ms = mn * scale_log2e;
+    m = mn;
+    // sweep 2 (from registers): numerators, partial row sum, bf16 pack -> this half's 64-key SW128 block of P
+    float rs = 0.f;
+    const uint32_t pbase = sP + half * (WIN * 128) + row * 128;
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float s0 = __uint_as_float(c2 == 0 ? r0[2 * i] : r1[2 * i]);
+        const float s1 = __uint_as_float(c2 == 0 ? r0[2 * i + 1] : r1[2 * i + 1]);
+        const float p0 = fast_ex2(fmaf(s0, scale_log2e, -ms));
+        const float p1 = fast_ex2(fmaf(s1, scale_log2e, -ms));
+        rs += p0 + p1;
+        pk[i] = ptx::pack_bf16x2(p0, p1);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = c2 * 4 + q;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbase + ((chunk ^ (row & 7)) << 4)), "r"(pk[4 * q]),
+                     "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
+      }
+    }
+    l = l * corr + rs;
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      issue_o(j);
+      if (j + 1 < nwin) issue_s(j + 1);
+    }
+    ptx::mbar_wait(&bar_o, j & 1);
+    ptx::tc_fence_after();
+    {
+      uint32_t ro[16];
+      ptx::tmem_ld_32x16(t_o, ro);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(ro[i]));
+    }
+  }
+  xsum[half][row] = l;
+  ptx::tc_fence_before();
+  __syncthreads();
+  const float inv = 1.f / (l + xsum[half ^ 1][row]);
+  const int D = H * DH;
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t(b) * L + size_t(w) * WIN + row) * D + h * DH + half * 16);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    dst[i] = make_uint4(ptx::pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), ptx::pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                        ptx::pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv), ptx::pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace attn

@@ -68,6 +68,21 @@ int make_store_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t c
   return BIOM3_OK;
 }
 
+// bf16 [rows][32] (64-byte rows, e.g. the head-major qkv buffer) -> tiles of [128 rows][32], 64-byte swizzle
+int make_tmap_sw64(CUtensorMap* tm, const void* base, uint64_t rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {32, rows};
+  cuuint64_t strides[1] = {32 * sizeof(bf16)};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled (sw64) failed: " + std::to_string(int(r)));
+  return BIOM3_OK;
+}
+
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(BIOM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -144,6 +159,9 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LOCAL_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::local_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::TC_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -203,6 +221,8 @@ struct biom3_model {
   int *inv_path = nullptr, *t_i32 = nullptr;
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
+  CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
+  bool attn_tc = false;                         // local attention on tcgen05 instead of mma.sync
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
   bool serpentine = true;                       // alternate the row walking direction kernel to kernel (L2 reuse)
@@ -358,9 +378,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     if (H - NL > 0)
       LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, lst>>>(m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
-    if (NL > 0)
-      LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
-                          m->qkv, m->att, B, H, L, scale_log2e, adir));
+    if (NL > 0) {
+      if (m->attn_tc)
+        LAUNCH(C_LOCAL, attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(
+                            m->tm_qkv_attn, m->att, B, H, L, scale_log2e, adir));
+      else
+        LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
+                            m->qkv, m->att, B, H, L, scale_log2e, adir));
+    }
     if (fork) {
       cudaEventRecord(m->ev_join, m->side_stream);
       cudaStreamWaitEvent(st, m->ev_join, 0);
@@ -466,6 +491,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   CU_OK(init_kernel_attributes());
@@ -611,6 +637,7 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
   TRY(make_tmap(&m->tm_hid, m->hid, M, 4 * D, 128));
   TRY(make_store_tmap(&m->tm_st_qkv, m->qkv, M * 3 * D / 32, 32));
+  TRY(make_tmap_sw64(&m->tm_qkv_attn, m->qkv, M * 3 * D / 32));
   TRY(make_store_tmap(&m->tm_st_hid, m->hid, M, 4 * D));
   for (int i = 0; i < 2; ++i) {
     const uint32_t box = i ? 256 : 128;
@@ -809,6 +836,31 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
   k::unmask_kernel<<<(B * group + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(tok), inv,
                                                               reinterpret_cast<long long*>(state), B, L, group, step);
   CU_OK(cudaFreeAsync(inv, st));
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
+int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL, int variant, void* stream) {
+  if (!qkv || !out || B < 1 || H < 1 || NL < 0 || NL > H || L < attn::WIN || L % attn::WIN)
+    return fail(BIOM3_ERR_INVALID, "bad attention_test argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CU_OK(init_kernel_attributes());
+  const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
+  const float q_scale = 1.0f / sqrtf(float(attn::DH));
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (NL > 0) {
+    if (variant == 1) {
+      CUtensorMap tm;
+      int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
+      if (r) return r;
+      attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(tm, o, B, H, L, scale_log2e, 0);
+    } else {
+      attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(q, o, B, H, L, scale_log2e, 0);
+    }
+  }
+  if (H - NL > 0)
+    attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }

@@ -160,3 +160,15 @@ def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ep
         _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
     return out
+
+
+def attention_test(qkv: torch.Tensor, NL: int, variant: int = 0) -> torch.Tensor:
+    """Unit-test hook: qkv bf16 [3, B, H, L, 32] (cuda) -> attention output bf16 [B*L, H*32]."""
+    lib = _lib.load()
+    _, B, H, L, dh = qkv.shape
+    assert dh == 32 and qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    out = torch.zeros(B * L, H * 32, device=qkv.device, dtype=torch.bfloat16)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.biom3_attention_test(_ptr(qkv), _ptr(out), B, H, L, NL, variant,
+                                            C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)))
+    return out

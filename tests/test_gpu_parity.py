@@ -354,3 +354,22 @@ def test_batch_of_one_decode_matches_oracle():
     for t in range(L):
         assert int((tr[t] != prev).sum()) <= 1
         prev = tr[t]
+
+
+# ---------------------------------------------------------------- attention kernels in isolation
+@pytest.mark.parametrize('B,H,L,NL', [(1, 2, 128, 1), (2, 4, 256, 2), (2, 16, 1024, 8)])
+@pytest.mark.parametrize('variant', [0, 1])
+def test_attention_kernels_vs_fp32_reference(B, H, L, NL, variant):
+    """variant 0: mma.sync local attention (the default), variant 1: the tcgen05 local-attention kernel (TMEM S/O,
+    MN-major V operand); heads >= NL: linear attention.  Same bf16 inputs, fp32 reference -> bf16 output rounding."""
+    from biom3_b200 import engine
+    from oracle.upstream_blocks import LocalAttention, linear_attention
+    g = torch.Generator().manual_seed(B * 100 + L)
+    qkv = (torch.randn(3, B, H, L, 32, generator=g) * 1.5).bfloat16()
+    q, k, v = (t.float() for t in qkv)
+    lo = LocalAttention(128)(q[:, :NL], k[:, :NL], v[:, :NL])
+    go = linear_attention(q[:, NL:], k[:, NL:], v[:, NL:])
+    ref = torch.cat([lo, go], 1).transpose(1, 2).reshape(B * L, H * 32)
+    out = engine.attention_test(qkv.cuda(), NL, variant).float().cpu()
+    assert rel_err(out[:, :NL * 32], ref[:, :NL * 32]) < 8e-3
+    assert rel_err(out[:, NL * 32:], ref[:, NL * 32:]) < 8e-3
