@@ -21,6 +21,8 @@ constexpr int WIN = 128;   // local window (fixed; checked at create time)
 // ldmatrix (8 rows x 16 B) is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
 constexpr int LOCAL_SMEM_BYTES = 7 * WIN * 64;   // Q (1 window) + K (3) + V (3), 64 B per row
+constexpr int LOCAL_CH = 64;                     // keys per online-softmax step (32 fits 4 CTAs / SM but measured 4 % slower)
+constexpr int LOCAL_NT = LOCAL_CH / 8;           // 8-key score tiles per step
 
 // 2^x as a single MUFU.EX2 (exp2f() adds denormal range handling: 3 more instructions per element)
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -31,7 +33,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LOCAL_CH == 32 ? 4 : 3)
 local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
                        float scale_log2e, int reverse) {
   // reverse: walk (sample, window) last-to-first so the QKV rows written last (still in L2) are read first
@@ -94,12 +96,12 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   float ol[4] = {0.f, 0.f, 0.f, 0.f};   // row sums, accumulated by the tensor core (every column holds the sum)
   float m0 = -INFINITY, m1 = -INFINITY;
 
-  for (int kc = 0; kc < nkeys; kc += 64) {
+  for (int kc = 0; kc < nkeys; kc += LOCAL_CH) {
     const uint32_t kbase = sk + uint32_t(kc) * 64u + laneK, vbase0 = sv + uint32_t(kc) * 64u + laneV0,
                    vbase1 = sv + uint32_t(kc) * 64u + laneV1;
-    float s[8][4];
+    float s[LOCAL_NT][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < LOCAL_NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       uint32_t kb0, kb1, kb2, kb3;
       ptx::ldmatrix_x4(kbase + nt * 512, kb0, kb1, kb2, kb3);
@@ -108,7 +110,7 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     }
     float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < LOCAL_NT; ++nt) {
       cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
       cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -127,7 +129,7 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     }
     ol[0] *= corr0; ol[1] *= corr0; ol[2] *= corr1; ol[3] *= corr1;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {        // 16 keys per step
+    for (int kk = 0; kk < LOCAL_NT / 2; ++kk) {        // 16 keys per step
       const uint32_t a0 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk][0], scale_log2e, -ms0)), fast_ex2(fmaf(s[2 * kk][1], scale_log2e, -ms0)));
       const uint32_t a1 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk][2], scale_log2e, -ms1)), fast_ex2(fmaf(s[2 * kk][3], scale_log2e, -ms1)));
       const uint32_t a2 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk + 1][0], scale_log2e, -ms0)), fast_ex2(fmaf(s[2 * kk + 1][1], scale_log2e, -ms0)));
