@@ -1,0 +1,254 @@
+// Kernels of the fp32-class forward (precision 1): activations stay fp32 in HBM, every dense contraction runs on
+// the tcgen05 GEMM as a three-product bf16 split (x = hi + lo, hi.Whi + hi.Wlo + lo.Whi, fp32 accumulate; see
+// Params::split3), attention runs in fp32 on the CUDA cores.  Target: logits within 1e-4 relative of the fp32
+// reference (BASELINE.json north_star); speed is secondary here, the bf16 path is the throughput mode.
+//
+// Split layout: a "[hi | lo]" buffer of an [M][K] fp32 matrix is bf16 [M][2K]: columns [0, K) hold bf16(x),
+// columns [K, 2K) hold bf16(x - bf16(x)).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace f32p {
+
+constexpr int DH = 32;
+constexpr int WIN = 128;
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// 4 consecutive fp32 -> 4 hi at `hi_dst`, 4 lo at `hi_dst + K`
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi_dst, int K, float4 v) {
+  __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x, h[0], l[0]);
+  split_bf16(v.y, h[1], l[1]);
+  split_bf16(v.z, h[2], l[2]);
+  split_bf16(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi_dst) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(hi_dst + K) = *reinterpret_cast<const uint2*>(l);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm (eps 1e-5, two-pass statistics like torch) + split: u fp32 [rows][D] -> a2 bf16 [rows][2D].
+// One warp per row, D <= 1024, D % 128 == 0.
+__global__ void __launch_bounds__(256)
+ln_split_kernel(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ a2, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        v[i] = *reinterpret_cast<const float4*>(u + size_t(row) * D + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    const float mean = warp_sum_f(s) / float(D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const float x0 = v[i].x - mean, x1 = v[i].y - mean, x2 = v[i].z - mean, x3 = v[i].w - mean;
+        q += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(q) / float(D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+        const float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        store_split4(a2 + size_t(row) * 2 * D + col, D, o);
+      }
+  }
+}
+
+// h fp32 [rows][N] -> split(gelu_erf(h + bias)) bf16 [rows][2N]   (exact erf form, torch's default nn.GELU)
+__global__ void __launch_bounds__(256)
+bias_gelu_split_kernel(const float* __restrict__ h, const float* __restrict__ bias, __nv_bfloat16* __restrict__ h2,
+                       size_t rows, int N) {
+  const size_t n4 = rows * size_t(N / 4);
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t row = i / size_t(N / 4);
+    const int col = int(i % size_t(N / 4)) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(h + row * N + col);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+    auto g = [](float t) { return 0.5f * t * (1.0f + erff(t * 0.70710678118654752440f)); };
+    const float4 o = make_float4(g(x.x + b.x), g(x.y + b.y), g(x.z + b.z), g(x.w + b.w));
+    store_split4(h2 + row * 2 * N + col, N, o);
+  }
+}
+
+// Windowed softmax attention, fp32.  qkv fp32 row-major [B*L][3*D] (column = which*D + h*32 + d), heads [0, NL).
+// grid (L/128, NL, B), 128 threads: thread = one query row; K and V of one key window at a time in shared memory
+// (every thread reads the same key -> broadcast), online softmax over chunks of 16 keys.  Windows w-1 and w+1 that
+// fall off the sequence are skipped, which equals the reference's -FLT_MAX fill (their exp underflows to exactly 0).
+// Output: split [hi | lo] of the [B*L][D] attention matrix, columns h*32 .. h*32+31.
+__global__ void __launch_bounds__(128)
+local_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
+                           float scale) {
+  __shared__ __align__(16) float sk[WIN][DH];
+  __shared__ __align__(16) float sv[WIN][DH];
+  const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * DH;
+  const int nw = L / WIN;
+  const int tid = threadIdx.x;
+  const size_t row = size_t(b) * L + size_t(w) * WIN + tid;
+  float q[DH], acc[DH];
+  {
+    const float* qp = qkv + row * 3 * D + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH / 4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(qp + 4 * i);
+      q[4 * i] = t.x * scale; q[4 * i + 1] = t.y * scale; q[4 * i + 2] = t.z * scale; q[4 * i + 3] = t.w * scale;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+  float mx = -INFINITY, den = 0.f;
+  for (int kw = w - 1; kw <= w + 1; ++kw) {
+    if (kw < 0 || kw >= nw) continue;
+    __syncthreads();
+    for (int i = tid; i < WIN * DH / 4; i += 128) {
+      const int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      const float* src = qkv + (size_t(b) * L + size_t(kw) * WIN + r) * 3 * D + h * DH + c;
+      *reinterpret_cast<float4*>(&sk[r][c]) = *reinterpret_cast<const float4*>(src + D);
+      *reinterpret_cast<float4*>(&sv[r][c]) = *reinterpret_cast<const float4*>(src + 2 * D);
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < WIN; j0 += 16) {
+      float s[16];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH / 4; ++i) {
+          const float4 kk = *reinterpret_cast<const float4*>(&sk[j0 + j][4 * i]);
+          d = fmaf(q[4 * i], kk.x, d);
+          d = fmaf(q[4 * i + 1], kk.y, d);
+          d = fmaf(q[4 * i + 2], kk.z, d);
+          d = fmaf(q[4 * i + 3], kk.w, d);
+        }
+        s[j] = d;
+        cm = fmaxf(cm, d);
+      }
+      const float nm = fmaxf(mx, cm);
+      const float corr = expf(mx - nm);          // first chunk: exp(-inf) = 0
+      mx = nm;
+      den *= corr;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) acc[i] *= corr;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pj = expf(s[j] - nm);
+        den += pj;
+#pragma unroll
+        for (int i = 0; i < DH / 4; ++i) {
+          const float4 vv = *reinterpret_cast<const float4*>(&sv[j0 + j][4 * i]);
+          acc[4 * i] = fmaf(pj, vv.x, acc[4 * i]);
+          acc[4 * i + 1] = fmaf(pj, vv.y, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(pj, vv.z, acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(pj, vv.w, acc[4 * i + 3]);
+        }
+      }
+    }
+  }
+  const float inv = 1.0f / den;
+  __nv_bfloat16* dst = att2 + row * 2 * D + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH / 4; ++i)
+    store_split4(dst + 4 * i, D, make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
+}
+
+// Linear attention, fp32, heads [NL, H): q = softmax_d(q) * dh^-0.5, k = softmax_n(k), ctx = k^T v, out = q ctx.
+// grid (H - NL, B), 256 threads.  Three passes over the head's [L][32] k / v / q columns (L2 resident).
+__global__ void __launch_bounds__(256)
+linear_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
+                            int NL, float q_scale) {
+  __shared__ float red[8][DH];
+  __shared__ float kmax[DH], kinv[DH];
+  __shared__ float ctx[DH][DH + 1];
+  __shared__ float part[8][DH][DH + 1];        // per-warp partial ctx (33 KB)
+  __shared__ float zpart[8][DH];
+  const int h = NL + blockIdx.x, b = blockIdx.y;
+  const int D = H * DH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* base = qkv + size_t(b) * L * 3 * D + h * DH;       // + n*3D (+ D for k, + 2D for v)
+  // pass 1: per-feature max of k over the sequence (lane = feature, warps stride over tokens)
+  float m = -INFINITY;
+  for (int n = warp; n < L; n += 8) m = fmaxf(m, base[size_t(n) * 3 * D + D + lane]);
+  red[warp][lane] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float mm = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i][lane]);
+    kmax[lane] = mm;
+  }
+  __syncthreads();
+  // pass 2: ctx[d][e] = sum_n exp(k[n][d] - max_d) v[n][e], Z[d] = sum_n exp(.)   (lane = e; warp strides tokens)
+  float c[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) c[d] = 0.f;
+  float z = 0.f;                                // lane = d for the Z sum
+  for (int n = warp; n < L; n += 8) {
+    const float kv = expf(base[size_t(n) * 3 * D + D + lane] - kmax[lane]);   // lane = d
+    const float vv = base[size_t(n) * 3 * D + 2 * D + lane];                  // lane = e
+    z += kv;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) c[d] = fmaf(__shfl_sync(0xffffffffu, kv, d), vv, c[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < DH; ++d) part[warp][d][lane] = c[d];
+  zpart[warp][lane] = z;
+  __syncthreads();
+  if (warp == 0) {
+    float zz = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zz += zpart[i][lane];
+    kinv[lane] = 1.0f / zz;
+  }
+  __syncthreads();
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i / DH, e = i % DH;
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sum += part[wv][d][e];
+    ctx[d][e] = sum * kinv[d];
+  }
+  __syncthreads();
+  // pass 3: out[n][e] = sum_d softmax_d(q[n])[d] * q_scale * ctx[d][e]   (lane = d for the softmax, = e for the output)
+  for (int n = warp; n < L; n += 8) {
+    const float qv = base[size_t(n) * 3 * D + lane];
+    float qm = qv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+    const float qe = expf(qv - qm);
+    const float qs = qe / warp_sum_f(qe) * q_scale;
+    float o = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o = fmaf(__shfl_sync(0xffffffffu, qs, d), ctx[d][lane], o);
+    __nv_bfloat16 hi, lo;
+    split_bf16(o, hi, lo);
+    __nv_bfloat16* dst = att2 + (size_t(b) * L + n) * 2 * D + h * DH + lane;
+    dst[0] = hi;
+    dst[D] = lo;
+  }
+}
+
+}  // namespace f32p

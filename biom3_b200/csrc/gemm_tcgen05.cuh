@@ -63,6 +63,8 @@ struct Params {
   // producer side (EPI_BIAS_RESID_F32): raw bf16 copy of the updated rows + their partial statistics
   __nv_bfloat16* out_bf16; // [M][N] or nullptr
   float* stats_out;        // [M][(N/BN)*2][2] or nullptr
+  int split3;              // fp32-class mode: A and W hold [hi | lo] bf16 halves (2K columns each); the K loop runs
+                           // hi.hi, hi.lo, lo.hi (3K/BK blocks, fp32 accumulate) = the product to ~2^-16 relative
   int tma_store;           // bf16 epilogues: 1 = store 32 x 32 blocks with TMA (tmap_c, 64B swizzle) instead of st.global
   int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
@@ -128,7 +130,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int n_workers = CG2 ? int(gridDim.x >> 1) : int(gridDim.x);
   const int n_tiles = p.N / BN;
   const int num_tiles = (p.M / TILE_M) * n_tiles;
-  const int k_blocks = p.K / BK;
+  const int nk = p.K / BK;
+  const int k_blocks = p.split3 ? 3 * nk : nk;
 
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
@@ -169,15 +172,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
+          // split3: blocks [0, nk) A_hi.W_hi, [nk, 2nk) A_hi.W_lo, [2nk, 3nk) A_lo.W_hi
+          const int ka = (kb < nk ? kb : kb - nk) * BK;
+          const int kw = (kb < 2 * nk ? kb : kb - 2 * nk) * BK;
           if constexpr (CG2) {
             // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::STAGE_BYTES);
-            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], kb * BK, m0 + p.a_row_offset);
-            ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
+            ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kw, n0);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0 + p.a_row_offset);
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kw, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

@@ -15,6 +15,7 @@
 
 #include "../../include/biom3_b200.h"
 #include "attention.cuh"
+#include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 
@@ -237,6 +238,14 @@ struct biom3_model {
   int graph_B = -1, graph_group = -1;
   std::vector<void*> allocs;
   int launches_per_step = 0;
+  // fp32-class mode (biom3_set_precision(m, 1) before finalize): split [hi | lo] weights and fp32 activations
+  int precision = 0;
+  bf16 *Wqkv2 = nullptr, *Wo2 = nullptr, *W1s = nullptr, *W2s = nullptr;       // [N][2K] per layer, stacked
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // [depth][D]
+  bf16 *a2 = nullptr, *hid2 = nullptr;                                            // [M][2D], [M][8D]
+  float *qkv32 = nullptr, *hid32 = nullptr;                                       // [M][3D], [M][4D]
+  CUtensorMap tm_a2{}, tm_hid2{};
+  CUtensorMap tm_wqkv2[2]{}, tm_wo2[2]{}, tm_w1s[2]{}, tm_w2s[2]{};
 };
 
 namespace {
@@ -276,6 +285,23 @@ int upload_bf16(biom3_model* m, const std::string& key, size_t numel, bf16* dst)
   std::vector<bf16> tmp(numel);
   for (size_t i = 0; i < numel; ++i) tmp[i] = __float2bfloat16_rn((*v)[i]);
   CU_OK(cudaMemcpy(dst, tmp.data(), numel * sizeof(bf16), cudaMemcpyHostToDevice));
+  return BIOM3_OK;
+}
+
+// fp32-class mode: W fp32 [N][K] -> bf16 [N][2K] = [bf16(W) | bf16(W - bf16(W))]
+int upload_split(biom3_model* m, const std::string& key, size_t N, size_t K, bf16* dst) {
+  const std::vector<float>* v;
+  int r = get_w(m, key, N * K, &v);
+  if (r) return r;
+  std::vector<bf16> tmp(N * 2 * K);
+  for (size_t n = 0; n < N; ++n)
+    for (size_t kk = 0; kk < K; ++kk) {
+      const float w = (*v)[n * K + kk];
+      const bf16 hi = __float2bfloat16_rn(w);
+      tmp[n * 2 * K + kk] = hi;
+      tmp[n * 2 * K + K + kk] = __float2bfloat16_rn(w - __bfloat162float(hi));
+    }
+  CU_OK(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   return BIOM3_OK;
 }
 
@@ -356,6 +382,35 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   int dir = 0;                                  // row walking direction of the next launch (see Params::reverse)
   auto next_dir = [&]() { const int d = dir; if (m->serpentine) dir ^= 1; return d; };
   next_dir();                                   // the embed kernel walked forward
+  if (m->precision == 1) {
+    // fp32-class layer loop (fp32_path.cuh): explicit fp32 LayerNorm / GELU / attention, bf16x3 split GEMMs
+    const int ew_blocks = m->num_sms * 8;
+    for (int j = 0; j < depth; ++j) {
+      gemm::Params p{};
+      p.L = L; p.H = H; p.Bsz = B; p.M = M; p.split3 = 1;
+      LAUNCH(C_LN, f32p::ln_split_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln1_g + size_t(j) * D, m->ln1_b + size_t(j) * D,
+                                                                    m->a2, M, D));
+      p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv32; p.reverse = 0;
+      LAUNCH(C_QKV, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_wqkv2[iw], m->tm_st_hid, p, m->num_sms, st));
+      if (H - NL > 0)
+        LAUNCH(C_LINEAR, f32p::linear_attention_f32_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
+      if (NL > 0)
+        LAUNCH(C_LOCAL, f32p::local_attention_f32_kernel<<<dim3(L / attn::WIN, NL, B), 128, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
+      gemm::Params r{};
+      r.L = L; r.H = H; r.Bsz = B; r.M = M; r.split3 = 1;
+      r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_a2, m->tm_wo2[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_LN, f32p::ln_split_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D, m->ln2_b + size_t(j) * D,
+                                                                    m->a2, M, D));
+      p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid32;
+      LAUNCH(C_FF1, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_w1s[iw], m->tm_st_hid, p, m->num_sms, st));
+      LAUNCH(C_OTHER, f32p::bias_gelu_split_kernel<<<ew_blocks, 256, 0, st>>>(m->hid32, m->b1 + size_t(j) * 4 * D, m->hid2, size_t(M), 4 * D));
+      r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
+      r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
+      r.cond_stride = JD;
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid2, m->tm_w2s[in], m->tm_st_hid, r, m->num_sms, st));
+    }
+  } else
   for (int j = 0; j < depth; ++j) {
     gemm::Params p{};
     p.L = L; p.H = H; p.Bsz = B; p.M = M;
@@ -524,6 +579,14 @@ int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t
   return BIOM3_OK;
 }
 
+int biom3_set_precision(biom3_model* m, int precision) {
+  if (!m) return fail(BIOM3_ERR_INVALID, "null model");
+  if (precision != 0 && precision != 1) return fail(BIOM3_ERR_INVALID, "precision must be 0 (bf16) or 1 (fp32-class)");
+  if (m->finalized) return fail(BIOM3_ERR_STATE, "precision must be chosen before biom3_finalize_weights");
+  m->precision = precision;
+  return BIOM3_OK;
+}
+
 int biom3_finalize_weights(biom3_model* m) {
   if (!m) return fail(BIOM3_ERR_INVALID, "null model");
   if (m->finalized) return fail(BIOM3_ERR_STATE, "weights already finalized");
@@ -585,6 +648,30 @@ int biom3_finalize_weights(biom3_model* m) {
     TRY(upload_bf16(m, P + "1.fn.fn.w2.weight", 4 * D * D, m->W2 + j * 4 * D * D));
     TRY(upload_f32(m, P + "1.fn.fn.w2.bias", D, m->b2 + j * D));
   }
+  if (m->precision == 1) {
+    TRY(dev_alloc(m, &m->Wqkv2, depth * 3 * D * 2 * D));
+    TRY(dev_alloc(m, &m->Wo2, depth * D * 2 * D));
+    TRY(dev_alloc(m, &m->W1s, depth * 4 * D * 2 * D));
+    TRY(dev_alloc(m, &m->W2s, depth * D * 8 * D));
+    TRY(dev_alloc(m, &m->ln1_g, depth * D));
+    TRY(dev_alloc(m, &m->ln1_b, depth * D));
+    TRY(dev_alloc(m, &m->ln2_g, depth * D));
+    TRY(dev_alloc(m, &m->ln2_b, depth * D));
+    for (size_t j = 0; j < depth; ++j) {
+      const std::string P = T + "transformer_blocks.0." + std::to_string(j) + ".layers.layers.0.";
+      TRY(upload_split(m, P + "0.fn.to_q.weight", D, D, m->Wqkv2 + (j * 3 + 0) * D * 2 * D));
+      TRY(upload_split(m, P + "0.fn.to_k.weight", D, D, m->Wqkv2 + (j * 3 + 1) * D * 2 * D));
+      TRY(upload_split(m, P + "0.fn.to_v.weight", D, D, m->Wqkv2 + (j * 3 + 2) * D * 2 * D));
+      TRY(upload_split(m, P + "0.fn.to_out.weight", D, D, m->Wo2 + j * D * 2 * D));
+      TRY(upload_split(m, P + "1.fn.fn.w1.weight", 4 * D, D, m->W1s + j * 4 * D * 2 * D));
+      TRY(upload_split(m, P + "1.fn.fn.w2.weight", D, 4 * D, m->W2s + j * D * 8 * D));
+      TRY(upload_f32(m, P + "1.fn.fn.w1.bias", 4 * D, m->b1 + j * 4 * D));
+      TRY(upload_f32(m, P + "0.norm.weight", D, m->ln1_g + j * D));
+      TRY(upload_f32(m, P + "0.norm.bias", D, m->ln1_b + j * D));
+      TRY(upload_f32(m, P + "1.norm.weight", D, m->ln2_g + j * D));
+      TRY(upload_f32(m, P + "1.norm.bias", D, m->ln2_b + j * D));
+    }
+  }
   // time-conditioning table: depends on the step only -> once per model load
   {
     float *te, *h1, *tt, *w0, *b0, *w2, *b2;
@@ -633,6 +720,21 @@ int biom3_finalize_weights(biom3_model* m) {
   CU_OK(cudaMemset(m->ctl, 0, sizeof(k::DecodeCtl)));
   CU_OK(cudaMemset(m->inv_path, 0, M * sizeof(int)));
 
+  if (m->precision == 1) {
+    TRY(dev_alloc(m, &m->a2, M * 2 * D));
+    TRY(dev_alloc(m, &m->hid2, M * 8 * D));
+    TRY(dev_alloc(m, &m->qkv32, M * 3 * D));
+    TRY(dev_alloc(m, &m->hid32, M * 4 * D));
+    TRY(make_tmap(&m->tm_a2, m->a2, M, 2 * D, 128));
+    TRY(make_tmap(&m->tm_hid2, m->hid2, M, 8 * D, 128));
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t box = i ? 256 : 128;
+      TRY(make_tmap(&m->tm_wqkv2[i], m->Wqkv2, depth * 3 * D, 2 * D, box));
+      TRY(make_tmap(&m->tm_wo2[i], m->Wo2, depth * D, 2 * D, box));
+      TRY(make_tmap(&m->tm_w1s[i], m->W1s, depth * 4 * D, 2 * D, box));
+      TRY(make_tmap(&m->tm_w2s[i], m->W2s, depth * D, 8 * D, box));
+    }
+  }
   TRY(make_tmap(&m->tm_a, m->a, M, D, 128));
   TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
   TRY(make_tmap(&m->tm_hid, m->hid, M, 4 * D, 128));
@@ -648,7 +750,7 @@ int biom3_finalize_weights(biom3_model* m) {
   }
 #undef TRY
   m->finalized = true;
-  m->launches_per_step = 2 + int(depth) * 6 + 2 - (c.local_heads == 0 ? int(depth) : 0) -
+  m->launches_per_step = 2 + int(depth) * (m->precision == 1 ? 9 : 6) + 2 - (c.local_heads == 0 ? int(depth) : 0) -
                          (c.heads == c.local_heads ? int(depth) : 0);
   return BIOM3_OK;
 }
@@ -870,6 +972,8 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   if (!A || !W || !out) return fail(BIOM3_ERR_INVALID, "null argument");
   if (block_n != 128 && block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 128 or 256");
   if (M % 128 || N % block_n || K % 64) return fail(BIOM3_ERR_INVALID, "M%128, N%block_n, K%64 must be 0");
+  const int split3 = (pair >> 1) & 1;          // bit 1: A and W are [hi | lo] halves of width 2K (fp32-class schedule)
+  pair &= 1;
   if (pair && (block_n != 256 || M % 256)) return fail(BIOM3_ERR_INVALID, "pair tiling needs block_n == 256 and M % 256 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static cudaDeviceProp prop;
@@ -882,9 +986,10 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   }
   CUtensorMap ta, tb;
   int r;
-  if ((r = make_tmap(&ta, A, M, K, 128))) return r;
-  if ((r = make_tmap(&tb, W, N, K, pair ? block_n / 2 : block_n))) return r;
+  if ((r = make_tmap(&ta, A, M, split3 ? 2 * K : K, 128))) return r;
+  if ((r = make_tmap(&tb, W, N, split3 ? 2 * K : K, pair ? block_n / 2 : block_n))) return r;
   gemm::Params p{};
+  p.split3 = split3;
   p.M = M; p.N = N; p.K = K; p.b_row_offset = 0; p.out = out; p.bias = bias; p.cond = nullptr; p.cond_stride = 0;
   p.L = M; p.H = 1; p.Bsz = 1;
   const int sms = prop.multiProcessorCount;

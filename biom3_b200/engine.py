@@ -4,6 +4,7 @@ memory, streams)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from argparse import Namespace
 from typing import Dict, Optional
 
@@ -27,7 +28,17 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class Engine:
-    def __init__(self, args: Namespace, state_dict: Dict[str, torch.Tensor], device: torch.device, max_batch: int):
+    PRECISIONS = {'bf16': 0, 'fp32': 1}
+
+    def __init__(self, args: Namespace, state_dict: Dict[str, torch.Tensor], device: torch.device, max_batch: int,
+                 precision: Optional[str] = None):
+        """precision: 'bf16' (default) or 'fp32' (fp32-class arithmetic, see biom3_set_precision); when None it is
+        taken from ``args.b200_precision`` or the BIOM3_PRECISION environment variable."""
+        if precision is None:
+            precision = getattr(args, 'b200_precision', None) or os.environ.get('BIOM3_PRECISION', 'bf16')
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise RuntimeError('biom3_b200 needs a CUDA device (sm_100a); there is no CPU path')
         self.lib = _lib.load()
@@ -44,6 +55,7 @@ class Engine:
         _lib.check(self.lib.biom3_create(C.byref(self.cfg), self.dev_index, self.max_batch, C.byref(h)))
         self.handle = h
         try:
+            _lib.check(self.lib.biom3_set_precision(self.handle, self.PRECISIONS[precision]))
             for key, t in state_dict.items():
                 t = t.detach().to('cpu', torch.float32).contiguous()
                 _lib.check(self.lib.biom3_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()), t.numel()))
@@ -149,15 +161,18 @@ def unmask_(state: torch.Tensor, tok: torch.Tensor, path: torch.Tensor, step: in
 
 
 def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int,
-              out: Optional[torch.Tensor] = None, pair: bool = False) -> torch.Tensor:
-    """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h)."""
+              out: Optional[torch.Tensor] = None, pair: bool = False, split3: bool = False) -> torch.Tensor:
+    """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h).
+    split3: A and W are [hi | lo] bf16 halves, [M, 2K] and [N, 2K] (the fp32-class K schedule)."""
     lib = _lib.load()
     M, K = A.shape
     N = W.shape[0]
+    if split3:
+        K //= 2
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
     with torch.cuda.device(A.device):
-        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair),
+        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
     return out
 

@@ -55,6 +55,13 @@ const char* biom3_last_error(void);
 int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t numel);
 int biom3_finalize_weights(biom3_model* m);
 
+/* Arithmetic of the forward: 0 = bf16 operands, fp32 accumulate and fp32 residual stream (default; logits within
+ * 1e-2 relative of the fp32 reference); 1 = fp32-class: fp32 activations, every contraction as a three-product
+ * bf16 split (hi.hi + hi.lo + lo.hi, fp32 accumulate) on the same tcgen05 GEMM, fp32 attention / LayerNorm / erf
+ * GELU (logits within 1e-4 relative).  The reference runs fp32 without autocast at inference
+ * (Stage3_source/cond_diff_transformer_layer.py:149-176).  Must be called before biom3_finalize_weights(). */
+int biom3_set_precision(biom3_model* m, int precision);
+
 /* Replaces DiffTransformer.forward(x, t, y_c) (cond_diff_transformer_layer.py:149-176, 249-251).
  * x: device int64 [B][L]; t: device int64 [B]; y_c: device fp32 [B][text_emb_dim];
  * logits: device fp32 [B][num_classes][L] (the reference's permuted layout). */
@@ -89,8 +96,9 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
 
 /* Unit-test hook for the tcgen05 GEMM: C = A . W^T with one of the fused epilogues.
  * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
- * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256.  pair != 0: CTA-pair (cta_group::2)
- * tiling, 256 x 256 tiles (needs block_n == 256, M % 256 == 0). */
+ * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256.  pair bit 0: CTA-pair (cta_group::2)
+ * tiling, 256 x 256 tiles (needs block_n == 256, M % 256 == 0); pair bit 1: fp32-class K schedule, A and W are
+ * [hi | lo] bf16 halves of width 2K and the result is hi.hi + hi.lo + lo.hi. */
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
                     int block_n, int pair, void* stream);
 

@@ -373,3 +373,72 @@ def test_attention_kernels_vs_fp32_reference(B, H, L, NL, variant):
     out = engine.attention_test(qkv.cuda(), NL, variant).float().cpu()
     assert rel_err(out[:, :NL * 32], ref[:, :NL * 32]) < 8e-3
     assert rel_err(out[:, NL * 32:], ref[:, NL * 32:]) < 8e-3
+
+
+# ---------------------------------------------------------------- fp32-class mode (biom3_set_precision(m, 1))
+FP32_TOL = 1e-4          # BASELINE.json north_star: logits within 1e-4 relative in fp32
+
+
+def test_gemm_split3_matches_fp32_product():
+    """The three-product bf16 split on the tcgen05 GEMM reproduces an fp32 x fp32 product to ~1e-5."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 512, 768, 512
+    A = torch.randn(M, K, generator=g) * 0.5
+    W = torch.randn(N, K, generator=g) * 0.1
+
+    def split(x):
+        hi = x.bfloat16()
+        return torch.cat([hi, (x - hi.float()).bfloat16()], 1).contiguous()
+
+    ref = A.double() @ W.double().t()
+    for bn, pair in ((128, False), (256, False), (256, True)):
+        out = engine.gemm_test(split(A).cuda(), split(W).cuda(), None, 4, bn, pair=pair, split3=True).cpu()
+        assert rel_err(out, ref) < 2e-5, (bn, pair)
+
+
+@pytest.mark.parametrize('name', ['gpu_small_b3', 'gpu_resume_b2', 'full_forward_b2'])
+def test_fp32_mode_forward_vs_reference_fixture(name):
+    from biom3_b200.engine import Engine
+    z = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    over = ast.literal_eval(str(z['overrides'])) if 'overrides' in z.files else {}
+    args = synthetic.stage3_args(**over)
+    sd = synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=name != 'full_forward_b2')
+    B = z['x'].shape[0]
+    eng = Engine(args, sd, torch.device('cuda'), B, precision='fp32')
+    got = eng.forward(torch.from_numpy(z['x'].astype(np.int64)).cuda(), torch.from_numpy(z['t'].astype(np.int64)).cuda(),
+                      torch.from_numpy(z['z_c']).cuda()).cpu()
+    assert rel_err(got, torch.from_numpy(z['logits'])) < FP32_TOL
+
+
+@pytest.mark.parametrize('name', ['gpu_small_b3', 'gpu_resume_b2'])
+def test_fp32_mode_decode_vs_reference_fixture(name):
+    """fp32-class decode against the real reference loop: strict identity, no margin allowance."""
+    from biom3_b200.engine import Engine
+    from oracle import sampler as osamp
+    z = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    over = ast.literal_eval(str(z['overrides']))
+    B, L = z['path'].shape
+    T = z['traj'].shape[0]
+    start = int(z['start'])
+    args = synthetic.stage3_args(**over)
+    sd = synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True)
+    eng = Engine(args, sd, torch.device('cuda'), B, precision='fp32')
+    noise = osamp.reference_noise_stream(int(z['noise_seed']), T, B, L, 29)
+    state0 = torch.from_numpy(z['state0'].astype(np.int64)).cuda() if start > 0 else None
+    tokens, traj = eng.decode(torch.from_numpy(z['z_c']).cuda(), torch.from_numpy(z['path'].astype(np.int64)).cuda(),
+                              state0=state0, start_step=start, num_steps=T, noise=noise.cuda(), want_traj=True)
+    assert np.array_equal(traj.cpu().numpy().astype(np.int64), z['traj'][:, :, 0].astype(np.int64))
+    assert np.array_equal(tokens.cpu().numpy(), z['traj'][-1, :, 0])
+
+
+def test_precision_is_fixed_at_finalize():
+    import ctypes as C
+    from biom3_b200 import _lib
+    args, sd, eng, _ = make(SMALL, 1)
+    assert eng.precision == 'bf16'
+    assert eng.lib.biom3_set_precision(eng.handle, 1) == -3          # BIOM3_ERR_STATE after finalize
+    assert b'before biom3_finalize_weights' in eng.lib.biom3_last_error()
+    with pytest.raises(ValueError):
+        from biom3_b200.engine import Engine
+        Engine(args, sd, torch.device('cuda'), 1, precision='fp64')
