@@ -1,4 +1,5 @@
-"""Mirror of the on-path part of /root/reference/Stage3_source/sampling_analysis.py.
+"""Mirror of /root/reference/Stage3_source/sampling_analysis.py: the batch sampler on the hot path plus the
+partial-start / inpainting entry points around it.
 
 ``batch_generate_denoised_sampled`` (:204-265) keeps the reference signature and return contract
 but runs the whole step loop on the device (one C-ABI call, no host round trip per step); the
@@ -13,6 +14,53 @@ import numpy as np
 import torch
 
 from . import transformer_training_helper as train_helper
+
+
+@torch.no_grad()
+def cond_autocomplete_real_samples(model, args, realization, y_c, idx):
+    """One-shot fill-in of the masked positions (:21-61): draws a random path per sample, masks every position
+    whose path index is >= idx, runs ONE forward and scores the true tokens.  Returns, like the reference,
+    (OneHotCategorical, probs.cpu() [B, C, L], masked tokens, true tokens, log_prob [B, L], paths, mask)."""
+    model.eval()
+    bs, channel, seq_length = realization.size()
+    sampled_random_path = train_helper.sample_random_path(bs, seq_length, device=args.device)
+    idx = idx.to(sampled_random_path.device)
+    random_path_mask = train_helper.create_mask_at_random_path_index(sampled_random_path, idx, bs, seq_length)
+    real_tokens, bs, seq_length = train_helper.create_token_labels(args, realization.to(sampled_random_path.device))
+    real_token_masked = train_helper.mask_realizations(real_tokens, random_path_mask)
+    conditional_prob, probs = train_helper.cond_predict_conditional_prob(model, real_token_masked, y_c, idx, args)
+    log_prob = train_helper.log_prob_of_realization(args, conditional_prob, real_tokens.to(probs.device))
+    return (conditional_prob, probs.cpu(), real_token_masked.cpu(), real_tokens.cpu(), log_prob.cpu(),
+            sampled_random_path.cpu(), random_path_mask.cpu())
+
+
+def extract_samples_with_labels(dataloader, target_labels: int, total_num: int, pad_included: bool = False) -> dict:
+    """First ``total_num`` samples of a (data, labels) loader whose label equals ``target_labels`` (:65-93); ids
+    shift by one to make room for the absorbing state unless the data already includes it."""
+    extracted = {'sample': [], 'label': []}
+    for data, labels in dataloader:
+        for i, label in enumerate(labels):
+            if label.item() == target_labels:
+                if not pad_included:
+                    data[i] += 1
+                extracted['sample'].append(data[i])
+                extracted['label'].append(label)
+                if len(extracted['label']) == total_num:
+                    return extracted
+    return extracted
+
+
+def corrupt_samples(args, realization, perc: float):
+    """Mask all but the first ``perc`` of a random path (:96-119): returns (masked tokens [B, L], paths [B, L],
+    idx = int(diffusion_steps * perc) as a 1-element tensor) — the (state, path, start step) triple a resumed
+    decode takes."""
+    bs, channels, seq_length = realization.size()
+    idx = (args.diffusion_steps * torch.Tensor([perc])).to(int).to(args.device)
+    sampled_random_path = train_helper.sample_random_path(bs, seq_length, device=args.device)
+    random_path_mask = train_helper.create_mask_at_random_path_index(sampled_random_path, idx, bs, seq_length)
+    real_tokens, bs, seq_length = train_helper.create_token_labels(args, realization.to(sampled_random_path.device))
+    real_token_masked = train_helper.mask_realizations(real_tokens, random_path_mask)
+    return real_token_masked, sampled_random_path, idx
 
 
 @torch.no_grad()
@@ -100,6 +148,21 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
     host.copy_(traj, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     return _LazyStates(host.numpy()), _LazyTimes(start, steps, B)
+
+
+@torch.no_grad()
+def generate_denoised_sampled(args, model, extract_digit_samples, extract_time, extract_digit_label, sampling_path,
+                              noise: Optional[torch.Tensor] = None, seed: Optional[int] = None):
+    """Single-sequence resume loop (:152-201).  The reference's indexing (``state[0, current_location]`` with a
+    [B, L] mask) only works for one sequence, and so does this: inputs [1, L] / [1] / [1, E] / [1, L].  Returns
+    (list of np.int64 [1, 1, L] states, list of 0-d float32 step indices), device loop as in the batch call."""
+    if extract_digit_samples.size(0) != 1 or sampling_path.size(0) != 1:
+        raise IndexError('generate_denoised_sampled handles one sequence (the reference mask indexing is [1, L])')
+    states, times = batch_generate_denoised_sampled(
+        args, model, extract_digit_samples, torch.as_tensor(extract_time).reshape(1).long(), extract_digit_label,
+        sampling_path, noise=noise, seed=seed)
+    start = int(torch.as_tensor(extract_time).reshape(-1)[0].item())
+    return states, [np.array(start + i, dtype=np.float32) for i in range(len(states))]
 
 
 def convert_num_to_chars(tokenizer, num_seq):

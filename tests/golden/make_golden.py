@@ -183,11 +183,72 @@ def facilitator_case():
     print('facilitator_p16', tuple(z_c.shape), sorted(sd.keys()))
 
 
+def inpaint_case(mod, samp, helper):
+    """the partial-start / inpainting entry points of the REAL reference
+    (sampling_analysis.py:21-61 cond_autocomplete_real_samples, :96-119 corrupt_samples, :152-201
+    generate_denoised_sampled) and the mask helpers they call (transformer_training_helper.py:16-44, 187-232),
+    at the GPU-testable small shape.  RNG: torch's global CPU generator, seeded right before each call."""
+    over = CASES['gpu_small_b3'][0]
+    args = synthetic.stage3_args(**over)
+    args.task = 'proteins'
+    L, C, B = args.diffusion_steps, args.num_classes, 3
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    model = mod.get_model(args, (args.image_size, args.image_size), C)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    g = torch.Generator().manual_seed(40)
+    realization = torch.randint(0, C - 1, (B, 1, L), generator=g)       # raw ids; tokens are ids + 1 (:203)
+    z_c = synthetic.synthetic_z_c(B, args.text_emb_dim, seed=12)
+    out = {}
+    torch.manual_seed(41)
+    masked, path, idx = samp.corrupt_samples(args, realization, 0.625)
+    out.update(corrupt_masked=masked.numpy(), corrupt_path=path.numpy(), corrupt_idx=idx.numpy())
+    torch.manual_seed(42)
+    idx2 = torch.tensor([[40], [128], [200]])
+    dist, probs, real_masked, real_tokens, log_prob, path2, mask2 = samp.cond_autocomplete_real_samples(
+        model, args, realization, z_c, idx2)
+    out.update(auto_idx=idx2.numpy(), auto_probs=probs.numpy(), auto_masked=real_masked.numpy(),
+               auto_tokens=real_tokens.numpy(), auto_log_prob=log_prob.numpy(), auto_path=path2.numpy(),
+               auto_mask=mask2.numpy())
+    # single-sample resume loop from the corrupted state of sample 0 (start = corrupt idx = 160)
+    seen_x = []
+
+    class Recorder(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x, t, y_c):
+            seen_x.append(x.detach().clone())
+            return self.inner(x=x, t=t, y_c=y_c)
+
+    start = int(idx.item())
+    torch.manual_seed(43)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):      # the reference prints a shape every step (:177)
+        states, times = samp.generate_denoised_sampled(
+            args=args, model=Recorder(model).eval(), extract_digit_samples=masked[0:1].clone().float(),
+            extract_time=torch.tensor([start]), extract_digit_label=z_c[0:1], sampling_path=path[0:1])
+    snaps = [sx.numpy()[:, None, :] for sx in seen_x[1:]] + [states[-1]]
+    out.update(single_start=np.int32(start), single_noise_seed=np.int32(43),
+               single_traj=np.stack(snaps).astype(np.uint8), single_len=np.int32(len(states)),
+               single_state_shape=np.array(states[0].shape), single_time_dtype=np.array(str(times[0].dtype)),
+               single_time_shape=np.array(times[0].shape, dtype=np.int64))
+    np.savez_compressed(os.path.join(HERE, 'inpaint_b3.npz'), realization=realization.numpy(), z_c=z_c.numpy(),
+                        weight_seed=np.int32(11), overrides=np.array(repr(over)), **out)
+    print('inpaint_b3', {k: getattr(v, 'shape', v) for k, v in out.items()})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     mod, samp, helper, ani = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'inpaint':
+        inpaint_case(mod, samp, helper)
+        return
     for name in CASES:
         run_case(mod, samp, name)
+    inpaint_case(mod, samp, helper)
     full_config_forward(mod)
     facilitator_case()
     # key schema of the real model at the stage3_config.json shape

@@ -146,3 +146,46 @@ def test_facilitator_mirror_keys():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match='no CPU path'):
             m(torch.zeros(2, 512))
+
+
+def test_inpainting_helpers_match_real_reference_fixture():
+    """corrupt_samples and the mask / token helpers against tests/golden/inpaint_b3.npz (the REAL reference run with
+    the same global seed); host logic only, no device."""
+    import ast
+    import numpy as np
+    from biom3_b200.Stage3_source import sampling_analysis as samp
+    from biom3_b200.Stage3_source import transformer_training_helper as th
+    z = np.load(os.path.join(GOLDEN, 'inpaint_b3.npz'))
+    args = synthetic.stage3_args(**ast.literal_eval(str(z['overrides'])))
+    args.task = 'proteins'
+    real = torch.from_numpy(z['realization'])
+    torch.manual_seed(41)
+    masked, path, idx = samp.corrupt_samples(args, real, 0.625)
+    assert np.array_equal(masked.numpy(), z['corrupt_masked'])
+    assert np.array_equal(path.numpy(), z['corrupt_path'])
+    assert np.array_equal(idx.numpy(), z['corrupt_idx']) and idx.shape == (1,)
+    # the state a resumed decode starts from: tokens where path < idx, mask (0) elsewhere
+    tokens, bs, L = th.create_token_labels(args, real)
+    assert (bs, L) == (3, 256) and torch.equal(tokens, real.squeeze(1) + 1)
+    assert torch.equal(masked == 0, path >= idx)
+    assert torch.equal(masked[path < idx], tokens[path < idx])
+    # per-sample idx [B, 1] as cond_autocomplete_real_samples passes it
+    m2 = th.create_mask_at_random_path_index(torch.from_numpy(z['auto_path']), torch.from_numpy(z['auto_idx']), 3, L)
+    assert np.array_equal(m2.numpy(), z['auto_mask'])
+    assert np.array_equal(th.mask_realizations(tokens, m2).numpy(), z['auto_masked'])
+    assert torch.equal(th.create_sampling_location_mask(path, idx, 3, L).sum(1), torch.ones(3, dtype=torch.long))
+    assert torch.equal(th.create_mask_at_future_path_index(path, idx, 3, L).sum(1), torch.full((3,), L - 161))
+    args.task = 'MNIST'
+    t2, _, _ = th.create_token_labels(args, torch.tensor([[[0, 1, 1, 0]]]))
+    assert t2.tolist() == [[1, 2, 2, 1]]
+    lp = th.log_prob_of_unsampled_locations(torch.full((2, 4), -1.0), torch.tensor([[1, 0, 0, 1], [0, 0, 0, 0]]))
+    assert lp.tolist() == [-2.0, -4.0]
+
+
+def test_extract_samples_with_labels():
+    from biom3_b200.Stage3_source import sampling_analysis as samp
+    data = [(torch.arange(12).reshape(4, 3), torch.tensor([0, 1, 1, 0])), (torch.zeros(2, 3, dtype=torch.long), torch.tensor([1, 1]))]
+    out = samp.extract_samples_with_labels(data, 1, 3)
+    assert len(out['sample']) == 3 and out['sample'][0].tolist() == [4, 5, 6] and out['sample'][2].tolist() == [1, 1, 1]
+    out = samp.extract_samples_with_labels([(torch.arange(6).reshape(2, 3), torch.tensor([1, 0]))], 1, 5, pad_included=True)
+    assert len(out['sample']) == 1 and out['sample'][0].tolist() == [0, 1, 2]

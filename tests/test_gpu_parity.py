@@ -442,3 +442,58 @@ def test_precision_is_fixed_at_finalize():
     with pytest.raises(ValueError):
         from biom3_b200.engine import Engine
         Engine(args, sd, torch.device('cuda'), 1, precision='fp64')
+
+
+# ---------------------------------------------------------------- inpainting / partial-start entry points
+def _inpaint_model(precision):
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+    z = np.load(os.path.join(GOLDEN, 'inpaint_b3.npz'))
+    args = synthetic.stage3_args(**ast.literal_eval(str(z['overrides'])))
+    args.device = 'cuda'
+    args.task = 'proteins'
+    args.b200_precision = precision
+    model = mod.get_model(args, (32, 32), 29)
+    model.load_state_dict(synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True))
+    return z, args, model.eval().to('cuda')
+
+
+@pytest.mark.parametrize('precision,ptol,ltol', [('bf16', 2e-3, 3e-2), ('fp32', 2e-5, 2e-4)])
+def test_cond_autocomplete_real_samples_vs_reference_fixture(precision, ptol, ltol):
+    """One-shot inpainting through the drop-in call against the REAL reference run (same global seed): paths, masks
+    and tokens identical; probabilities and per-position log-probs within the mode's tolerance."""
+    from biom3_b200.Stage3_source import sampling_analysis as samp
+    z, args, model = _inpaint_model(precision)
+    torch.manual_seed(42)
+    dist_, probs, masked, tokens, log_prob, path, mask = samp.cond_autocomplete_real_samples(
+        model, args, torch.from_numpy(z['realization']), torch.from_numpy(z['z_c']), torch.from_numpy(z['auto_idx']))
+    assert np.array_equal(path.numpy(), z['auto_path']) and np.array_equal(mask.numpy(), z['auto_mask'])
+    assert np.array_equal(masked.numpy(), z['auto_masked']) and np.array_equal(tokens.numpy(), z['auto_tokens'])
+    assert probs.device.type == 'cpu' and probs.shape == z['auto_probs'].shape
+    assert np.abs(probs.numpy() - z['auto_probs']).max() < ptol
+    assert np.abs(log_prob.numpy() - z['auto_log_prob']).max() < ltol
+    assert dist_.sample().shape == (3, 256, 29)
+
+
+def test_generate_denoised_sampled_single_sequence_vs_reference_fixture():
+    """corrupt_samples -> generate_denoised_sampled (resume of ONE sequence from step 160) against the real loop."""
+    from biom3_b200.Stage3_source import sampling_analysis as samp
+    from oracle import sampler as osamp
+    z, args, model = _inpaint_model('bf16')
+    torch.manual_seed(41)
+    masked, path, idx = samp.corrupt_samples(args, torch.from_numpy(z['realization']), 0.625)
+    assert np.array_equal(masked.cpu().numpy(), z['corrupt_masked']) and np.array_equal(path.cpu().numpy(), z['corrupt_path'])
+    start = int(idx.item())
+    assert start == int(z['single_start']) == 160
+    T = int(z['single_len'])
+    noise = osamp.reference_noise_stream(int(z['single_noise_seed']), T, 1, 256, 29)
+    states, times = samp.generate_denoised_sampled(
+        args=args, model=model, extract_digit_samples=masked[0:1].float(), extract_time=torch.tensor([start]),
+        extract_digit_label=torch.from_numpy(z['z_c'])[0:1], sampling_path=path[0:1], noise=noise)
+    assert len(states) == T == len(times)
+    assert states[0].shape == tuple(z['single_state_shape']) and states[0].dtype == np.int64
+    assert str(times[0].dtype) == str(z['single_time_dtype']) and times[0].shape == () and float(times[3]) == start + 3
+    np.testing.assert_array_equal(np.stack(list(states)), z['single_traj'].astype(np.int64))
+    with pytest.raises(IndexError):
+        samp.generate_denoised_sampled(args=args, model=model, extract_digit_samples=masked.float(),
+                                       extract_time=torch.tensor([start]), extract_digit_label=torch.from_numpy(z['z_c']),
+                                       sampling_path=path)
