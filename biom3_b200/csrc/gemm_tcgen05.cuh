@@ -83,14 +83,15 @@ struct SmemLayout {
 // erf-GELU, x * Phi(x), evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))): the three coefficients are a
 // least-squares fit to the exact erf form (max abs error 3.0e-5 on [-8, 8], below the bf16 rounding of the
 // stored result); one MUFU.TANH + 6 FP32 ops instead of erff()'s ~30, so the FF1 epilogue keeps up with the MMAs.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);      // beyond +-8 the tanh argument saturates anyway
-  const float x2 = xc * xc;
-  const float poly = fmaf(fmaf(-3.58732362e-4f, x2, 3.70503451e-2f), x2, 7.97458471e-1f);
+// The argument is h = x / 2 (the caller folds the 1/2 into its scale vectors): with g = h^2 clamped to 16 (|x| <= 8;
+// beyond that the tanh saturates and the polynomial, whose x^4 coefficient is negative, must not change sign)
+//   gelu = h + h * tanh(h * (2a + 8b g + 32c g^2)).
+__device__ __forceinline__ float gelu_erf_half(float h) {
+  const float g = fminf(h * h, 16.0f);
+  const float poly = fmaf(fmaf(32.0f * -3.58732362e-4f, g, 8.0f * 3.70503451e-2f), g, 2.0f * 7.97458471e-1f);
   float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(xc * poly));
-  const float hx = 0.5f * x;
-  return fmaf(hx, th, hx);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h * poly));
+  return fmaf(h, th, h);
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -169,7 +170,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
         const int n0 = (tile % n_tiles) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
           // split3: blocks [0, nk) A_hi.W_hi, [nk, 2nk) A_hi.W_lo, [2nk, 3nk) A_lo.W_hi
@@ -195,7 +196,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        ptx::mbar_wait(&acc_empty[as], aphase ^ 1);
+        ptx::mbar_wait_parked(&acc_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -237,6 +238,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       return reinterpret_cast<float*>(p.out) + size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN +
              col_half * COLS_PER_WARP + 4 * ch;
     };
+    // Hand an accumulator stage back to the MMA warp (leader CTA) as soon as this warp's last TMEM load of the tile
+    // has landed in registers; the math and the stores of that last chunk then overlap the next-but-one mainloop.
+    auto release_acc = [&](uint32_t as) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG2 && !leader) ptx::mbar_arrive_remote(&acc_empty[as], 0);
+        else ptx::mbar_arrive(&acc_empty[as]);
+      }
+    };
     float4 res[2][8];                                  // residual rows, double buffered one chunk ahead
     if constexpr (EPI == EPI_BIAS_RESID_F32) {
       if (worker < num_tiles) {
@@ -257,7 +268,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
 
       if (p.debug_skip == 1 || p.debug_skip == 2) {
-        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::mbar_wait_parked(&acc_full[as], aphase);
         ptx::tc_fence_after();
         if (p.debug_skip == 1) {
           uint32_t r[32];
@@ -267,6 +278,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           if (r[lane] == 0x7fc12345u) reinterpret_cast<float*>(p.out)[0] = 1.f;   // keep the loads alive
         }
+        release_acc(as);
       } else if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_STORE_F32) {
         // fp32 path.  Read phase: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte column
         // group lane%8): every global access is 4 full 128-byte lines per warp instruction.  The residual of
@@ -288,7 +300,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
-        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::mbar_wait_parked(&acc_full[as], aphase);
         ptx::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -344,6 +356,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
+        release_acc(as);           // (an earlier release costs registers this 168-register path does not have)
       } else {
         // bf16 path: thread = row while the fused math runs, then a 32 x 64-byte block is transposed
         // through smem so each warp store instruction writes 8 rows x 64 contiguous bytes.
@@ -361,8 +374,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (p.ln_stats) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + nbase) + vl);
           __syncwarp();
           if (lane < COLS_PER_WARP / 4) {
+            constexpr float tsc = EPI == EPI_BIAS_GELU_BF16 ? 0.5f : 1.0f;   // the GELU epilogue works on x / 2
             st_shared_v4(cvs + lane * 16, __float_as_uint(s4.x), __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
-            st_shared_v4(cvs + CV_HALF + lane * 16, __float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
+            st_shared_v4(cvs + CV_HALF + lane * 16, __float_as_uint(t4.x * tsc), __float_as_uint(t4.y * tsc),
+                         __float_as_uint(t4.z * tsc), __float_as_uint(t4.w * tsc));
           }
           if (p.ln_stats) {
             const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + size_t(rbase + lane) * p.ln_parts;
@@ -377,6 +392,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           __syncwarp();
         }
+        if constexpr (EPI == EPI_BIAS_GELU_BF16) rstd *= 0.5f;   // x / 2 = acc * (rstd / 2) + (-mean * rstd / 2) * s[n] + t[n] / 2
         const float nm = -mean * rstd;
         // output addressing, hoisted out of the chunk loop (a warp's 128 columns never straddle q/k/v or a sample)
         __nv_bfloat16* dst0;
@@ -398,7 +414,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tma_c0 = 0;
           tma_c1 = (((nbase / D) * p.Bsz + bidx) * p.H + ((nbase % D) >> 5)) * p.L + rbase % p.L;
         }
-        ptx::mbar_wait(&acc_full[as], aphase);
+        ptx::mbar_wait_parked(&acc_full[as], aphase);
         ptx::tc_fence_after();
         uint32_t r[2][32];                                 // TMEM loads run one chunk ahead of the math
         ptx::tmem_ld_32x32(t_row, r[0]);
@@ -406,6 +422,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int c = 0; c < NCH; ++c) {
           ptx::tmem_ld_wait();
           if (c + 1 < NCH) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
+          else release_acc(as);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
@@ -423,7 +440,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if constexpr (EPI == EPI_BIAS_GELU_BF16) {
             if (p.debug_skip != 5) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
             }
           }
           if (p.tma_store) {
@@ -457,13 +474,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           __syncwarp();
         }
-      }
-      // accumulator stage drained: hand it back to the MMA warp (which lives in the leader CTA)
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG2 && !leader) ptx::mbar_arrive_remote(&acc_empty[as], 0);
-        else ptx::mbar_arrive(&acc_empty[as]);
       }
     }
   }

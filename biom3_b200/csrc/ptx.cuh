@@ -60,6 +60,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, for waits that are expected to be long (a whole tile): the suspend-time hint lets the hardware park the
+// warp until the phase completes instead of re-polling every few dozen cycles, which hands the issue slots the
+// polling would burn to the warps that have work.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+  } while (!ok);
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
