@@ -248,12 +248,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         else ptx::mbar_arrive(&acc_empty[as]);
       }
     };
-    float4 res[2][8];                                  // residual rows, double buffered one chunk ahead
+    // Residual rows of the chunk being processed; each slot is reloaded with the NEXT chunk's value (or the next
+    // tile's first chunk) right after it is consumed, so every load has a full chunk period to land while only 32
+    // registers hold prefetched data (a second buffer pushed this 168-register path into spills, and a spilled
+    // prefetch register waits for its load at the spill store).
+    float4 res[8];
     if constexpr (EPI == EPI_BIAS_RESID_F32) {
       if (worker < num_tiles) {
         const float* g0 = tile_gbase(worker);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) res[0][j] = *reinterpret_cast<const float4*>(g0 + size_t(4 * j) * p.N);
+        for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(g0 + size_t(4 * j) * p.N);
       }
     }
     uint32_t it = 0;
@@ -304,13 +308,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            const float* gn = (c + 1 < NCH) ? gbase + (c + 1) * 32 : gnext;
-            if (gn) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(gn + size_t(4 * j) * p.N);
-            }
-          }
+          const float* gn = (c + 1 < NCH) ? gbase + (c + 1) * 32 : gnext;
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
@@ -326,7 +324,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint4 a4 = ld_shared_v4(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
             if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              const float4 rv = res[c & 1][j];
+              const float4 rv = res[j];
+              if (gn) res[j] = *reinterpret_cast<const float4*>(gn + size_t(4 * j) * p.N);
               o.x += rv.x + add.x; o.y += rv.y + add.y; o.z += rv.z + add.z; o.w += rv.w + add.w;
             }
             *reinterpret_cast<float4*>(gbase + size_t(4 * j) * p.N + c * 32) = o;
