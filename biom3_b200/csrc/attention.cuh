@@ -36,6 +36,7 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(ro
 __global__ void __launch_bounds__(256, LOCAL_CH == 32 ? 4 : 3)
 local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
                        float scale_log2e, int reverse) {
+  ptx::pdl_sync();
   // reverse: walk (sample, window) last-to-first so the QKV rows written last (still in L2) are read first
   const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,
             b = reverse ? int(gridDim.z) - 1 - int(blockIdx.z) : int(blockIdx.z);
@@ -187,6 +188,7 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
 __global__ void __launch_bounds__(128)
 linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
                         int NL, float q_scale, int reverse) {
+  ptx::pdl_sync();
   const int h = NL + blockIdx.x, b = reverse ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
   const size_t head_stride = size_t(L) * DH;
   const size_t plane = size_t(B) * H * head_stride;
@@ -421,6 +423,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
 __global__ void __launch_bounds__(256)
 local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
                           int L, float scale_log2e, int reverse) {
+  ptx::pdl_sync();
   // 8 warps: two threads per query row.  Thread (row = tid & 127, half = tid >> 7) owns keys [64*half, +64) of each
   // 128-key window (one K-major SW128 block of P) and output features [16*half, +16).
   const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,

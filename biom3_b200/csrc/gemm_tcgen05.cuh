@@ -160,6 +160,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  ptx::pdl_sync();          // everything above touched only this CTA's smem / TMEM
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)

@@ -8,6 +8,7 @@
 //   softmax(dim=1) + OneHotCategorical                    /root/reference/Stage3_source/transformer_training_helper.py:443-449
 //   sample every position, argmax, unmask write           /root/reference/Stage3_source/sampling_analysis.py:251-256
 #pragma once
+#include <climits>
 #include "ptx.cuh"
 
 namespace k {
@@ -66,6 +67,7 @@ __device__ __forceinline__ void ln_row_store(const float4 (&v)[MAXV], int nv, in
 __global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* __restrict__ Y,
                                   const int* __restrict__ t_per_sample, const DecodeCtl* __restrict__ ctl,
                                   float* __restrict__ cvec, int B, int JD) {
+  ptx::pdl_sync();
   const int b = blockIdx.y;
   const int t = t_per_sample ? t_per_sample[b] : ctl->step;
   const float4* tt = reinterpret_cast<const float4*>(Ttab + size_t(t) * JD);
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256)
 embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
              const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride, float* __restrict__ u,
              __nv_bfloat16* __restrict__ ub, float* __restrict__ stats, int parts, int rows, int L, int W, int D) {
+  ptx::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
@@ -194,6 +197,7 @@ struct HeadArgs {
 
 __global__ void __launch_bounds__(256)
 head_kernel(const HeadArgs a) {
+  ptx::pdl_sync();
   extern __shared__ float s_w[];                 // [C][D] staged vocab head
   for (int i = threadIdx.x; i < a.C * a.D / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(a.w_out) + i);
@@ -315,16 +319,88 @@ sample_all_kernel(const float* __restrict__ logits, const float* __restrict__ no
   tok[i] = bi;
 }
 
-// K12: the reference unmask write.  For every sample b' and every sample b of its group:
-// state[b'][loc[b]] = tok[b'][loc[b]], loc[b] = position with path[b][loc] == step.
-__global__ void unmask_kernel(const long long* __restrict__ tok, const int* __restrict__ inv_path,
-                              long long* __restrict__ state, int B, int L, int group, int step) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * group) return;
-  const int b = i / group;
-  const int src = (b / group) * group + (i % group);
-  const int l = inv_path[size_t(src) * L + step];
-  state[size_t(b) * L + l] = tok[size_t(b) * L + l];
+// Same draw, staged: one block = 256 consecutive positions of one sequence (needs L % 256 == 0).  The block's logits
+// tile [C][256] and its noise block [256][C] (contiguous in memory) are copied to shared memory with 16-byte
+// cp.async, so every global access is a full coalesced line and ~2 KB * C per block is in flight without holding
+// registers; the per-position math then reads shared memory conflict-free (logits: consecutive threads, consecutive
+// words; noise: stride C words, odd for C = 29).  Three blocks per SM overlap one block's loads with another's math
+// (29 exp + 87 IEEE divides per position: the kernel is as much ALU as HBM time; a persistent two-stage version with
+// fewer resident warps measured slower).  Same operation order as sample_all_kernel: bit-identical tokens.
+constexpr int SAMPLE_TILE = 256;
+__global__ void __launch_bounds__(SAMPLE_TILE)
+sample_all_tiled_kernel(const float* __restrict__ logits, const float* __restrict__ noise, long long* __restrict__ tok,
+                        int B, int L, int C) {
+  extern __shared__ __align__(16) float s_samp[];
+  float* sl = s_samp;                           // [C][256]
+  float* sn = s_samp + C * SAMPLE_TILE;         // [256][C]
+  const int tiles_per_row = L / SAMPLE_TILE;
+  const int b = blockIdx.x / tiles_per_row, l0 = (blockIdx.x % tiles_per_row) * SAMPLE_TILE;
+  const size_t i0 = size_t(b) * L + l0;
+  const float* lg = logits + size_t(b) * C * L + l0;
+  const float* qn = noise + i0 * C;
+  for (int v = threadIdx.x; v < C * (SAMPLE_TILE / 4); v += SAMPLE_TILE) {
+    const int c = v / (SAMPLE_TILE / 4), part = v % (SAMPLE_TILE / 4);
+    ptx::cp_async_16(ptx::smem_u32(sl + c * SAMPLE_TILE + part * 4), lg + size_t(c) * L + part * 4);
+    ptx::cp_async_16(ptx::smem_u32(sn + v * 4), qn + size_t(v) * 4);
+  }
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
+  __syncthreads();
+  const int t = threadIdx.x;
+  float x[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = sl[c * SAMPLE_TILE + t];
+      mx = fmaxf(mx, x[c]);
+    }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = expf(x[c] - mx);
+      sum += x[c];
+    }
+  float s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      x[c] = x[c] / sum;
+      s2 += x[c];
+    }
+  float best = -INFINITY;
+  int bi = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < C) {
+      const float r = (x[c] / s2) / sn[t * C + c];
+      if (r > best) { best = r; bi = c; }
+    }
+  tok[i0 + t] = bi;
+}
+
+// K12: the reference unmask write in one launch, no scratch.  Block = one source sample b: find loc[b] = the first
+// position with path[b][loc] == step (argmax of the match mask, sampling_analysis.py:254; 0 when nothing matches, as
+// argmax of an all-false mask is), then for every sample b' of b's group: state[b'][loc[b]] = tok[b'][loc[b]].
+__global__ void __launch_bounds__(256)
+unmask_scan_kernel(const long long* __restrict__ tok, const long long* __restrict__ path, long long* __restrict__ state,
+                   int B, int L, int group, int step) {
+  __shared__ int s_loc;
+  const int src = blockIdx.x;
+  if (threadIdx.x == 0) s_loc = INT_MAX;
+  __syncthreads();
+  int best = INT_MAX;
+  for (int l = threadIdx.x; l < L; l += blockDim.x)
+    if (path[size_t(src) * L + l] == step) best = min(best, l);
+  if (best != INT_MAX) atomicMin(&s_loc, best);
+  __syncthreads();
+  const int loc = s_loc == INT_MAX ? 0 : s_loc;
+  const int g0 = (src / group) * group;
+  for (int i = threadIdx.x; i < group; i += blockDim.x) {
+    const size_t at = size_t(g0 + i) * L + loc;
+    state[at] = tok[at];
+  }
 }
 
 __global__ void inverse_path_kernel(const long long* __restrict__ path, int* __restrict__ inv, int B, int L) {
@@ -351,6 +427,7 @@ __global__ void i64_to_i32_kernel(const long long* __restrict__ src, int* __rest
 // Last kernel of a step: snapshot the state into the trajectory, then advance `step` exactly once
 // (the last block to finish does it, after every block has read the old value).
 __global__ void advance_kernel(DecodeCtl* ctl, const uint8_t* __restrict__ state, int n) {
+  ptx::pdl_sync();
   const int step = ctl->step;
   if (ctl->traj) {
     uint8_t* dst = ctl->traj + size_t(step - ctl->start) * n;

@@ -98,6 +98,25 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, u
   return BIOM3_OK;
 }
 
+// Programmatic dependent launch (see ptx::pdl_sync): set by run_step for the launches of one decode step.
+thread_local bool g_pdl = false;
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute when g_pdl is set
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN, bool CG2>
 constexpr int gemm_stages() { return CG2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : 5); }
 
@@ -116,16 +135,19 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     cfg.blockDim = dim3(64 + 32 * gemm::epi_warps(EPI));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, p);
   } else {
-    gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false><<<grid, 64 + 32 * gemm::epi_warps(EPI), smem, st>>>(ta, tb, tc, p);
+    launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(64 + 32 * gemm::epi_warps(EPI)), size_t(smem), st,
+             ta, tb, tc, p);
   }
 }
 
@@ -167,6 +189,9 @@ cudaError_t init_kernel_attributes_impl() {
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k::sample_all_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * 32 * k::SAMPLE_TILE * int(sizeof(float)));
   return e;
 }
 
@@ -226,6 +251,7 @@ struct biom3_model {
   bool attn_tc = false;                         // local attention on tcgen05 instead of mma.sync
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
+  bool use_pdl = true;                          // programmatic dependent launch between the kernels of a step
   bool serpentine = true;                       // alternate the row walking direction kernel to kernel (L2 reuse)
   int mlp_slabs = 1;                            // FF1/FF2 row slabs per layer (hid slab reused, L2 resident)
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
@@ -360,6 +386,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const int JD = depth * D;
   int launches = 0;
   cudaError_t err = cudaSuccess;
+  g_pdl = m->use_pdl && !prof && m->precision == 0;
 #define LAUNCH(cat, ...)                     \
   do {                                       \
     if (prof) prof->begin(cat);              \
@@ -367,13 +394,13 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     if (prof) prof->end();                   \
     ++launches;                              \
     err = cudaGetLastError();                \
-    if (err != cudaSuccess) return err;      \
+    if (err != cudaSuccess) { g_pdl = false; return err; } \
   } while (0)
 
   const int row_blocks = std::min((M + 7) / 8, m->num_sms * 8);
-  LAUNCH(C_OTHER, k::cond_build_kernel<<<dim3(std::max(1, JD / 4 / 256), B), 256, 0, st>>>(
+  LAUNCH(C_OTHER, launch_k(k::cond_build_kernel, dim3(std::max(1, JD / 4 / 256), B), dim3(256), 0, st,
                       m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
-  LAUNCH(C_EMBED, k::embed_kernel<<<row_blocks, 256, 0, st>>>(m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a,
+  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a,
                                                               m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
@@ -431,14 +458,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     }
     cudaStream_t lst = fork ? m->side_stream : st;
     if (H - NL > 0)
-      LAUNCH(C_LINEAR, attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, lst>>>(m->qkv, m->att, B, H, L, NL,
+      LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), lst, m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
     if (NL > 0) {
       if (m->attn_tc)
-        LAUNCH(C_LOCAL, attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(
+        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc_kernel, dim3(L / attn::WIN, NL, B), dim3(256), size_t(attn::TC_SMEM_BYTES), st,
                             m->tm_qkv_attn, m->att, B, H, L, scale_log2e, adir));
       else
-        LAUNCH(C_LOCAL, attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(
+        LAUNCH(C_LOCAL, launch_k(attn::local_attention_kernel, dim3(L / attn::WIN, NL, B), dim3(256), size_t(attn::LOCAL_SMEM_BYTES), st,
                             m->qkv, m->att, B, H, L, scale_log2e, adir));
     }
     if (fork) {
@@ -477,13 +504,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
   const int ntok = sample ? B * group : M;
   const int head_blocks = std::min((ntok + 7) / 8, m->num_sms * 2);
-  LAUNCH(C_HEAD, k::head_kernel<<<head_blocks, 256, size_t(C) * D * sizeof(float), st>>>(ha));
+  LAUNCH(C_HEAD, launch_k(k::head_kernel, dim3(head_blocks), dim3(256), size_t(C) * D * sizeof(float), st, ha));
   if (advance) {
     const int n = M;
     const int blocks = std::min(std::max(1, n / (256 * 16)), m->num_sms);
-    LAUNCH(C_OTHER, k::advance_kernel<<<blocks, 256, 0, st>>>(m->ctl, m->state, n));
+    LAUNCH(C_OTHER, launch_k(k::advance_kernel, dim3(blocks), dim3(256), 0, st, m->ctl, m->state, n));
   }
 #undef LAUNCH
+  g_pdl = false;
   if (n_launch) *n_launch = launches;
   return cudaSuccess;
 }
@@ -546,6 +574,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
@@ -921,7 +950,13 @@ int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int 
   if (!logits || !noise || !tok || B < 1 || L < 1 || C < 2 || C > 32) return fail(BIOM3_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n = B * L;
-  k::sample_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(logits, noise, reinterpret_cast<long long*>(tok), B, L, C);
+  if (L % k::SAMPLE_TILE == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(noise)) & 15) == 0) {
+    CU_OK(init_kernel_attributes());
+    k::sample_all_tiled_kernel<<<n / k::SAMPLE_TILE, k::SAMPLE_TILE, size_t(2) * C * k::SAMPLE_TILE * sizeof(float), st>>>(
+        logits, noise, reinterpret_cast<long long*>(tok), B, L, C);
+  } else {
+    k::sample_all_kernel<<<(n + 255) / 256, 256, 0, st>>>(logits, noise, reinterpret_cast<long long*>(tok), B, L, C);
+  }
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }
@@ -931,13 +966,8 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
   if (!tok || !path || !state || B < 1 || L < 1 || group < 1 || B % group != 0 || step < 0 || step >= L)
     return fail(BIOM3_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int* inv = nullptr;
-  CU_OK(cudaMallocAsync(&inv, size_t(B) * L * sizeof(int), st));
-  const int n = B * L;
-  k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), inv, B, L);
-  k::unmask_kernel<<<(B * group + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(tok), inv,
-                                                              reinterpret_cast<long long*>(state), B, L, group, step);
-  CU_OK(cudaFreeAsync(inv, st));
+  k::unmask_scan_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const long long*>(tok), reinterpret_cast<const long long*>(path),
+                                           reinterpret_cast<long long*>(state), B, L, group, step);
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }

@@ -28,6 +28,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the decode step calls this once, before its first read of anything an earlier kernel wrote:
+// wait for the preceding grid in the stream to complete (a no-op unless this grid was launched with the
+// programmatic-stream-serialization attribute), then let the NEXT grid start launching as SMs free up, so its
+// launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) hide under this grid's tail.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
