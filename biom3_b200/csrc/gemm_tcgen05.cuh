@@ -33,7 +33,7 @@ constexpr int CV_TOTAL = 8192;    // the two per-column epilogue vectors of ever
 // Epilogue warps per CTA.  The fp32 residual epilogues use 8 (two per TMEM lane quarter, 128 columns each, 168
 // registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
 // smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
-__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 3 || epi == 4) ? 8 : 16; }
+__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 3 || epi == 4 || epi == 5) ? 8 : 16; }
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
@@ -41,6 +41,9 @@ enum Epi : int {
   EPI_BIAS_GELU_BF16 = 2,  // C bf16 row-major, gelu_erf(x + bias[n])
   EPI_BIAS_RESID_F32 = 3,  // R fp32 row-major [M, N]: R += acc + bias[n] (+ cond[b(m)][n]), in place
   EPI_STORE_F32 = 4,       // C fp32 row-major (unit tests)
+  EPI_BIAS_RESID_SPLIT = 5, // like 3, but R lives as two bf16 arrays, R = hi + lo (hi = bf16(R), lo = bf16(R - hi)):
+                            // `out_bf16` is hi (the array the next GEMM reads as its A operand), `out` is lo.  Same
+                            // bytes read, 2 instead of 6 bytes per element written; R keeps 16 significant bits.
 };
 
 struct Params {
@@ -233,11 +236,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
     const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
-    auto tile_gbase = [&](int t) -> float* {           // this lane's first fp32 element of a tile (row rr, group ch)
+    constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT);
+    constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT);
+    auto tile_goff = [&](int t) -> size_t {            // element offset of this lane's first element of a tile (row rr, group ch)
       const int tile = p.reverse ? num_tiles - 1 - t : t;
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
-      return reinterpret_cast<float*>(p.out) + size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN +
-             col_half * COLS_PER_WARP + 4 * ch;
+      return size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN + col_half * COLS_PER_WARP + 4 * ch;
+    };
+    // 4 residual values at element offset `off`, as raw bits: fp32 x 4, or (hi bf16 x 4, lo bf16 x 4)
+    auto load_res = [&](size_t off) -> uint4 {
+      if constexpr (SPLIT) {
+        const uint2 h = *reinterpret_cast<const uint2*>(p.out_bf16 + off);
+        const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + off);
+        return make_uint4(h.x, h.y, l.x, l.y);
+      } else {
+        return *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.out) + off);
+      }
     };
     // Hand an accumulator stage back to the MMA warp (leader CTA) as soon as this warp's last TMEM load of the tile
     // has landed in registers; the math and the stores of that last chunk then overlap the next-but-one mainloop.
@@ -253,12 +267,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // tile's first chunk) right after it is consumed, so every load has a full chunk period to land while only 32
     // registers hold prefetched data (a second buffer pushed this 168-register path into spills, and a spilled
     // prefetch register waits for its load at the spill store).
-    float4 res[8];
-    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+    uint4 res[8];
+    if constexpr (RESID) {
       if (worker < num_tiles) {
-        const float* g0 = tile_gbase(worker);
+        const size_t g0 = tile_goff(worker);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(g0 + size_t(4 * j) * p.N);
+        for (int j = 0; j < 8; ++j) res[j] = load_res(g0 + size_t(4 * j) * p.N);
       }
     }
     uint32_t it = 0;
@@ -284,18 +298,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (r[lane] == 0x7fc12345u) reinterpret_cast<float*>(p.out)[0] = 1.f;   // keep the loads alive
         }
         release_acc(as);
-      } else if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_STORE_F32) {
+      } else if constexpr (RESID || EPI == EPI_STORE_F32) {
         // fp32 path.  Read phase: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte column
-        // group lane%8): every global access is 4 full 128-byte lines per warp instruction.  The residual of
-        // the NEXT chunk (or of the next tile's first chunk) is always in flight while this one is processed.
+        // group lane%8): every global access is 4 full 128-byte lines per warp instruction (4 x 64 bytes per array
+        // in the split form).  The residual of the NEXT chunk (or of the next tile's first chunk) is always in flight
+        // while this one is processed.
         float rs[8], rq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
-        float* gbase = tile_gbase(t);
+        const size_t goff = tile_goff(t);
         const int next_t = t + n_workers;
-        const float* gnext = next_t < num_tiles ? tile_gbase(next_t) : nullptr;
+        const bool have_next = next_t < num_tiles;
+        const size_t gnext = have_next ? tile_goff(next_t) : 0;
         float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        if constexpr (RESID) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             addv[c] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c * 32 + 4 * ch));
@@ -308,8 +324,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_wait_parked(&acc_full[as], aphase);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const float* gn = (c + 1 < NCH) ? gbase + (c + 1) * 32 : gnext;
+        for (int ci = 0; ci < NCH; ++ci) {
+          // Split form: a 128-byte line of a bf16 plane spans two 32-column chunks; walking the chunks 0, 2, 1, 3 keeps
+          // the prefetch of the next chunk off the line the current chunk is storing to.
+          auto order = [](int i) { return (SPLIT && NCH == 4) ? (((i & 1) << 1) | (i >> 1)) : i; };
+          const int c = order(ci);
+          const bool more = (ci + 1 < NCH) || have_next;
+          const size_t gn = (ci + 1 < NCH) ? goff + order(ci + 1) * 32 : gnext;
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
@@ -318,29 +339,48 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             st_shared_v4(stg + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           __syncwarp();
           float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (EPI == EPI_BIAS_RESID_F32) add = addv[c];
+          if constexpr (RESID) add = addv[c];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int row = 4 * j + rr;
             const uint4 a4 = ld_shared_v4(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
-            if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              const float4 rv = res[j];
-              if (gn) res[j] = *reinterpret_cast<const float4*>(gn + size_t(4 * j) * p.N);
+            if constexpr (RESID) {
+              const uint4 rb = res[j];
+              if (more) res[j] = load_res(gn + size_t(4 * j) * p.N);
+              float4 rv;
+              if constexpr (SPLIT) {
+                rv = make_float4(__uint_as_float(rb.x << 16) + __uint_as_float(rb.z << 16),
+                                 __uint_as_float(rb.x & 0xffff0000u) + __uint_as_float(rb.z & 0xffff0000u),
+                                 __uint_as_float(rb.y << 16) + __uint_as_float(rb.w << 16),
+                                 __uint_as_float(rb.y & 0xffff0000u) + __uint_as_float(rb.w & 0xffff0000u));
+              } else {
+                rv = make_float4(__uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w));
+              }
               o.x += rv.x + add.x; o.y += rv.y + add.y; o.z += rv.z + add.z; o.w += rv.w + add.w;
             }
-            *reinterpret_cast<float4*>(gbase + size_t(4 * j) * p.N + c * 32) = o;
-            if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              if (p.out_bf16)
-                *reinterpret_cast<uint2*>(p.out_bf16 + size_t(rbase + row) * p.N + nbase + c * 32 + 4 * ch) =
-                    make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+            const size_t eoff = goff + size_t(4 * j) * p.N + c * 32;
+            if constexpr (SPLIT) {
+              const uint32_t h0 = ptx::pack_bf16x2(o.x, o.y), h1 = ptx::pack_bf16x2(o.z, o.w);
+              *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + eoff) =
+                  make_uint2(ptx::pack_bf16x2(o.x - __uint_as_float(h0 << 16), o.y - __uint_as_float(h0 & 0xffff0000u)),
+                             ptx::pack_bf16x2(o.z - __uint_as_float(h1 << 16), o.w - __uint_as_float(h1 & 0xffff0000u)));
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + eoff) = o;
+            }
+            if constexpr (RESID) {
+              if constexpr (!SPLIT) {
+                if (p.out_bf16)
+                  *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+              }
               rs[j] += (o.x + o.y) + (o.z + o.w);
               rq[j] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
             }
           }
           __syncwarp();
         }
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        if constexpr (RESID) {
           if (p.stats_out) {
             const int parts = n_tiles * 2, part = n_tile * 2 + col_half;
 #pragma unroll

@@ -85,7 +85,8 @@ __global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* _
 __global__ void __launch_bounds__(256)
 embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
              const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride, float* __restrict__ u,
-             __nv_bfloat16* __restrict__ ub, float* __restrict__ stats, int parts, int rows, int L, int W, int D) {
+             __nv_bfloat16* __restrict__ ub, __nv_bfloat16* __restrict__ ulo, float* __restrict__ stats, int parts,
+             int rows, int L, int W, int D) {
   ptx::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
@@ -107,8 +108,14 @@ embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, c
         const float4 x3 = __ldg(reinterpret_cast<const float4*>(cv + col));
         const float4 v = make_float4((x0.x + (x1.x + x2.x)) + x3.x, (x0.y + (x1.y + x2.y)) + x3.y,
                                      (x0.z + (x1.z + x2.z)) + x3.z, (x0.w + (x1.w + x2.w)) + x3.w);
-        *reinterpret_cast<float4*>(u + size_t(row) * D + col) = v;
-        *reinterpret_cast<uint2*>(ub + size_t(row) * D + col) = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+        const uint32_t h0 = ptx::pack_bf16x2(v.x, v.y), h1 = ptx::pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(ub + size_t(row) * D + col) = make_uint2(h0, h1);
+        if (ulo)       // split residual stream: u = hi + lo, both bf16 (see gemm::EPI_BIAS_RESID_SPLIT)
+          *reinterpret_cast<uint2*>(ulo + size_t(row) * D + col) =
+              make_uint2(ptx::pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u)),
+                         ptx::pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u)));
+        else
+          *reinterpret_cast<float4*>(u + size_t(row) * D + col) = v;
         s += (v.x + v.y) + (v.z + v.w);
         q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       }
@@ -184,7 +191,9 @@ __device__ __forceinline__ int categorical_draw(float logit, float q, int lane, 
 // and scatters tokens.  SELECTED mode (decode): token list = {(b', loc[b]) : b in group(b')},
 // loc[b] = inv_path[b][step]  -> this IS the reference's B x B unmask write.  ALL mode: every token.
 struct HeadArgs {
-  const float* u;            // [rows][D] fp32 hidden after the last block
+  const float* u;            // [rows][D] fp32 hidden after the last block, or nullptr when it is stored split:
+  const __nv_bfloat16* u_hi; //   u = u_hi + u_lo, both bf16 [rows][D]
+  const __nv_bfloat16* u_lo;
   const float* gamma; const float* beta;     // final LayerNorm
   const float* w_out;        // [C][D] fp32
   const float* b_out;        // [C]
@@ -222,7 +231,16 @@ head_kernel(const HeadArgs a) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
-        v[i] = *reinterpret_cast<const float4*>(a.u + row * a.D + (i * 32 + lane) * 4);
+        if (a.u) {
+          v[i] = *reinterpret_cast<const float4*>(a.u + row * a.D + (i * 32 + lane) * 4);
+        } else {
+          const uint2 h = *reinterpret_cast<const uint2*>(a.u_hi + row * a.D + (i * 32 + lane) * 4);
+          const uint2 l = *reinterpret_cast<const uint2*>(a.u_lo + row * a.D + (i * 32 + lane) * 4);
+          v[i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
+                             __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                             __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
+                             __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+        }
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     const float mean = warp_sum(s) / float(a.D);

@@ -174,6 +174,7 @@ cudaError_t init_kernel_attributes_impl() {
 #define SET_GEMM(EPI) SET_GEMM1(256, EPI, false) SET_GEMM1(128, EPI, false) SET_GEMM1(256, EPI, true)
   SET_GEMM(gemm::EPI_QKV_HEADMAJOR)
   SET_GEMM(gemm::EPI_BIAS_RESID_F32)
+  SET_GEMM(gemm::EPI_BIAS_RESID_SPLIT)
   SET_GEMM(gemm::EPI_BIAS_GELU_BF16)
   SET_GEMM(gemm::EPI_STORE_BF16)
   SET_GEMM(gemm::EPI_STORE_F32)
@@ -240,7 +241,9 @@ struct biom3_model {
   float *Ttab = nullptr;
   float *y_w0 = nullptr, *y_b0 = nullptr, *y_w2 = nullptr, *y_b2 = nullptr;
   // workspace
-  float* u = nullptr;
+  float* u = nullptr;                           // fp32 residual stream (fp32-class mode, or BIOM3_SPLIT_RESID=0)
+  bf16* u_lo = nullptr;                         // split residual stream: u = a (hi, bf16) + u_lo (bf16)
+  bool split_resid = true;
   bf16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
   float *Yh = nullptr, *Ytmp = nullptr, *Y = nullptr, *cvec = nullptr;
   uint8_t* state = nullptr;
@@ -398,9 +401,10 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   } while (0)
 
   const int row_blocks = std::min((M + 7) / 8, m->num_sms * 8);
+  const bool split = m->precision == 0 && m->split_resid;      // residual stream stored as bf16 hi + lo
   LAUNCH(C_OTHER, launch_k(k::cond_build_kernel, dim3(std::max(1, JD / 4 / 256), B), dim3(256), 0, st,
                       m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
-  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a,
+  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a, split ? m->u_lo : nullptr,
                                                               m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
@@ -477,7 +481,12 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
     r.out_bf16 = m->a; r.stats_out = m->stats; r.reverse = next_dir();
-    LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+    if (split) {
+      r.out = m->u_lo;
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+    } else {
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+    }
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t), then
     // u += hid . W2^T + b2 (+ next layer's conditioning vector).  Optionally in row slabs that reuse one hid
     // slab buffer, so the 4D-wide hidden activation lives in L2 between the two GEMMs instead of HBM.
@@ -495,11 +504,16 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.out = m->u + row0 * D; r.out_bf16 = m->a + row0 * D; r.stats_out = m->stats + row0 * m->ln_parts * 2;
       r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D + size_t(sl) * Bs * JD : nullptr;
       r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+      if (split) {
+        r.out = m->u_lo + row0 * D;
+        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+      } else {
+        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+      }
     }
   }
   k::HeadArgs ha{};
-  ha.u = m->u; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
+  ha.u = split ? nullptr : m->u; ha.u_hi = m->a; ha.u_lo = m->u_lo; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
   ha.logits_out = logits_out; ha.state = sample ? m->state : nullptr; ha.inv_path = m->inv_path; ha.ctl = m->ctl;
   ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
   const int ntok = sample ? B * group : M;
@@ -575,6 +589,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
@@ -731,7 +746,11 @@ int biom3_finalize_weights(biom3_model* m) {
   m->host_w.clear();
 
   // workspace, sized for max_batch
-  TRY(dev_alloc(m, &m->u, M * D));
+  if (m->precision == 0 && m->split_resid) {
+    TRY(dev_alloc(m, &m->u_lo, M * D));
+  } else {
+    TRY(dev_alloc(m, &m->u, M * D));
+  }
   TRY(dev_alloc(m, &m->a, M * D));
   TRY(dev_alloc(m, &m->qkv, M * 3 * D));
   TRY(dev_alloc(m, &m->att, M * D));
@@ -893,7 +912,8 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
   const std::string n(name);
   const void* src = nullptr;
   size_t sz = 0;
-  if (n == "u") { src = m->u; sz = M * D * 4; }
+  if (n == "u") { src = m->u; sz = m->u ? M * D * 4 : 0; }
+  else if (n == "u_lo") { src = m->u_lo; sz = m->u_lo ? M * D * 2 : 0; }
   else if (n == "a") { src = m->a; sz = M * D * 2; }
   else if (n == "qkv") { src = m->qkv; sz = M * 3 * D * 2; }
   else if (n == "att") { src = m->att; sz = M * D * 2; }
@@ -1041,6 +1061,10 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
       launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_BIAS_RESID_SPLIT:      // out = bf16 [2][M][N]: hi plane then lo plane, updated in place
+      p.out_bf16 = reinterpret_cast<bf16*>(out);
+      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
+      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -96,7 +96,8 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
 
 /* Unit-test hook for the tcgen05 GEMM: C = A . W^T with one of the fused epilogues.
  * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
- * 3 fp32 in-place residual (+bias), 4 fp32 out.  block_n: 128 or 256.  pair bit 0: CTA-pair (cta_group::2)
+ * 3 fp32 in-place residual (+bias), 4 fp32 out, 5 in-place residual stored split (out = bf16 [2][M][N]: hi plane
+ * bf16(R), lo plane bf16(R - hi)).  block_n: 128 or 256.  pair bit 0: CTA-pair (cta_group::2)
  * tiling, 256 x 256 tiles (needs block_n == 256, M % 256 == 0); pair bit 1: fp32-class K schedule, A and W are
  * [hi | lo] bf16 halves of width 2K and the result is hi.hi + hi.lo + lo.hi. */
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,

@@ -497,3 +497,24 @@ def test_generate_denoised_sampled_single_sequence_vs_reference_fixture():
         samp.generate_denoised_sampled(args=args, model=model, extract_digit_samples=masked.float(),
                                        extract_time=torch.tensor([start]), extract_digit_label=torch.from_numpy(z['z_c']),
                                        sampling_path=path)
+
+
+@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
+def test_gemm_split_residual_epilogue(bn, pair):
+    """Epilogue 5: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 1024, 512, 512
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    R = (torch.randn(M, N, generator=g) * 3.0).cuda()
+    hi = R.bfloat16()
+    planes = torch.stack([hi, (R - hi.float()).bfloat16()]).contiguous()
+    r0 = planes[0].float() + planes[1].float()
+    assert rel_err(r0, R) < 1e-5                                  # the split itself keeps 16 significant bits
+    ref = r0 + A.float() @ W.float().t() + bias
+    engine.gemm_test(A, W, bias, 5, bn, out=planes, pair=pair)
+    got = planes[0].float() + planes[1].float()
+    assert rel_err(got, ref) < 2e-5
+    assert torch.equal(planes[0], got.bfloat16()) or rel_err(planes[0].float(), ref) < 4e-3   # hi plane = bf16(R)

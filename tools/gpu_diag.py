@@ -157,9 +157,12 @@ def stage_stages():
     hid = eng.debug_buffer('hid', (B, L, 4 * D), torch.bfloat16).float()
     print('hid rel_err:', rel_err(hid, hid_ref))
     u2 = u1 + F.linear(hid_ref, sd[p + '1.fn.fn.w2.weight'], sd[p + '1.fn.fn.w2.bias'])
-    ud = eng.debug_buffer('u', (B, L, D), torch.float32)
-    print('u final rel_err:', rel_err(ud, u2))
     ab = eng.debug_buffer('a', (B, L, D), torch.bfloat16).float()
+    if os.environ.get('BIOM3_SPLIT_RESID', '1') != '0':          # residual stream stored as bf16 hi ('a') + lo
+        ud = ab + eng.debug_buffer('u_lo', (B, L, D), torch.bfloat16).float()
+    else:
+        ud = eng.debug_buffer('u', (B, L, D), torch.float32)
+    print('u final rel_err:', rel_err(ud, u2))
     print('bf16 copy of u rel_err:', rel_err(ab, u2))
     ref = orc(x, t, z)
     print('logits rel_err:', rel_err(logits, ref), ' max|ref|', ref.abs().max().item())
