@@ -186,6 +186,9 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::local_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::TC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::local_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::TC2_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -251,7 +254,7 @@ struct biom3_model {
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
-  bool attn_tc = false;                         // local attention on tcgen05 instead of mma.sync
+  int attn_tc = 0;                              // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
   bool use_pdl = true;                          // programmatic dependent launch between the kernels of a step
@@ -465,7 +468,11 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), lst, m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
     if (NL > 0) {
-      if (m->attn_tc)
+      if (m->attn_tc == 2)
+        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc2_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
+                                 dim3(attn::TC2_THREADS), size_t(attn::TC2_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
+                                 scale_log2e, adir));
+      else if (m->attn_tc == 1)
         LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc_kernel, dim3(L / attn::WIN, NL, B), dim3(256), size_t(attn::TC_SMEM_BYTES), st,
                             m->tm_qkv_attn, m->att, B, H, L, scale_log2e, adir));
       else
@@ -590,7 +597,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   CU_OK(init_kernel_attributes());
@@ -1002,11 +1009,19 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   if (NL > 0) {
-    if (variant == 1) {
+    if (variant == 1 || variant == 2) {
       CUtensorMap tm;
       int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
       if (r) return r;
-      attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(tm, o, B, H, L, scale_log2e, 0);
+      if (variant == 2) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attn::local_attention_tc2_kernel<<<std::min(sms, (L / attn::WIN) * NL * B), attn::TC2_THREADS, attn::TC2_SMEM_BYTES, st>>>(
+            tm, o, B, H, L, NL, scale_log2e, 0);
+      } else {
+        attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(tm, o, B, H, L, scale_log2e, 0);
+      }
     } else {
       attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(q, o, B, H, L, scale_log2e, 0);
     }

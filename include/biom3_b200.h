@@ -104,7 +104,8 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
                     int block_n, int pair, void* stream);
 
 /* Unit-test hook for the attention kernels: qkv device bf16 [3][B][H][L][32] -> out device bf16 [B*L][H*32].
- * Heads [0, NL) windowed softmax (variant 0: mma.sync kernel, 1: tcgen05 kernel), heads [NL, H) linear attention. */
+ * Heads [0, NL) windowed softmax (variant 0: mma.sync kernel, 1: tcgen05 kernel, one item per CTA, 2: tcgen05 persistent
+ * kernel with P kept in tensor memory), heads [NL, H) linear attention. */
 int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL, int variant, void* stream);
 
 /* Per-kernel device timings (ms) of the last biom3_profile_step() call; for bench.py's roofline. */
