@@ -856,4 +856,274 @@ local_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bflo
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
+
+// ================================================================================================
+// Variant 3: the same persistent tcgen05 schedule split into TWO independent streams per CTA (ping-pong).  Each
+// stream owns a TMA producer warp, an MMA issuer warp, four softmax warps (ONE thread per query row: no cross-thread
+// exchange at all), half of the TMEM (3 S/P slots of 64 key columns + 2 O buffers = 256 columns) and its own smem
+// ring, and walks every other item of the CTA.  The two softmax warps that share an SMSP now belong to different
+// streams, so one stream's waits, maxima and TMEM traffic hide under the other's exponentials.
+// A block is 64 keys: (K/V tile of 128 keys, sub-block 0/1); blocks of a stream are numbered g, slot g % 3.
+// ================================================================================================
+constexpr int TC3_NST = 3;
+constexpr int TC3_THREADS = 384;
+constexpr int TC3_STREAM_TILES = 2 + 2 * TC3_NST;
+constexpr int TC3_SMEM_BYTES = 2 * TC3_STREAM_TILES * TC_TILE + 1024;
+
+struct Tc3Bars {
+  uint64_t q_full[2], q_free[2], kv_full[TC3_NST], kv_free[TC3_NST], s_full[3], p_ready[3], s_free[3], o_full[2], o_free[2];
+};
+struct Tc3Cursor {
+  int i, n, t, g, kt, sb, nkt, w, b, h, w_lo;
+  bool valid;
+};
+
+__global__ void __launch_bounds__(TC3_THREADS, 1)
+local_attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
+                           int L, int NL, float scale_log2e, int reverse) {
+  const int nw = L / WIN;
+  const int total = nw * B * NL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stream = warp < 4 ? (warp >> 1) : ((warp - 4) >> 2);
+  const int role = warp < 4 ? (warp & 1) : 2;            // 0 producer, 1 issuer, 2 softmax
+
+  extern __shared__ uint8_t tc3_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc3_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + stream * TC3_STREAM_TILES * TC_TILE;      // 2 tiles
+  uint8_t* sKV = sQ + 2 * TC_TILE;                               // TC3_NST x (K tile, V tile)
+  __shared__ Tc3Bars bars[2];
+  __shared__ uint32_t tmem_slot;
+  Tc3Bars& bar = bars[stream];
+
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_qkv);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      Tc3Bars& x = bars[s2];
+      for (int k = 0; k < 2; ++k) {
+        ptx::mbar_init(&x.q_full[k], 1);
+        ptx::mbar_init(&x.q_free[k], 1);
+        ptx::mbar_init(&x.o_full[k], 1);
+        ptx::mbar_init(&x.o_free[k], 4);
+      }
+      for (int k = 0; k < TC3_NST; ++k) {
+        ptx::mbar_init(&x.kv_full[k], 1);
+        ptx::mbar_init(&x.kv_free[k], 1);
+      }
+      for (int k = 0; k < 3; ++k) {
+        ptx::mbar_init(&x.s_full[k], 1);
+        ptx::mbar_init(&x.p_ready[k], 4);
+        ptx::mbar_init(&x.s_free[k], 1);
+      }
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot + stream * 256;          // this stream's half: S/P slots at 0, 64, 128; O at 192, 224
+  ptx::pdl_sync();
+
+  auto seek = [&](Tc3Cursor& c) {
+    const int f = int(blockIdx.x) + c.i * int(gridDim.x);
+    c.valid = f < total;
+    if (!c.valid) return;
+    const int ff = reverse ? total - 1 - f : f;
+    c.h = ff % NL;
+    c.b = (ff / NL) % B;
+    c.w = ff / (NL * B);
+    c.w_lo = max(c.w - 1, 0);
+    c.nkt = min(c.w + 1, nw - 1) - c.w_lo + 1;
+    c.kt = 0;
+    c.sb = 0;
+  };
+  auto start = [&](Tc3Cursor& c) { c.i = stream; c.n = 0; c.t = 0; c.g = 0; seek(c); };
+  auto advance = [&](Tc3Cursor& c) {
+    ++c.g;
+    if (++c.sb == 2) {
+      c.sb = 0;
+      ++c.t;
+      if (++c.kt == c.nkt) { c.i += 2; ++c.n; seek(c); }
+    }
+  };
+  auto first_block = [](const Tc3Cursor& c) { return c.kt == 0 && c.sb == 0; };
+  auto last_block = [](const Tc3Cursor& c) { return c.kt == c.nkt - 1 && c.sb == 1; };
+
+  if (role == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int plane = B * H * L;
+      Tc3Cursor c;
+      for (start(c); c.valid; advance(c)) {
+        if (c.sb != 0) continue;
+        const int rq = (c.b * H + c.h) * L;
+        if (c.kt == 0) {
+          const int qb = c.n & 1;
+          ptx::mbar_wait_parked(&bar.q_free[qb], ((c.n >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
+          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + c.w * WIN);
+        }
+        const int st = c.t % TC3_NST;
+        ptx::mbar_wait_parked(&bar.kv_free[st], ((c.t / TC3_NST) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
+        ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (c.w_lo + c.kt) * WIN);
+        ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kt) * WIN);
+      }
+    }
+  } else if (role == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      auto issue_s = [&](const Tc3Cursor& c) {
+        const int qb = c.n & 1, st = c.t % TC3_NST, slot = c.g % 3;
+        if (first_block(c)) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
+        if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[st], (c.t / TC3_NST) & 1);
+        ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g / 3) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
+        const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE) + c.sb * 64 * 64);
+        ptx::umma_bf16(tmem + slot * 64, dq, dk, IDESC_S, 0);
+        ptx::umma_bf16(tmem + slot * 64, dq + 2, dk + 2, IDESC_S, 1);
+        ptx::umma_commit(&bar.s_full[slot]);
+        if (last_block(c)) ptx::umma_commit(&bar.q_free[qb]);
+      };
+      auto issue_pv = [&](const Tc3Cursor& c) {
+        const int ob = c.n & 1, st = c.t % TC3_NST, slot = c.g % 3;
+        if (first_block(c)) ptx::mbar_wait_parked(&bar.o_free[ob], ((c.n >> 1) & 1) ^ 1);
+        ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g / 3) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE) + c.sb * 64 * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_bf16_ts(tmem + 192 + ob * 32, tmem + slot * 64 + ks * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
+                            !(first_block(c) && ks == 0));
+        ptx::umma_commit(&bar.s_free[slot]);
+        if (c.sb == 1) ptx::umma_commit(&bar.kv_free[st]);
+        if (last_block(c)) ptx::umma_commit(&bar.o_full[ob]);
+      };
+      Tc3Cursor sc, pc;
+      start(sc);
+      start(pc);
+      while (pc.valid) {
+        while (sc.valid && sc.g < pc.g + 3) {
+          issue_s(sc);
+          advance(sc);
+        }
+        issue_pv(pc);
+        advance(pc);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (4 warps per stream)
+    // Online softmax per 64-key block against a lazily updated reference maximum (see variant 2), one thread per row.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
+    const int D = H * DH;
+    constexpr float LAZY_LOG2 = 8.0f;
+    float m_ref = 0.f, rs = 0.f;
+    bool pend = false;
+    int p_n = 0;
+    float p_inv = 0.f;
+    __nv_bfloat16* p_dst = nullptr;
+    auto epilogue = [&]() {
+      const int ob = p_n & 1;
+      ptx::mbar_wait(&bar.o_full[ob], (p_n >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t ro[32];
+      ptx::tmem_ld_32x32(lane_base + 192 + ob * 32, ro);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.o_free[ob]);
+      uint4* dst = reinterpret_cast<uint4*>(p_dst);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * p_inv, __uint_as_float(ro[8 * k + 1]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * p_inv, __uint_as_float(ro[8 * k + 3]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
+    };
+    Tc3Cursor c;
+    for (start(c); c.valid; advance(c)) {
+      const int g = c.g, slot = g % 3;
+      const uint32_t t_s = lane_base + slot * 64;
+      ptx::mbar_wait(&bar.s_full[slot], (g / 3) & 1);
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32(t_s, r0);
+      ptx::tmem_ld_32x32(t_s + 32, r1);
+      ptx::tmem_ld_wait();
+      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        b0 = fmaxf(b0, __uint_as_float(r0[2 * k]));
+        b1 = fmaxf(b1, __uint_as_float(r0[2 * k + 1]));
+        b2 = fmaxf(b2, __uint_as_float(r1[2 * k]));
+        b3 = fmaxf(b3, __uint_as_float(r1[2 * k + 1]));
+      }
+      const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+      if (first_block(c)) {
+        m_ref = bm;
+        rs = 0.f;
+      } else {
+        const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          const int gp = g - 1;                            // every PV issued so far must have landed in O
+          ptx::mbar_wait(&bar.s_free[gp % 3], (gp / 3) & 1);
+          ptx::tc_fence_after();
+          const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
+          uint32_t ro[32];
+          const uint32_t t_o = lane_base + 192 + (c.n & 1) * 32;
+          ptx::tmem_ld_32x32(t_o, ro);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
+          ptx::tmem_st_32x32(t_o, ro);
+          ptx::tmem_st_wait();
+          rs *= f;
+          if (need) m_ref = bm;
+        }
+      }
+      const float ms = m_ref * scale_log2e;
+      uint32_t pk[32];                                     // P (bf16 pairs) over the first 32 of the slot's 64 columns
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
+        const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
+        const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
+        const float p3 = fast_ex2(fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms));
+        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        pk[k] = ptx::pack_bf16x2(p0, p1);
+        pk[16 + k] = ptx::pack_bf16x2(p2, p3);
+      }
+      rs += (s0 + s1) + (s2 + s3);
+      ptx::tmem_st_32x32(t_s, pk);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+      if (first_block(c) && pend) {
+        epilogue();
+        pend = false;
+      }
+      if (last_block(c)) {
+        pend = true;
+        p_n = c.n;
+        p_inv = 1.f / rs;
+        p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH;
+      }
+    }
+    if (pend) epilogue();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
+}
+
 }  // namespace attn

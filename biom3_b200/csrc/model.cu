@@ -189,6 +189,9 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::local_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::TC2_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::local_attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::TC3_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -254,7 +257,8 @@ struct biom3_model {
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
-  int attn_tc = 0;                              // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM)
+  int attn_tc = 3;                              // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM),
+                                                // 3 = 2 split into two ping-pong streams per CTA (default; BIOM3_ATTN_TC)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   bool tma_store = true;
   bool use_pdl = true;                          // programmatic dependent launch between the kernels of a step
@@ -468,7 +472,11 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), lst, m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
     if (NL > 0) {
-      if (m->attn_tc == 2)
+      if (m->attn_tc == 3)
+        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc3_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
+                                 dim3(attn::TC3_THREADS), size_t(attn::TC3_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
+                                 scale_log2e, adir));
+      else if (m->attn_tc == 2)
         LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc2_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
                                  dim3(attn::TC2_THREADS), size_t(attn::TC2_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
                                  scale_log2e, adir));
@@ -1009,11 +1017,17 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   if (NL > 0) {
-    if (variant == 1 || variant == 2) {
+    if (variant >= 1 && variant <= 3) {
       CUtensorMap tm;
       int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
       if (r) return r;
-      if (variant == 2) {
+      if (variant == 3) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attn::local_attention_tc3_kernel<<<std::min(sms, (L / attn::WIN) * NL * B), attn::TC3_THREADS, attn::TC3_SMEM_BYTES, st>>>(
+            tm, o, B, H, L, NL, scale_log2e, 0);
+      } else if (variant == 2) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

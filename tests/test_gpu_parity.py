@@ -357,22 +357,26 @@ def test_batch_of_one_decode_matches_oracle():
 
 
 # ---------------------------------------------------------------- attention kernels in isolation
-@pytest.mark.parametrize('B,H,L,NL', [(1, 2, 128, 1), (2, 4, 256, 2), (2, 16, 1024, 8)])
-@pytest.mark.parametrize('variant', [0, 1])
-def test_attention_kernels_vs_fp32_reference(B, H, L, NL, variant):
-    """variant 0: mma.sync local attention (the default), variant 1: the tcgen05 local-attention kernel (TMEM S/O,
-    MN-major V operand); heads >= NL: linear attention.  Same bf16 inputs, fp32 reference -> bf16 output rounding."""
+@pytest.mark.parametrize('B,H,L,NL,amp', [(1, 2, 128, 1, 1.5), (2, 4, 256, 2, 1.5), (2, 16, 1024, 8, 1.5),
+                                          (2, 4, 512, 2, 4.0), (3, 4, 1024, 3, 6.0), (5, 8, 384, 8, 1.0)])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3])
+def test_attention_kernels_vs_fp32_reference(B, H, L, NL, amp, variant):
+    """Local attention variants: 0 mma.sync; 1 tcgen05, one item per CTA (TMEM S/O, MN-major V operand); 2 tcgen05
+    persistent with P kept in TMEM and a lazily rescaled online softmax; 3 = 2 as two ping-pong streams per CTA (the
+    default in the decode step).  Heads >= NL: linear attention.  amp >= 4 gives peaked rows whose block maxima jump
+    by more than 2^8, which exercises the rescale path of variants 2 / 3.  Same bf16 inputs, fp32 reference."""
     from biom3_b200 import engine
     from oracle.upstream_blocks import LocalAttention, linear_attention
     g = torch.Generator().manual_seed(B * 100 + L)
-    qkv = (torch.randn(3, B, H, L, 32, generator=g) * 1.5).bfloat16()
+    qkv = (torch.randn(3, B, H, L, 32, generator=g) * amp).bfloat16()
     q, k, v = (t.float() for t in qkv)
     lo = LocalAttention(128)(q[:, :NL], k[:, :NL], v[:, :NL])
     go = linear_attention(q[:, NL:], k[:, NL:], v[:, NL:])
     ref = torch.cat([lo, go], 1).transpose(1, 2).reshape(B * L, H * 32)
     out = engine.attention_test(qkv.cuda(), NL, variant).float().cpu()
     assert rel_err(out[:, :NL * 32], ref[:, :NL * 32]) < 8e-3
-    assert rel_err(out[:, NL * 32:], ref[:, NL * 32:]) < 8e-3
+    if NL < H:
+        assert rel_err(out[:, NL * 32:], ref[:, NL * 32:]) < 8e-3
 
 
 # ---------------------------------------------------------------- fp32-class mode (biom3_set_precision(m, 1))
