@@ -271,19 +271,26 @@ def run_cuda_arm(a):
     # ---- per-kernel roofline: CUDA events around every launch of one un-graphed decode step
     profs = [eng.profile_step(BATCH, BATCH) for _ in range(3)]
     prof = {k: statistics.median(p[k] for p in profs) for k in profs[0]}
+    prof['launches'], prof['compact_rows'] = int(prof['launches']), int(prof['compact_rows'])
     depth = 16
     M = BATCH * L
+    # Last-layer row compaction: the last layer's out-proj / FF1 / FF2 run on `compact_rows` selected token rows instead
+    # of M (the rest of that layer's output is never read).  Per-kernel rates count the FLOPs EXECUTED: a category's
+    # time covers (depth - 1) full launches + one launch on compact_rows rows.
+    mc = int(prof.get('compact_rows', 0))
+    full_equiv = depth if mc == 0 else depth - 1 + mc / M           # full-size launches the category's time is worth
     kern = {
-        'gemm_ff1 (tcgen05, bias+GELU epilogue)': (prof['gemm_ff1_ms'] / depth, 2.0 * M * 2048 * 512),
-        'gemm_ff2 (tcgen05, bias+residual epilogue)': (prof['gemm_ff2_ms'] / depth, 2.0 * M * 512 * 2048),
+        'gemm_ff1 (tcgen05, bias+GELU epilogue)': (prof['gemm_ff1_ms'] / full_equiv, 2.0 * M * 2048 * 512),
+        'gemm_ff2 (tcgen05, bias+residual epilogue)': (prof['gemm_ff2_ms'] / full_equiv, 2.0 * M * 512 * 2048),
         'gemm_qkv (tcgen05, head-major store)': (prof['gemm_qkv_ms'] / depth, 2.0 * M * 1536 * 512),
-        'gemm_out (tcgen05, bias+residual epilogue)': (prof['gemm_out_ms'] / depth, 2.0 * M * 512 * 512),
+        'gemm_out (tcgen05, bias+residual epilogue)': (prof['gemm_out_ms'] / full_equiv, 2.0 * M * 512 * 512),
         'local_attention': (prof['local_attn_ms'] / depth, 360448.0 * M),
         'linear_attention': (prof['linear_attn_ms'] / depth, 32768.0 * M),
     }
     dom = max(kern, key=lambda k_: kern[k_][0])
     dom_ms, dom_flop = kern[dom]
     achieved = dom_flop / (dom_ms * 1e-3) / 1e12
+    executed_flop_per_seq_step = FLOP_PER_SEQ_STEP - (0 if mc == 0 else (1.0 - mc / M) * L * (524288 + 4194304))
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tpath):
@@ -295,9 +302,15 @@ def run_cuda_arm(a):
         'peak_source': f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}; kernel timed inside a long step)",
         'how': 'median of 3 un-graphed decode steps with CUDA events around every launch on the launching stream, right after the timed region',
         'step_ms_ungraphed': prof['total_ms'],
-        'share_of_step': dom_ms * depth / prof['total_ms'],
+        'share_of_step': dom_ms * (full_equiv if 'attention' not in dom and 'qkv' not in dom else depth) / prof['total_ms'],
         'whole_step_tflops': FLOP_PER_SEQ_STEP * BATCH / (ms_total / a.steps / L * 1e-3) / 1e12,
         'whole_step_frac_of_peak': FLOP_PER_SEQ_STEP * BATCH / (ms_total / a.steps / L * 1e-3) / 1e12 / peaks['tf_sustained'],
+        'whole_step_note': 'whole_step_* use the reference algorithm\'s FLOPs (109.552 GFLOP per sequence per step, SURVEY.md 8d); '
+                           'whole_step_executed_* count only the FLOPs this build executes (last-layer row compaction skips '
+                           'rows whose output the sampler never reads)',
+        'last_layer_compact_rows': mc,
+        'whole_step_executed_tflops': executed_flop_per_seq_step * BATCH / (ms_total / a.steps / L * 1e-3) / 1e12,
+        'whole_step_executed_frac_of_peak': executed_flop_per_seq_step * BATCH / (ms_total / a.steps / L * 1e-3) / 1e12 / peaks['tf_sustained'],
         'per_kernel_ms_per_step': {k_: round(v, 4) for k_, v in prof.items()},
         'per_kernel_tflops': {k_: round(f / (ms * 1e-3) / 1e12, 1) for k_, (ms, f) in kern.items() if ms > 0},
     }

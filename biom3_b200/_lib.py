@@ -26,7 +26,7 @@ class Config(C.Structure):
 class StepProfile(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         'total_ms', 'gemm_qkv_ms', 'gemm_out_ms', 'gemm_ff1_ms', 'gemm_ff2_ms', 'local_attn_ms',
-        'linear_attn_ms', 'layernorm_ms', 'embed_ms', 'head_ms', 'other_ms')] + [('launches', C.c_int32)]
+        'linear_attn_ms', 'layernorm_ms', 'embed_ms', 'head_ms', 'other_ms')] + [('launches', C.c_int32), ('compact_rows', C.c_int32)]
 
 
 _lib = None

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'model.cu')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('model.cu', 'ptx.cuh', 'gemm_tcgen05.cuh', 'attention.cuh', 'kernels.cuh')]
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('model.cu', 'ptx.cuh', 'gemm_tcgen05.cuh', 'attention.cuh', 'kernels.cuh', 'fp32_path.cuh')]
 DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'biom3_b200.h'))
 LIB = os.path.join(HERE, 'libbiom3_b200.so')
 

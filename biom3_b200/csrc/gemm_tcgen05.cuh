@@ -28,7 +28,8 @@ constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STG_TOTAL = 32768;  // epilogue staging: one 32 x 32 block per warp (fp32: 8 warps x 4 KB, bf16: 16 warps x 2 KB)
-constexpr int CV_TOTAL = 8192;    // the two per-column epilogue vectors of every warp's column range
+constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of every warp's column range, double buffered
+                                  // (the next tile's vectors are fetched with cp.async while this tile is processed)
 
 // Epilogue warps per CTA.  The fp32 residual epilogues use 8 (two per TMEM lane quarter, 128 columns each, 168
 // registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
@@ -61,14 +62,16 @@ struct Params {
   // consumer side of the folded LayerNorm (bf16-output epilogues): x = rstd*(acc - mean*ln_s[n]) + ln_t[n]
   const float* ln_stats;   // [M][ln_parts][2] partial (sum, sumsq) over the K features, or nullptr
   const float* ln_s;       // [N]
-  const float* ln_t;       // [N]
+  const float* ln_t;       // [N]; for EPI_BIAS_GELU_BF16 the caller stores t / 2 (that epilogue works on x / 2; halving is exact)
   int ln_parts;
   // producer side (EPI_BIAS_RESID_F32): raw bf16 copy of the updated rows + their partial statistics
   __nv_bfloat16* out_bf16; // [M][N] or nullptr
   float* stats_out;        // [M][(N/BN)*2][2] or nullptr
   int split3;              // fp32-class mode: A and W hold [hi | lo] bf16 halves (2K columns each); the K loop runs
                            // hi.hi, hi.lo, lo.hi (3K/BK blocks, fp32 accumulate) = the product to ~2^-16 relative
-  int tma_store;           // bf16 epilogues: 1 = store 32 x 32 blocks with TMA (tmap_c, 64B swizzle) instead of st.global
+  int tma_store;           // bf16 epilogues: 0 = smem transpose + coalesced st.global, 1 = smem block + TMA store (tmap_c, 64B
+                           // swizzle), 2 = no staging, two 256-bit stores per thread and chunk (thread = row)
+  int no_pipe;             // 1 = load the per-tile epilogue vectors / statistics at the point of use (A/B switch, BIOM3_EPI_PIPE=0)
   int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
 
@@ -114,7 +117,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   using SL = SmemLayout<BN, STAGES, CG2>;
   constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr int STG_BYTES = STG_TOTAL / EPI_WARPS;
-  constexpr int CV_BYTES = CV_TOTAL / EPI_WARPS;
+  constexpr int CV_BYTES = CV_TOTAL / 2 / EPI_WARPS;   // one buffer: scale vector, then shift vector
   constexpr int CV_HALF = CV_BYTES / 2;             // bytes of one per-column vector of a warp
   constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulator stages
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(CG2 ? 2 * BM : BM, BN);
@@ -234,7 +237,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
     constexpr int NCH = COLS_PER_WARP / 32;
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
-    const uint32_t cvs = ptx::smem_u32(smem + SL::CV_OFFSET + ew * CV_BYTES);   // scale vector, then shift vector
+    const uint32_t cvs0 = ptx::smem_u32(smem + SL::CV_OFFSET + ew * 2 * CV_BYTES);   // two buffers: scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
     constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT);
     constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT);
@@ -274,6 +277,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) res[j] = load_res(g0 + size_t(4 * j) * p.N);
       }
+    }
+    // bf16 epilogues with a folded LayerNorm: the per-tile inputs (this warp's slices of ln_s / ln_t and its rows' partial
+    // statistics) are fetched ONE TILE AHEAD — vectors with cp.async straight into the other smem buffer, statistics into
+    // 8 registers — so their L2 latency no longer sits at the head of every tile (it was ~30 % of the epilogue warps'
+    // stall samples in ncu).  Statistics with more than 4 partial slots per row fall back to loading at the point of use.
+    constexpr bool kVecEpi = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR);
+    const bool pipe = kVecEpi && p.ln_stats != nullptr && (p.ln_parts == 2 || p.ln_parts == 4) && p.debug_skip == 0 && !p.no_pipe;
+    float4 pst[2];                                        // prefetched partial statistics of this thread's row
+    auto tile_rn = [&](int t, int& rbase_o, int& nbase_o) {
+      const int tile = p.reverse ? num_tiles - 1 - t : t;
+      rbase_o = (tile / n_tiles) * TILE_M + int(cta_rank) * BM + quarter * 32;
+      nbase_o = (tile % n_tiles) * BN + col_half * COLS_PER_WARP;
+    };
+    auto prefetch_tile = [&](int t, uint32_t buf) {
+      int rb, nb;
+      tile_rn(t, rb, nb);
+      if (lane < COLS_PER_WARP / 4) {
+        ptx::cp_async_16(buf + lane * 16, p.ln_s + nb + lane * 4);
+        ptx::cp_async_16(buf + CV_HALF + lane * 16, p.ln_t + nb + lane * 4);
+      }
+      ptx::cp_async_commit();
+      const float4* sp4 = reinterpret_cast<const float4*>(p.ln_stats + size_t(rb + lane) * p.ln_parts * 2);
+      pst[0] = sp4[0];
+      if (p.ln_parts == 4) pst[1] = sp4[1];
+    };
+    if constexpr (kVecEpi) {
+      if (pipe && worker < num_tiles) prefetch_tile(worker, cvs0);
     }
     uint32_t it = 0;
     for (int t = worker; t < num_tiles; t += n_workers, ++it) {
@@ -406,7 +436,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         constexpr bool kHasVec = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR);
         float mean = 0.f, rstd = 1.f;
         const bool use_vec = kHasVec && (p.ln_stats != nullptr || p.bias != nullptr);
-        if (use_vec) {
+        const uint32_t cvs = cvs0 + (pipe ? (it & 1) * CV_BYTES : 0);
+        if (pipe) {
+          // this tile's vectors and statistics were requested one tile ago
+          float sm = 0.f, q = 0.f;
+          sm += pst[0].x; q += pst[0].y;
+          sm += pst[0].z; q += pst[0].w;
+          if (p.ln_parts == 4) {
+            sm += pst[1].x; q += pst[1].y;
+            sm += pst[1].z; q += pst[1].w;
+          }
+          mean = sm / float(p.K);
+          rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
+          ptx::cp_async_wait<0>();
+          __syncwarp();
+          if (t + n_workers < num_tiles) prefetch_tile(t + n_workers, cvs0 + ((it + 1) & 1) * CV_BYTES);
+        } else if (use_vec) {
           const float* tsrc = p.ln_stats ? p.ln_t : p.bias;
           const int vl = lane < COLS_PER_WARP / 4 ? lane : 0;      // lanes that carry a float4 of the vectors
           const float4 t4 = __ldg(reinterpret_cast<const float4*>(tsrc + nbase) + vl);
@@ -414,7 +459,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (p.ln_stats) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + nbase) + vl);
           __syncwarp();
           if (lane < COLS_PER_WARP / 4) {
-            constexpr float tsc = EPI == EPI_BIAS_GELU_BF16 ? 0.5f : 1.0f;   // the GELU epilogue works on x / 2
+            // the GELU epilogue works on x / 2; a folded-LayerNorm ln_t already holds t / 2 (see Params::ln_t)
+            const float tsc = (EPI == EPI_BIAS_GELU_BF16 && !p.ln_stats) ? 0.5f : 1.0f;
             st_shared_v4(cvs + lane * 16, __float_as_uint(s4.x), __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
             st_shared_v4(cvs + CV_HALF + lane * 16, __float_as_uint(t4.x * tsc), __float_as_uint(t4.y * tsc),
                          __float_as_uint(t4.z * tsc), __float_as_uint(t4.w * tsc));
@@ -483,7 +529,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
             }
           }
-          if (p.tma_store) {
+          if (p.tma_store == 2) {
+            // Direct stores: thread = row, its 32 columns of the chunk are 64 contiguous bytes in both output layouts ->
+            // two 256-bit stores of full 32-byte sectors, no shared-memory staging at all.  The mainloop keeps the SM's
+            // shared-memory port busy (TMA writes + MMA operand reads), so every staged byte costs mainloop time.
+            __nv_bfloat16* dst = dst0 + size_t(lane) * row_stride + size_t(c) * chunk_stride;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              ptx::st_global_v8(dst + 16 * i, ptx::pack_bf16x2(v[16 * i], v[16 * i + 1]), ptx::pack_bf16x2(v[16 * i + 2], v[16 * i + 3]),
+                                ptx::pack_bf16x2(v[16 * i + 4], v[16 * i + 5]), ptx::pack_bf16x2(v[16 * i + 6], v[16 * i + 7]),
+                                ptx::pack_bf16x2(v[16 * i + 8], v[16 * i + 9]), ptx::pack_bf16x2(v[16 * i + 10], v[16 * i + 11]),
+                                ptx::pack_bf16x2(v[16 * i + 12], v[16 * i + 13]), ptx::pack_bf16x2(v[16 * i + 14], v[16 * i + 15]));
+            continue;
+          }
+          if (p.tma_store == 1) {
             // the previous chunk's TMA store must have finished READING the staging block before it is rewritten
             if (lane == 0) ptx::tma_store_wait_read();
             __syncwarp();
@@ -493,7 +552,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             st_shared_v4(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]),
                          ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
                          ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          if (p.tma_store) {
+          if (p.tma_store == 1) {
             // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one lane stores
             ptx::fence_proxy_async();
             __syncwarp();
@@ -518,7 +577,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   }
 
-  if (p.tma_store && warp >= 2 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
+  if (p.tma_store == 1 && warp >= 2 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
   ptx::tc_fence_before();
   __syncwarp();
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();

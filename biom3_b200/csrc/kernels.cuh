@@ -187,6 +187,49 @@ __device__ __forceinline__ int categorical_draw(float logit, float q, int lane, 
   return idx;
 }
 
+// Last-layer row compaction (decode only).  After the last block's attention every remaining operation of the step
+// (out-proj, residual, LayerNorm, MLP, final norm, vocab head) is per token, and the sampler consumes only the
+// tokens of the SELECTED list below (the reference computes all B*L and discards the rest,
+// sampling_analysis.py:251-256).  This kernel copies the three per-token inputs of those operations — the attention
+// output row and the (hi, lo) residual row — for list entry ti = b' * group + g into row ti of compact buffers, so
+// the last layer's three GEMMs run on ceil256(B * group) rows instead of B * L.  Rows >= ntok are zero-filled
+// padding up to the GEMM tile height.  One warp per row, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ att, const __nv_bfloat16* __restrict__ u_hi,
+                   const __nv_bfloat16* __restrict__ u_lo, __nv_bfloat16* __restrict__ att_c,
+                   __nv_bfloat16* __restrict__ hi_c, __nv_bfloat16* __restrict__ lo_c, const int* __restrict__ inv_path,
+                   const DecodeCtl* __restrict__ ctl, int L, int D, int group, int ntok, int rows_c) {
+  ptx::pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int step = ctl->step;
+  const int n16 = D / 8;                           // 16-byte pieces per row
+  for (int ti = blockIdx.x * 8 + (threadIdx.x >> 5); ti < rows_c; ti += gridDim.x * 8) {
+    uint4* da = reinterpret_cast<uint4*>(att_c + size_t(ti) * D);
+    uint4* dh = reinterpret_cast<uint4*>(hi_c + size_t(ti) * D);
+    uint4* dl = reinterpret_cast<uint4*>(lo_c + size_t(ti) * D);
+    if (ti < ntok) {
+      const int b = ti / group;
+      const int src = (b / group) * group + (ti % group);          // sample whose location is written (head_kernel)
+      const size_t row = size_t(b) * L + inv_path[size_t(src) * L + step];
+      const uint4* sa = reinterpret_cast<const uint4*>(att + row * D);
+      const uint4* sh = reinterpret_cast<const uint4*>(u_hi + row * D);
+      const uint4* sl = reinterpret_cast<const uint4*>(u_lo + row * D);
+      for (int i = lane; i < n16; i += 32) {
+        da[i] = sa[i];
+        dh[i] = sh[i];
+        dl[i] = sl[i];
+      }
+    } else {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < n16; i += 32) {
+        da[i] = z;
+        dh[i] = z;
+        dl[i] = z;
+      }
+    }
+  }
+}
+
 // Final LayerNorm + vocab head for a list of tokens; optionally writes logits [B][C][L] and/or draws
 // and scatters tokens.  SELECTED mode (decode): token list = {(b', loc[b]) : b in group(b')},
 // loc[b] = inv_path[b][step]  -> this IS the reference's B x B unmask write.  ALL mode: every token.
@@ -202,6 +245,7 @@ struct HeadArgs {
   const int* inv_path;       // [B][L] (SELECTED mode)
   const DecodeCtl* ctl;      // step / noise / seed (sampling)
   int B, L, D, C, group;     // group = samples per reference batch (SELECTED mode); 0 -> ALL mode
+  int compact;               // SELECTED mode: the hidden rows are compacted, entry ti lives in row ti (gather_rows_kernel)
 };
 
 __global__ void __launch_bounds__(256)
@@ -225,17 +269,18 @@ head_kernel(const HeadArgs a) {
       b = ti / a.L;
       l = ti % a.L;
     }
-    const size_t row = size_t(b) * a.L + l;
+    const size_t row = size_t(b) * a.L + l;        // token position (state / logits / noise index)
+    const size_t hrow = a.compact ? size_t(ti) : row;   // row of the hidden state
     float4 v[MAXV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
         if (a.u) {
-          v[i] = *reinterpret_cast<const float4*>(a.u + row * a.D + (i * 32 + lane) * 4);
+          v[i] = *reinterpret_cast<const float4*>(a.u + hrow * a.D + (i * 32 + lane) * 4);
         } else {
-          const uint2 h = *reinterpret_cast<const uint2*>(a.u_hi + row * a.D + (i * 32 + lane) * 4);
-          const uint2 l = *reinterpret_cast<const uint2*>(a.u_lo + row * a.D + (i * 32 + lane) * 4);
+          const uint2 h = *reinterpret_cast<const uint2*>(a.u_hi + hrow * a.D + (i * 32 + lane) * 4);
+          const uint2 l = *reinterpret_cast<const uint2*>(a.u_lo + hrow * a.D + (i * 32 + lane) * 4);
           v[i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
                              __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
                              __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),

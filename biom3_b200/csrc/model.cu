@@ -260,10 +260,20 @@ struct biom3_model {
   int attn_tc = 3;                              // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM),
                                                 // 3 = 2 split into two ping-pong streams per CTA (default; BIOM3_ATTN_TC)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
-  bool tma_store = true;
+  int tma_store = 1;                            // bf16 epilogue store path, see gemm::Params::tma_store (BIOM3_TMA_STORE)
   bool use_pdl = true;                          // programmatic dependent launch between the kernels of a step
   bool serpentine = true;                       // alternate the row walking direction kernel to kernel (L2 reuse)
   int mlp_slabs = 1;                            // FF1/FF2 row slabs per layer (hid slab reused, L2 resident)
+  // Last-layer row compaction (decode, split residual): after the last block's attention only the B * group token
+  // rows the sampler consumes are carried through out-proj / MLP / head (k::gather_rows_kernel).  BIOM3_COMPACT=0
+  // computes every row like the reference does.
+  bool compact_last = true;
+  bool epi_pipe = true;                         // bf16 GEMM epilogues fetch their per-tile vectors / statistics one tile ahead
+  int compact_rows_max = 0;                     // rows allocated for the compact buffers (multiple of 256), 0 = none
+  int last_compact_rows = 0;                    // rows the last run_step() carried through the last layer's MLP (0 = all)
+  bf16 *att_c = nullptr, *a_c = nullptr, *ulo_c = nullptr, *hid_c = nullptr;
+  float* stats_c = nullptr;
+  CUtensorMap tm_att_c{}, tm_a_c{}, tm_hid_c{}, tm_st_hid_c{};
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
   cudaStream_t cap_stream = nullptr;
@@ -343,8 +353,10 @@ int upload_split(biom3_model* m, const std::string& key, size_t N, size_t K, bf1
 
 // LayerNorm folded into the following linear layer (see gemm_tcgen05.cuh): uploads W' = gamma (.) W as bf16
 // [N][K], s[n] = sum_k bf16(W'[n][k]) and t[n] = sum_k beta[k] W[n][k] (+ bias[n] if bias_key is non-empty).
+// t_scale: 0.5 for the GELU consumer, whose epilogue works on x / 2 (gemm::Params::ln_t); the halving is exact.
 int upload_folded(biom3_model* m, const std::string& g_key, const std::string& b_key, const std::string& w_key,
-                  const std::string& bias_key, size_t N, size_t K, bf16* w_dst, float* s_dst, float* t_dst) {
+                  const std::string& bias_key, size_t N, size_t K, bf16* w_dst, float* s_dst, float* t_dst,
+                  float t_scale = 1.0f) {
   const std::vector<float>*g, *b, *w, *bias = nullptr;
   int r;
   if ((r = get_w(m, g_key, K, &g))) return r;
@@ -363,7 +375,7 @@ int upload_folded(biom3_model* m, const std::string& g_key, const std::string& b
       ta += double((*b)[kk]) * double(wv);
     }
     s[n] = float(sa);
-    t[n] = float(ta + (bias ? double((*bias)[n]) : 0.0));
+    t[n] = float(ta + (bias ? double((*bias)[n]) : 0.0)) * t_scale;
   }
   CU_OK(cudaMemcpy(w_dst, wf.data(), N * K * sizeof(bf16), cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(s_dst, s.data(), N * sizeof(float), cudaMemcpyHostToDevice));
@@ -417,6 +429,13 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const bool pw = m->use_pair && m->bn_wide == 256 && M % 256 == 0, pn = m->use_pair && m->bn_narrow == 256 && M % 256 == 0;
   const int iw = (m->bn_wide == 256 && !pw) ? 1 : 0, in = (m->bn_narrow == 256 && !pn) ? 1 : 0;   // weight map: 256- or 128-row box
+  // last-layer row compaction: rows of the compact buffers, 0 = every row goes through the last layer's MLP
+  int Mc = 0;
+  if (sample && split && group > 0 && m->compact_rows_max > 0 && m->mlp_slabs == 1) {
+    const int want = (B * group + 255) / 256 * 256;
+    if (want <= m->compact_rows_max && want * 2 <= M) Mc = want;
+  }
+  m->last_compact_rows = Mc;
   int dir = 0;                                  // row walking direction of the next launch (see Params::reverse)
   auto next_dir = [&]() { const int d = dir; if (m->serpentine) dir ^= 1; return d; };
   next_dir();                                   // the embed kernel walked forward
@@ -451,10 +470,10 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   } else
   for (int j = 0; j < depth; ++j) {
     gemm::Params p{};
-    p.L = L; p.H = H; p.Bsz = B; p.M = M;
+    p.L = L; p.H = H; p.Bsz = B; p.M = M; p.no_pipe = m->epi_pipe ? 0 : 1;
     // q, k, v = LN1(u) Wqkv^T (no bias; LayerNorm folded) -> head-major bf16
     p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
-    p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store ? 1 : 0;
+    p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
     p.reverse = next_dir();
     LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
@@ -496,6 +515,22 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
     r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
     r.out_bf16 = m->a; r.stats_out = m->stats; r.reverse = next_dir();
+    const bool cl = Mc > 0 && j == depth - 1;   // compact last layer: the rest of the step runs on the selected rows only
+    if (cl) {
+      LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
+                               m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc));
+      r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+      p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
+      p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
+      p.ln_stats = m->stats_c;
+      p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
+      LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
+      r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
+      r.cond = nullptr; r.cond_stride = JD;
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+      continue;
+    }
     if (split) {
       r.out = m->u_lo;
       LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
@@ -528,7 +563,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     }
   }
   k::HeadArgs ha{};
-  ha.u = split ? nullptr : m->u; ha.u_hi = m->a; ha.u_lo = m->u_lo; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
+  ha.u = split ? nullptr : m->u; ha.u_hi = Mc ? m->a_c : m->a; ha.u_lo = Mc ? m->ulo_c : m->u_lo; ha.compact = Mc ? 1 : 0; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
   ha.logits_out = logits_out; ha.state = sample ? m->state : nullptr; ha.inv_path = m->inv_path; ha.ctl = m->ctl;
   ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
   const int ntok = sample ? B * group : M;
@@ -602,12 +637,14 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_BN_WIDE")) m->bn_wide = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
+  if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_EPI_PIPE")) m->epi_pipe = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   CU_OK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
@@ -703,7 +740,7 @@ int biom3_finalize_weights(biom3_model* m) {
     TRY(upload_bf16(m, P + "0.fn.to_out.weight", D * D, m->Wo + j * D * D));
     TRY(upload_f32(m, P + "0.fn.to_out.bias", D, m->bo + j * D));
     TRY(upload_folded(m, P + "1.norm.weight", P + "1.norm.bias", P + "1.fn.fn.w1.weight", P + "1.fn.fn.w1.bias", 4 * D, D,
-                      m->W1 + j * 4 * D * D, m->ln_s_ff + j * 4 * D, m->ln_t_ff + j * 4 * D));
+                      m->W1 + j * 4 * D * D, m->ln_s_ff + j * 4 * D, m->ln_t_ff + j * 4 * D, 0.5f));
     TRY(upload_bf16(m, P + "1.fn.fn.w2.weight", 4 * D * D, m->W2 + j * 4 * D * D));
     TRY(upload_f32(m, P + "1.fn.fn.w2.bias", D, m->b2 + j * D));
   }
@@ -798,6 +835,22 @@ int biom3_finalize_weights(biom3_model* m) {
       TRY(make_tmap(&m->tm_w2s[i], m->W2s, depth * D, 8 * D, box));
     }
   }
+  if (m->precision == 0 && m->split_resid && m->compact_last) {
+    // at most max_batch^2 selected tokens; worth it only while that is a fraction of the B * L rows
+    const size_t want = (Bm * Bm + 255) / 256 * 256;
+    if (want * 2 <= M) {
+      m->compact_rows_max = int(want);
+      TRY(dev_alloc(m, &m->att_c, want * D));
+      TRY(dev_alloc(m, &m->a_c, want * D));
+      TRY(dev_alloc(m, &m->ulo_c, want * D));
+      TRY(dev_alloc(m, &m->hid_c, want * 4 * D));
+      TRY(dev_alloc(m, &m->stats_c, want * size_t(m->ln_parts) * 2));
+      TRY(make_tmap(&m->tm_att_c, m->att_c, want, D, 128));
+      TRY(make_tmap(&m->tm_a_c, m->a_c, want, D, 128));
+      TRY(make_tmap(&m->tm_hid_c, m->hid_c, want, 4 * D, 128));
+      TRY(make_store_tmap(&m->tm_st_hid_c, m->hid_c, want, 4 * D));
+    }
+  }
   TRY(make_tmap(&m->tm_a, m->a, M, D, 128));
   TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
   TRY(make_tmap(&m->tm_hid, m->hid, M, 4 * D, 128));
@@ -866,8 +919,10 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
       }
       cudaGraph_t graph;
       CU_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-      cudaError_t e = run_step(m, B, group, nullptr, nullptr, true, true, m->cap_stream, nullptr, nullptr);
+      int n_launch = 0;
+      cudaError_t e = run_step(m, B, group, nullptr, nullptr, true, true, m->cap_stream, nullptr, &n_launch);
       cudaError_t e2 = cudaStreamEndCapture(m->cap_stream, &graph);
+      if (e == cudaSuccess) m->launches_per_step = n_launch;
       if (e != cudaSuccess) return fail(BIOM3_ERR_CUDA, std::string("step capture: ") + cudaGetErrorString(e));
       CU_OK(e2);
       CU_OK(cudaGraphInstantiate(&m->graph_exec, graph, 0));
@@ -888,6 +943,7 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
   if (!out) return fail(BIOM3_ERR_INVALID, "null argument");
   if (group < 1 || B % group != 0) return fail(BIOM3_ERR_INVALID, "B must be a multiple of group");
   CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());             // a decode still running on the caller's stream owns the resident state
   cudaStream_t st = m->cap_stream;
   // a valid resident state is assumed (call after a decode); run one warm step then a timed one
   set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull);
@@ -918,6 +974,7 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
   out->layernorm_ms = acc[C_LN]; out->embed_ms = acc[C_EMBED]; out->head_ms = acc[C_HEAD];
   out->other_ms = acc[C_OTHER];
   out->launches = launches;
+  out->compact_rows = m->last_compact_rows;
   return BIOM3_OK;
 }
 
@@ -1078,7 +1135,7 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_BIAS_GELU_BF16) {
     if ((r = make_store_tmap(&tc, out, M, N))) return r;
     p.tma_store = 1;
-    if (const char* e = getenv("BIOM3_TMA_STORE")) p.tma_store = atoi(e) != 0;
+    if (const char* e = getenv("BIOM3_TMA_STORE")) p.tma_store = std::max(0, std::min(2, atoi(e)));
   }
   CU_OK(init_kernel_attributes());
   switch (epi) {

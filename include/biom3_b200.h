@@ -114,6 +114,7 @@ typedef struct biom3_step_profile {
   float gemm_qkv_ms, gemm_out_ms, gemm_ff1_ms, gemm_ff2_ms;
   float local_attn_ms, linear_attn_ms, layernorm_ms, embed_ms, head_ms, other_ms;
   int32_t launches;
+  int32_t compact_rows;   /* rows carried through the LAST layer's out-proj / MLP (selected tokens, padded to 256); 0 = all B*L */
 } biom3_step_profile;
 /* Runs one decode step un-graphed with CUDA events around every launch (synchronous). */
 int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out);
@@ -132,7 +133,8 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
 int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
                       const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream);
 
-/* Number of kernel launches one decode step issues (for bench.py's gpu_launches). */
+/* Number of kernel launches one decode step issues (for bench.py's gpu_launches): the count of the most recently
+ * captured step graph, or the full-row estimate before the first decode. */
 int biom3_launches_per_step(const biom3_model* m);
 
 #ifdef __cplusplus

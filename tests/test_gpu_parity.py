@@ -233,6 +233,25 @@ def test_decode_groups_equal_separate_calls():
     assert not torch.equal(whole, fused)          # the cross-sample write makes grouping matter
 
 
+@pytest.mark.parametrize('B,group', [(6, 6), (6, 3), (8, 8)])
+def test_last_layer_row_compaction_is_bit_identical(B, group, monkeypatch):
+    """The last layer's out-proj / MLP / head run on the B * group selected token rows only (gather_rows_kernel);
+    BIOM3_COMPACT=0 carries every row like the reference.  Same trajectory, bit for bit."""
+    L, C = 256, 29
+    z = synthetic.synthetic_z_c(1, 64, seed=4).repeat(B, 1).cuda()
+    path = synthetic.synthetic_paths(B, L, seed=8).cuda()
+    noise = synthetic.synthetic_noise(L, B, L, C, seed=9).cuda()
+    out = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('BIOM3_COMPACT', flag)
+        args, sd, eng, _ = make(SMALL, B)
+        out[flag] = eng.decode(z, path, group=group, noise=noise, want_traj=True)
+        rows = eng.profile_step(B, group)['compact_rows']
+        assert rows == (256 if flag == '1' else 0)
+        assert eng.launches_per_step == 2 + 2 * 6 + 2 + (1 if flag == '1' else 0)
+    assert torch.equal(out['1'][0], out['0'][0]) and torch.equal(out['1'][1], out['0'][1])
+
+
 def test_decode_trajectory_properties_and_philox_repeatability():
     """On-device noise: same seed -> same tokens; trajectory changes only at the current locations."""
     B, L = 4, 256
