@@ -13,6 +13,13 @@
 //                 version is bound by the SM's L2->smem ingest (~43 B/clk measured, 48 KB per 512 MMA cycles);
 //                 the pair needs 32 KB per CTA for the same MMA work.
 //
+// ARES = true (CTA pairs, K <= 512, bf16 epilogues): the A row block stays RESIDENT in shared memory.  These GEMMs run at the
+// L2 throughput cap (ncu: ~11.9 TB/s of L2->SM + SM->L2 traffic on the QKV GEMM, the ~6300 B/clk LTS limit), so bytes
+// through L2 are what bounds them: a 256 x 256 tile with K = 512 pulls 256 KB of A + 256 KB of W through L2 and writes
+// 128 KB.  A worker therefore walks a CONTIGUOUS run of tiles (consecutive column tiles of one 256-row block), loads
+// the block's A once (8 k-blocks x 16 KB per CTA, one full / empty barrier pair per k-block so the next row block's
+// A streams in behind the last column tile's MMAs) and only W goes through the 4-stage ring: A traffic / n_tiles.
+//
 // Fusions (the reference runs each as separate library / element-wise kernels; block structure from
 // linear-attention-transformer, called at /root/reference/Stage3_source/cond_diff_transformer_layer.py:171):
 //   * pre-norm LayerNorm is folded into the consumer GEMM:  LN(u) W^T = rstd (u (g*W)^T - mean * sum_k g_k W_nk)
@@ -34,7 +41,9 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 // Epilogue warps per CTA.  The fp32 residual epilogues use 8 (two per TMEM lane quarter, 128 columns each, 168
 // registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
 // smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
-__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 3 || epi == 4 || epi == 5) ? 8 : 16; }
+// The A-resident variant has 16 KB of staging left: 8 warps x 2 KB.
+__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || epi == 3 || epi == 4 || epi == 5) ? 8 : 16; }
+constexpr int ARES_NK = 8;         // k-blocks of the resident A row block (K <= 512)
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
@@ -75,14 +84,16 @@ struct Params {
   int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
 
-template <int BN, int STAGES, bool CG2>
+template <int BN, int STAGES, bool CG2, bool ARES = false>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;         // weight rows staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int CV_OFFSET = STG_OFFSET + STG_TOTAL;
+  static constexpr int A_RES_BYTES = ARES ? ARES_NK * A_BYTES : 0;   // resident A row block, in front of the ring
+  static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES_TOTAL = ARES ? STG_TOTAL / 2 : STG_TOTAL;
+  static constexpr int STG_OFFSET = A_RES_BYTES + STAGES * STAGE_BYTES;
+  static constexpr int CV_OFFSET = STG_OFFSET + STG_BYTES_TOTAL;
   static constexpr int TOTAL = CV_OFFSET + CV_TOTAL + 1024;   // + alignment slack
 };
 
@@ -109,14 +120,16 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-template <int BN, int STAGES, int EPI, bool CG2>
-__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
+template <int BN, int STAGES, int EPI, bool CG2, bool ARES = false>
+__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI, ARES), 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
-  using SL = SmemLayout<BN, STAGES, CG2>;
-  constexpr int EPI_WARPS = epi_warps(EPI);
-  constexpr int STG_BYTES = STG_TOTAL / EPI_WARPS;
+  static_assert(!ARES || (CG2 && BN == 256 && (EPI == EPI_STORE_BF16 || EPI == EPI_QKV_HEADMAJOR || EPI == EPI_BIAS_GELU_BF16)),
+                "the A-resident variant is pair-tiled with a bf16 epilogue");
+  using SL = SmemLayout<BN, STAGES, CG2, ARES>;
+  constexpr int EPI_WARPS = epi_warps(EPI, ARES);
+  constexpr int STG_BYTES = SL::STG_BYTES_TOTAL / EPI_WARPS;
   constexpr int CV_BYTES = CV_TOTAL / 2 / EPI_WARPS;   // one buffer: scale vector, then shift vector
   constexpr int CV_HALF = CV_BYTES / 2;             // bytes of one per-column vector of a warp
   constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulator stages
@@ -125,6 +138,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[ARES_NK], a_empty[ARES_NK];      // ARES: one pair per resident A k-block
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -139,6 +153,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_tiles = (p.M / TILE_M) * n_tiles;
   const int nk = p.K / BK;
   const int k_blocks = p.split3 ? 3 * nk : nk;
+  // Tile walk of this worker, t = t_begin, t_begin + t_step, ... < t_end.  Round robin normally; ARES: a contiguous run,
+  // so that consecutive tiles are consecutive column tiles of the same row block (tile = row block * n_tiles + column tile).
+  int t_begin = worker, t_step = n_workers, t_end = num_tiles;
+  if constexpr (ARES) {
+    const int base = num_tiles / n_workers, rem = num_tiles % n_workers;
+    t_begin = worker * base + (worker < rem ? worker : rem);
+    t_end = t_begin + base + (worker < rem ? 1 : 0);
+    t_step = 1;
+  }
 
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
@@ -150,6 +173,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
       ptx::mbar_init(&acc_empty[s], CG2 ? 2 * EPI_WARPS : EPI_WARPS);
+    }
+    if constexpr (ARES) {
+      for (int s = 0; s < ARES_NK; ++s) {
+        ptx::mbar_init(&a_full[s], 1);
+        ptx::mbar_init(&a_empty[s], 1);
+      }
     }
     ptx::fence_mbar_init();
   }
@@ -172,10 +201,29 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = worker; t < num_tiles; t += n_workers) {
+      int cur_mb = -1;
+      uint32_t run = 0;                                    // ARES: row-block runs started so far
+      for (int t = t_begin; t < t_end; t += t_step) {
         const int tile = p.reverse ? num_tiles - 1 - t : t;
         const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
         const int n0 = (tile % n_tiles) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
+        if constexpr (ARES) {
+          const bool new_mb = tile / n_tiles != cur_mb;
+          if (new_mb) { cur_mb = tile / n_tiles; ++run; }
+          for (int kb = 0; kb < nk; ++kb) {
+            if (new_mb) {
+              // slot kb of the resident block is free once the previous run's last tile has consumed it
+              ptx::mbar_wait_parked(&a_empty[kb], (run & 1) ^ 0);      // run r (1-based): parity of completion r - 1
+              if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * SL::A_BYTES);
+              ptx::tma_load_2d_cg2(smem + kb * SL::A_BYTES, &tmap_a, &a_full[kb], kb * BK, m0 + p.a_row_offset);
+            }
+            ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::B_BYTES);
+            ptx::tma_load_2d_cg2(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
@@ -201,11 +249,35 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ MMA issuer (leader CTA only when paired)
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
+      int cur_mb = -1;
+      uint32_t run = 0;
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         ptx::mbar_wait_parked(&acc_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        if constexpr (ARES) {
+          const int mb = (p.reverse ? num_tiles - 1 - t : t) / n_tiles;
+          const bool new_mb = mb != cur_mb;
+          if (new_mb) { cur_mb = mb; ++run; }
+          // the run's last tile hands the resident A k-blocks back, one by one, behind its own MMAs
+          const bool last_of_run = t + 1 >= t_end || (p.reverse ? num_tiles - 2 - t : t + 1) / n_tiles != mb;
+          for (int kb = 0; kb < nk; ++kb) {
+            if (new_mb) ptx::mbar_wait(&a_full[kb], (run & 1) ^ 1);      // run r (1-based) waits completion r
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smem + kb * SL::A_BYTES));
+            const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+            ptx::umma_commit_cg2(&empty_bar[stage], 3);
+            if (last_of_run) ptx::umma_commit_cg2(&a_empty[kb], 3);
+            if (kb == nk - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -272,8 +344,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // prefetch register waits for its load at the spill store).
     uint4 res[8];
     if constexpr (RESID) {
-      if (worker < num_tiles) {
-        const size_t g0 = tile_goff(worker);
+      if (t_begin < t_end) {
+        const size_t g0 = tile_goff(t_begin);
 #pragma unroll
         for (int j = 0; j < 8; ++j) res[j] = load_res(g0 + size_t(4 * j) * p.N);
       }
@@ -303,10 +375,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (p.ln_parts == 4) pst[1] = sp4[1];
     };
     if constexpr (kVecEpi) {
-      if (pipe && worker < num_tiles) prefetch_tile(worker, cvs0);
+      if (pipe && t_begin < t_end) prefetch_tile(t_begin, cvs0);
     }
     uint32_t it = 0;
-    for (int t = worker; t < num_tiles; t += n_workers, ++it) {
+    for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int tile = p.reverse ? num_tiles - 1 - t : t;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
@@ -337,8 +409,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
         const size_t goff = tile_goff(t);
-        const int next_t = t + n_workers;
-        const bool have_next = next_t < num_tiles;
+        const int next_t = t + t_step;
+        const bool have_next = next_t < t_end;
         const size_t gnext = have_next ? tile_goff(next_t) : 0;
         float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
         if constexpr (RESID) {
@@ -450,7 +522,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
           ptx::cp_async_wait<0>();
           __syncwarp();
-          if (t + n_workers < num_tiles) prefetch_tile(t + n_workers, cvs0 + ((it + 1) & 1) * CV_BYTES);
+          if (t + t_step < t_end) prefetch_tile(t + t_step, cvs0 + ((it + 1) & 1) * CV_BYTES);
         } else if (use_vec) {
           const float* tsrc = p.ln_stats ? p.ln_t : p.bias;
           const int vl = lane < COLS_PER_WARP / 4 ? lane : 0;      // lanes that carry a float4 of the vectors

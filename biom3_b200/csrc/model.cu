@@ -119,6 +119,32 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
 
 template <int BN, bool CG2>
 constexpr int gemm_stages() { return CG2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : 5); }
+constexpr int ARES_STAGES = 4;     // weight-ring stages of the A-resident variant (gemm_tcgen05.cuh)
+
+// A-resident pair-tiled launch (bf16 epilogues, K <= 512): contiguous tile runs per CTA pair
+template <int EPI>
+void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p,
+                      int num_sms, cudaStream_t st) {
+  const int smem = gemm::SmemLayout<256, ARES_STAGES, true, true>::TOTAL;
+  const int tiles = (p.M / 256) * (p.N / 256);
+  const int workers = num_sms / 2;
+  const int grid = (tiles < workers ? tiles : workers) * 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(64 + 32 * gemm::epi_warps(EPI, true));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>, ta, tb, tc, p);
+}
 
 // launch only; the caller checks cudaGetLastError()
 template <int BN, int EPI, bool CG2>
@@ -180,6 +206,15 @@ cudaError_t init_kernel_attributes_impl() {
   SET_GEMM(gemm::EPI_STORE_F32)
 #undef SET_GEMM1
 #undef SET_GEMM
+#define SET_ARES(EPI)                                                                                            \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>,                           \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
+                           gemm::SmemLayout<256, ARES_STAGES, true, true>::TOTAL);                               \
+  if (e != cudaSuccess) return e;
+  SET_ARES(gemm::EPI_STORE_BF16)
+  SET_ARES(gemm::EPI_QKV_HEADMAJOR)
+  SET_ARES(gemm::EPI_BIAS_GELU_BF16)
+#undef SET_ARES
   e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LOCAL_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -268,6 +303,10 @@ struct biom3_model {
   // rows the sampler consumes are carried through out-proj / MLP / head (k::gather_rows_kernel).  BIOM3_COMPACT=0
   // computes every row like the reference does.
   bool compact_last = true;
+  bool a_res = false;                           // QKV / FF1: A-resident pair-tiled GEMM (K <= 512), see gemm_tcgen05.cuh (BIOM3_ARES=1).
+                                                // Bit-identical and halves the L2->SM operand traffic, but measured no faster
+                                                // (step 9.99 vs 9.97 ms): these GEMMs are not L2-bound, so the default stays
+                                                // the streaming ring for both operands
   bool epi_pipe = true;                         // bf16 GEMM epilogues fetch their per-tile vectors / statistics one tile ahead
   int compact_rows_max = 0;                     // rows allocated for the compact buffers (multiple of 256), 0 = none
   int last_compact_rows = 0;                    // rows the last run_step() carried through the last layer's MLP (0 = all)
@@ -436,6 +475,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     if (want <= m->compact_rows_max && want * 2 <= M) Mc = want;
   }
   m->last_compact_rows = Mc;
+  const bool ares = m->a_res && m->precision == 0 && M % 256 == 0 && D <= gemm::ARES_NK * gemm::BK && (3 * D) % 256 == 0;
   int dir = 0;                                  // row walking direction of the next launch (see Params::reverse)
   auto next_dir = [&]() { const int d = dir; if (m->serpentine) dir ^= 1; return d; };
   next_dir();                                   // the embed kernel walked forward
@@ -476,7 +516,10 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
     p.reverse = next_dir();
-    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
+    if (ares)
+      LAUNCH(C_QKV, launch_gemm_ares<gemm::EPI_QKV_HEADMAJOR>(m->tm_a, m->tm_wqkv[0], m->tm_st_qkv, p, m->num_sms, st));
+    else
+      LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
     const int adir = next_dir();                // both attention kernels read the same QKV output
     // The two attention kernels read the same QKV output and write disjoint column ranges of `att`.  Outside the
     // profiler they are forked onto two streams (two branches of the step graph): the linear heads are latency /
@@ -525,7 +568,10 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
       p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-      LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
+      if (ares)
+        LAUNCH(C_FF1, launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(m->tm_a_c, m->tm_w1[0], m->tm_st_hid_c, p, m->num_sms, st));
+      else
+        LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
       LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
@@ -548,7 +594,10 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
       p.ln_stats = m->stats + row0 * m->ln_parts * 2;
       p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-      LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
+      if (ares)
+        LAUNCH(C_FF1, launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(m->tm_a, m->tm_w1[0], m->tm_st_hid, p, m->num_sms, st));
+      else
+        LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
       r.M = Ms; r.a_row_offset = 0; r.reverse = next_dir();
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.out = m->u + row0 * D; r.out_bf16 = m->a + row0 * D; r.stats_out = m->stats + row0 * m->ln_parts * 2;
@@ -645,6 +694,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_EPI_PIPE")) m->epi_pipe = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_ARES")) m->a_res = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   CU_OK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
@@ -1109,7 +1159,10 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   if (block_n != 128 && block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 128 or 256");
   if (M % 128 || N % block_n || K % 64) return fail(BIOM3_ERR_INVALID, "M%128, N%block_n, K%64 must be 0");
   const int split3 = (pair >> 1) & 1;          // bit 1: A and W are [hi | lo] halves of width 2K (fp32-class schedule)
+  const int ares = (pair >> 2) & 1;            // bit 2: A-resident pair tiling (bf16 epilogues 0 / 2, K <= 512)
   pair &= 1;
+  if (ares && (!pair || split3 || K > gemm::ARES_NK * gemm::BK || (epi != gemm::EPI_STORE_BF16 && epi != gemm::EPI_BIAS_GELU_BF16)))
+    return fail(BIOM3_ERR_INVALID, "A-resident tiling needs pair tiling, K <= 512 and a bf16 epilogue");
   if (pair && (block_n != 256 || M % 256)) return fail(BIOM3_ERR_INVALID, "pair tiling needs block_n == 256 and M % 256 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static cudaDeviceProp prop;
@@ -1139,10 +1192,15 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   }
   CU_OK(init_kernel_attributes());
   switch (epi) {
-    case gemm::EPI_STORE_BF16: launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_STORE_BF16:
+      if (ares) launch_gemm_ares<gemm::EPI_STORE_BF16>(ta, tb, tc, p, sms, st);
+      else launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
+      break;
     case gemm::EPI_BIAS_GELU_BF16:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+      if (ares) launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(ta, tb, tc, p, sms, st);
+      else launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
+      break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
       launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;

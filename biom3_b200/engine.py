@@ -161,9 +161,10 @@ def unmask_(state: torch.Tensor, tok: torch.Tensor, path: torch.Tensor, step: in
 
 
 def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int,
-              out: Optional[torch.Tensor] = None, pair: bool = False, split3: bool = False) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, pair: bool = False, split3: bool = False, ares: bool = False) -> torch.Tensor:
     """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h).
-    split3: A and W are [hi | lo] bf16 halves, [M, 2K] and [N, 2K] (the fp32-class K schedule)."""
+    split3: A and W are [hi | lo] bf16 halves, [M, 2K] and [N, 2K] (the fp32-class K schedule).
+    ares: the A-resident pair tiling (pair=True, K <= 512, epi 0 or 2)."""
     lib = _lib.load()
     M, K = A.shape
     N = W.shape[0]
@@ -174,7 +175,7 @@ def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ep
             raise ValueError('epilogue 5 updates `out` = bf16 [2, M, N] (hi plane, lo plane) in place')
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
     with torch.cuda.device(A.device):
-        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0),
+        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0) | (4 if ares else 0),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
     return out
 

@@ -67,6 +67,25 @@ def test_gemm_epilogues(bn, pair):
     assert rel_err(out, resid + ref + bias) < 1e-5                                     # in-place residual
 
 
+@pytest.mark.parametrize('M,N,K', [(256, 256, 64), (1024, 1536, 512), (20224, 2048, 512), (37888, 1536, 256), (4096, 2048, 512),
+                                   (65536, 1536, 512)])
+def test_gemm_a_resident_matches_streaming_pair_kernel(M, N, K):
+    """A-resident pair tiling (contiguous tile runs, the A row block loaded once per run) against torch fp32 and, bit for bit,
+    against the streaming pair kernel (same per-element accumulation order); uneven runs, runs that start mid row block,
+    K < 512, and both bf16 epilogues."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.float() @ W.float().t()
+    for epi, want in ((0, ref), (2, torch.nn.functional.gelu(ref + bias))):
+        got = engine.gemm_test(A, W, bias, epi, 256, pair=True, ares=True)
+        base = engine.gemm_test(A, W, bias, epi, 256, pair=True)
+        assert rel_err(got.float(), want) < 4e-3
+        assert torch.equal(got, base)
+
+
 # ---------------------------------------------------------------- sampler kernels, bit exact
 @pytest.mark.parametrize('B,L', [(1, 128), (5, 512), (64, 1024)])
 def test_sample_all_bit_exact(B, L):

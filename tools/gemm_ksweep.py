@@ -15,19 +15,23 @@ def run():
     from biom3_b200 import engine
     M = 65536
     skip = os.environ.get('BIOM3_EPI_SKIP', '0')
-    for (N, epi, name) in [(2048, 2, 'ff1 bias+gelu bf16'), (1536, 0, 'store bf16'), (512, 5, 'split resid')]:
-        for K in (128, 256, 512, 1024, 2048):
+    ares = os.environ.get('KSWEEP_ARES', '0') == '1'          # A-resident pair tiling (bf16 epilogues, K <= 512)
+    shapes = [(2048, 2, 'ff1 bias+gelu bf16'), (1536, 0, 'store bf16'), (512, 5, 'split resid')]
+    if ares:
+        shapes = [(N, e, 'ARES ' + n) for (N, e, n) in shapes if e != 5]
+    for (N, epi, name) in shapes:
+        for K in ((128, 256, 512) if ares else (128, 256, 512, 1024, 2048)):
             A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
             W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
             bias = torch.randn(N, device='cuda')
             out = torch.zeros(2, M, N, device='cuda', dtype=torch.bfloat16) if epi == 5 else torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
             for _ in range(3):
-                engine.gemm_test(A, W, bias, epi, 256, out=out, pair=True)
+                engine.gemm_test(A, W, bias, epi, 256, out=out, pair=True, ares=ares)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
-                engine.gemm_test(A, W, bias, epi, 256, out=out, pair=True)
+                engine.gemm_test(A, W, bias, epi, 256, out=out, pair=True, ares=ares)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 10 * 1e3

@@ -2,14 +2,14 @@
 set -x
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-BIOM3_TMA_STORE=2 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "gemm or forward or decode_vs_reference" > gpurun_out/pytest_store2.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_store2.log
-tail -4 gpurun_out/pytest_store2.log
-for st in 1 2; do
-  BIOM3_TMA_STORE=$st BIOM3_EPI_SKIP=0 python tools/gemm_ksweep.py run 2>&1 | grep -v "split resid" | sed "s/^/store=$st /" >> gpurun_out/ksweep_store.log
-done
-cat gpurun_out/ksweep_store.log
-for st in 1 2 1 2; do
-  BIOM3_TMA_STORE=$st timeout 300 python tools/ab_step.py 384 2>/dev/null | tail -1 >> gpurun_out/ab_store.jsonl
-done
-cat gpurun_out/ab_store.jsonl
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_full.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu_full.log
+tail -4 gpurun_out/pytest_gpu_full.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke.log
+tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+echo "bench exit $?"
+cat gpurun_out/bench_final.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+echo "ncu exit $?"
