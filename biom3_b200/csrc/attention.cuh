@@ -162,12 +162,17 @@ local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 // Linear attention (global heads): q <- softmax_d(q) * dh^-0.5 ; k <- softmax over the L tokens ;
 // ctx = k^T v (32 x 32) ; out = q ctx.  One CTA (4 warps) per (global head, sample).
 //   phase A  each warp streams a quarter of the sequence in 32-row chunks (cp.async, 2 stages) and
-//            accumulates exp(k - running max)^T v on the tensor cores (mma.sync, fp32 accumulators),
-//            rescaling when the running per-feature max moves (the softmax over tokens is shift invariant)
+//            accumulates exp(k - reference)^T v on the tensor cores (mma.sync, fp32 accumulators).  The softmax over
+//            tokens is shift invariant, so the per-feature reference only has to stay within e^8 of the running
+//            maximum: it moves (and the accumulators are rescaled) only when a chunk's maximum exceeds it by more
+//            than 8 — after the first chunk practically never — which takes the per-chunk rescale of the 32 x 32
+//            context out of the loop (the kernel is issue bound)
 //   merge    the four partial (max, denominator, ctx) sets are combined in shared memory -> ctx^T bf16
 //   phase B  each warp softmaxes its q rows in registers (quad shuffles) and multiplies by ctx
 // ------------------------------------------------------------------------------------------------
 constexpr int LIN_CH = 32;                         // rows per chunk
+constexpr float LIN_LAZY = 8.0f;                   // the column reference may trail the running maximum by e^8
+constexpr float LOG2E = 1.4426950408889634f;
 constexpr int LIN_STAGE_BYTES = 2 * LIN_CH * 64;   // k + v (or q alone in phase B)
 constexpr int LIN_WARP_BYTES = 2 * LIN_STAGE_BYTES;
 constexpr int LIN_SMEM_BYTES = 4 * LIN_WARP_BYTES + 4 * DH * DH * 4 + 2 * 4 * DH * 4 + DH * 64;
@@ -254,22 +259,25 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         }
         cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
         cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-        const float mn = fmaxf(mrun[mt][hf], cm);
-        const float f = __expf(mrun[mt][hf] - mn);
-        mrun[mt][hf] = mn;
-        den[mt][hf] *= f;
+        // lazy reference (quad-uniform: the four lanes of a quad own the same features): -inf on the first chunk
+        if (cm > mrun[mt][hf] + LIN_LAZY) {
+          const float f = __expf(mrun[mt][hf] - cm);       // 0 on the first chunk
+          mrun[mt][hf] = cm;
+          den[mt][hf] *= f;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          acc[mt][nt][2 * hf] *= f;
-          acc[mt][nt][2 * hf + 1] *= f;
+          for (int nt = 0; nt < 4; ++nt) {
+            acc[mt][nt][2 * hf] *= f;
+            acc[mt][nt][2 * hf + 1] *= f;
+          }
         }
+        const float ml2 = mrun[mt][hf] * LOG2E;
         float dsum = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
           for (int q2 = 0; q2 < 2; ++q2) {
             const float2 x = bf2_to_f2(kr[ks][mt][hf + 2 * q2]);
-            const float e0 = __expf(x.x - mn), e1 = __expf(x.y - mn);
+            const float e0 = fast_ex2(fmaf(x.x, LOG2E, -ml2)), e1 = fast_ex2(fmaf(x.y, LOG2E, -ml2));
             dsum += e0 + e1;
             kr[ks][mt][hf + 2 * q2] = ptx::pack_bf16x2(e0, e1);
           }
@@ -359,10 +367,11 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         float s = 0.f;
+        const float mxl = mx * LOG2E;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          x[i].x = __expf(x[i].x - mx);
-          x[i].y = __expf(x[i].y - mx);
+          x[i].x = fast_ex2(fmaf(x[i].x, LOG2E, -mxl));
+          x[i].y = fast_ex2(fmaf(x[i].y, LOG2E, -mxl));
           s += x[i].x + x[i].y;
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);

@@ -43,6 +43,10 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 // smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
 // The A-resident variant has 16 KB of staging left: 8 warps x 2 KB.
 __host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || epi == 3 || epi == 4 || epi == 5) ? 8 : 16; }
+// First epilogue warp.  RD = 2 (two residual chunks prefetched, 64 registers) does not fit the 168 registers a 10-warp CTA
+// gets, so that variant pads the two control warps to a full warpgroup (warps 2, 3 idle) and moves registers with
+// setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the 384 x 168 the CTA was launched with (an inc beyond the pool would block forever).
+__host__ __device__ constexpr int epi_warp0(int rd) { return rd == 2 ? 4 : 2; }
 constexpr int ARES_NK = 8;         // k-blocks of the resident A row block (K <= 512)
 
 enum Epi : int {
@@ -120,15 +124,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-template <int BN, int STAGES, int EPI, bool CG2, bool ARES = false>
-__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI, ARES), 1)
+template <int BN, int STAGES, int EPI, bool CG2, bool ARES = false, int RD = 1>
+__global__ void __launch_bounds__(32 * (epi_warp0(RD) + epi_warps(EPI, ARES)), 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
+  static_assert(RD == 1 || RD == 2, "residual prefetch depth");
   static_assert(!ARES || (CG2 && BN == 256 && (EPI == EPI_STORE_BF16 || EPI == EPI_QKV_HEADMAJOR || EPI == EPI_BIAS_GELU_BF16)),
                 "the A-resident variant is pair-tiled with a bf16 epilogue");
   using SL = SmemLayout<BN, STAGES, CG2, ARES>;
   constexpr int EPI_WARPS = epi_warps(EPI, ARES);
+  constexpr uint32_t EPI_WARP0 = epi_warp0(RD);
   constexpr int STG_BYTES = SL::STG_BYTES_TOTAL / EPI_WARPS;
   constexpr int CV_BYTES = CV_TOTAL / 2 / EPI_WARPS;   // one buffer: scale vector, then shift vector
   constexpr int CV_HALF = CV_BYTES / 2;             // bytes of one per-column vector of a warp
@@ -197,6 +203,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
   ptx::pdl_sync();          // everything above touched only this CTA's smem / TMEM
 
+  // (setmaxnreg sits at the head of each role branch so that it dominates the code whose register budget it changes)
+  if (warp < EPI_WARP0) {
+  if constexpr (RD == 2) ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
@@ -301,9 +310,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
       }
     }
+  }
   } else {
-    // ------------------------------------------------------------ epilogue (8 warps, every CTA)
-    const uint32_t ew = warp - 2;
+    // ------------------------------------------------------------ epilogue (8 or 16 warps, every CTA)
+    if constexpr (RD == 2) ptx::setmaxnreg_inc<224>();
+    const uint32_t ew = warp - EPI_WARP0;
     const uint32_t quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
     const uint32_t col_half = ew >> 2;                 // 2 or 4 warps share a lane quarter and split the columns
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
@@ -338,16 +349,24 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         else ptx::mbar_arrive(&acc_empty[as]);
       }
     };
-    // Residual rows of the chunk being processed; each slot is reloaded with the NEXT chunk's value (or the next
-    // tile's first chunk) right after it is consumed, so every load has a full chunk period to land while only 32
-    // registers hold prefetched data (a second buffer pushed this 168-register path into spills, and a spilled
-    // prefetch register waits for its load at the spill store).
-    uint4 res[8];
+    // Residual rows of the chunk being processed; each slot is reloaded right after it is consumed with the value of the
+    // chunk RD positions later in the walk (the next tile's first chunks at the end of a tile), so every load has RD chunk
+    // periods to land.  RD = 1 (default): 32 registers of prefetched data; RD = 2: two buffers used alternately, 64 registers.
+    // ncu attributes 35-45 % of this epilogue's stall samples to these loads and the K sweep in DESIGN.md shows 10.8 us per
+    // tile whatever K is, which reads as latency bound — but RD = 2 measured 3 % SLOWER per tile and 7 % slower on the
+    // out-proj GEMM in the step, so the second chunk period is not what it lacks.  Kept as a switch (BIOM3_RESID_DEPTH=2).
+    // Chunk walk: RD = 1 visits the 32-column chunks 0, 2, 1, 3 so that the prefetch of the next chunk never touches the
+    // 128-byte line the current chunk is storing to (two chunks of a bf16 plane share a line); with RD = 2 the loads
+    // issued during a chunk are for the position after next, and the natural order 0, 1, 2, 3 keeps THOSE on the other line.
+    auto order = [](int i) { return (SPLIT && NCH == 4 && RD == 1) ? (((i & 1) << 1) | (i >> 1)) : i; };
+    uint4 res[RD][8];
     if constexpr (RESID) {
       if (t_begin < t_end) {
         const size_t g0 = tile_goff(t_begin);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = load_res(g0 + size_t(4 * j) * p.N);
+        for (int b = 0; b < RD; ++b)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[b][j] = load_res(g0 + order(b) * 32 + size_t(4 * j) * p.N);
       }
     }
     // bf16 epilogues with a folded LayerNorm: the per-tile inputs (this warp's slices of ln_s / ln_t and its rows' partial
@@ -427,12 +446,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
-          // Split form: a 128-byte line of a bf16 plane spans two 32-column chunks; walking the chunks 0, 2, 1, 3 keeps
-          // the prefetch of the next chunk off the line the current chunk is storing to.
-          auto order = [](int i) { return (SPLIT && NCH == 4) ? (((i & 1) << 1) | (i >> 1)) : i; };
           const int c = order(ci);
-          const bool more = (ci + 1 < NCH) || have_next;
-          const size_t gn = (ci + 1 < NCH) ? goff + order(ci + 1) * 32 : gnext;
+          // position ci + RD of the walk: a later chunk of this tile, or one of the next tile's first RD chunks
+          const bool more = (ci + RD < NCH) || have_next;
+          const size_t gn = (ci + RD < NCH) ? goff + order(ci + RD) * 32 : gnext + order(ci + RD - NCH) * 32;
+          auto& resb = res[ci % RD];                           // buffer of this position (NCH is a multiple of RD)
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
@@ -448,8 +466,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint4 a4 = ld_shared_v4(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
             if constexpr (RESID) {
-              const uint4 rb = res[j];
-              if (more) res[j] = load_res(gn + size_t(4 * j) * p.N);
+              const uint4 rb = resb[j];
+              if (more) resb[j] = load_res(gn + size_t(4 * j) * p.N);
               float4 rv;
               if constexpr (SPLIT) {
                 rv = make_float4(__uint_as_float(rb.x << 16) + __uint_as_float(rb.z << 16),
@@ -649,7 +667,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   }
 
-  if (p.tma_store == 1 && warp >= 2 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
+  if (p.tma_store == 1 && warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
   ptx::tc_fence_before();
   __syncwarp();
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();

@@ -147,7 +147,7 @@ void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 }
 
 // launch only; the caller checks cudaGetLastError()
-template <int BN, int EPI, bool CG2>
+template <int BN, int EPI, bool CG2, int RD = 1>
 void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p,
                    int num_sms, cudaStream_t st) {
   constexpr int STAGES = gemm_stages<BN, CG2>();
@@ -158,7 +158,7 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   if constexpr (CG2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(64 + 32 * gemm::epi_warps(EPI));
+    cfg.blockDim = dim3(32 * (gemm::epi_warp0(RD) + gemm::epi_warps(EPI)));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -170,7 +170,7 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, p);
+    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true, false, RD>, ta, tb, tc, p);
   } else {
     launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(64 + 32 * gemm::epi_warps(EPI)), size_t(smem), st,
              ta, tb, tc, p);
@@ -179,12 +179,18 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 
 // bn: 128 or 256 columns per tile.  pair: CTA-pair (cta_group::2) tiling, needs bn == 256 and M % 256 == 0;
 // `tb` must then be the 128-row-box weight map (each CTA stages half of the 256 weight rows).
+// rd: residual prefetch depth of the pair-tiled residual epilogues (1 or 2, see gemm_tcgen05.cuh); ignored elsewhere
 template <int EPI>
 void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                 const gemm::Params& p, int num_sms, cudaStream_t st) {
+                 const gemm::Params& p, int num_sms, cudaStream_t st, int rd = 1) {
+  constexpr bool kResid = (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT);
   if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, tc, p, num_sms, st);
-  else if (pair) launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
-  else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
+  else if (pair) {
+    if constexpr (kResid) {
+      if (rd == 2) { launch_gemm_t<256, EPI, true, 2>(ta, tb, tc, p, num_sms, st); return; }
+    }
+    launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
+  } else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -206,6 +212,14 @@ cudaError_t init_kernel_attributes_impl() {
   SET_GEMM(gemm::EPI_STORE_F32)
 #undef SET_GEMM1
 #undef SET_GEMM
+#define SET_RD2(EPI)                                                                                             \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, gemm_stages<256, true>(), EPI, true, false, 2>,          \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
+                           gemm::SmemLayout<256, gemm_stages<256, true>(), true>::TOTAL);                        \
+  if (e != cudaSuccess) return e;
+  SET_RD2(gemm::EPI_BIAS_RESID_F32)
+  SET_RD2(gemm::EPI_BIAS_RESID_SPLIT)
+#undef SET_RD2
 #define SET_ARES(EPI)                                                                                            \
   e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>,                           \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
@@ -307,6 +321,9 @@ struct biom3_model {
                                                 // Bit-identical and halves the L2->SM operand traffic, but measured no faster
                                                 // (step 9.99 vs 9.97 ms): these GEMMs are not L2-bound, so the default stays
                                                 // the streaming ring for both operands
+  int resid_depth = 1;                          // residual prefetch depth of the out-proj / FF2 epilogues (BIOM3_RESID_DEPTH=1|2).
+                                                // 2 (two chunks in flight, setmaxnreg register reallocation) measured SLOWER:
+                                                // out-proj 1.34 -> 1.44 ms/step, 11.5 -> 11.8 us per tile in the K sweep
   bool epi_pipe = true;                         // bf16 GEMM epilogues fetch their per-tile vectors / statistics one tile ahead
   int compact_rows_max = 0;                     // rows allocated for the compact buffers (multiple of 256), 0 = none
   int last_compact_rows = 0;                    // rows the last run_step() carried through the last layer's MLP (0 = all)
@@ -496,7 +513,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       gemm::Params r{};
       r.L = L; r.H = H; r.Bsz = B; r.M = M; r.split3 = 1;
       r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_a2, m->tm_wo2[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_a2, m->tm_wo2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       LAUNCH(C_LN, f32p::ln_split_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D, m->ln2_b + size_t(j) * D,
                                                                     m->a2, M, D));
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid32;
@@ -505,7 +522,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
       r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid2, m->tm_w2s[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid2, m->tm_w2s[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
     }
   } else
   for (int j = 0; j < depth; ++j) {
@@ -563,7 +580,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
                                m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc));
       r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
@@ -574,14 +591,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
         LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       continue;
     }
     if (split) {
       r.out = m->u_lo;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
     } else {
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
     }
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t), then
     // u += hid . W2^T + b2 (+ next layer's conditioning vector).  Optionally in row slabs that reuse one hid
@@ -605,9 +622,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.cond_stride = JD;
       if (split) {
         r.out = m->u_lo + row0 * D;
-        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       } else {
-        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
+        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       }
     }
   }
@@ -695,6 +712,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_EPI_PIPE")) m->epi_pipe = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ARES")) m->a_res = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_RESID_DEPTH")) m->resid_depth = atoi(e) == 2 ? 2 : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   CU_OK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
@@ -1191,6 +1209,8 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
     if (const char* e = getenv("BIOM3_TMA_STORE")) p.tma_store = std::max(0, std::min(2, atoi(e)));
   }
   CU_OK(init_kernel_attributes());
+  int rd = 1;
+  if (const char* e = getenv("BIOM3_RESID_DEPTH")) rd = atoi(e) == 2 ? 2 : 1;
   switch (epi) {
     case gemm::EPI_STORE_BF16:
       if (ares) launch_gemm_ares<gemm::EPI_STORE_BF16>(ta, tb, tc, p, sms, st);
@@ -1203,12 +1223,12 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
       break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
     case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_BIAS_RESID_SPLIT:      // out = bf16 [2][M][N]: hi plane then lo plane, updated in place
       p.out_bf16 = reinterpret_cast<bf16*>(out);
       p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
-      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -38,6 +38,13 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Warp-specialised register reallocation (whole warpgroups, sm_90+): the control warpgroup gives registers away, the
+// epilogue warpgroups take them.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
