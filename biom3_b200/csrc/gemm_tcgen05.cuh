@@ -42,7 +42,7 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 // registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
 // smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
 // The A-resident variant has 16 KB of staging left: 8 warps x 2 KB.
-__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || epi == 3 || epi == 4 || epi == 5) ? 8 : 16; }
+__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || (epi >= 3 && epi <= 7)) ? 8 : 16; }
 // First epilogue warp.  RD = 2 (two residual chunks prefetched, 64 registers) does not fit the 168 registers a 10-warp CTA
 // gets, so that variant pads the two control warps to a full warpgroup (warps 2, 3 idle) and moves registers with
 // setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the 384 x 168 the CTA was launched with (an inc beyond the pool would block forever).
@@ -58,6 +58,12 @@ enum Epi : int {
   EPI_BIAS_RESID_SPLIT = 5, // like 3, but R lives as two bf16 arrays, R = hi + lo (hi = bf16(R), lo = bf16(R - hi)):
                             // `out_bf16` is hi (the array the next GEMM reads as its A operand), `out` is lo.  Same
                             // bytes read, 2 instead of 6 bytes per element written; R keeps 16 significant bits.
+  EPI_BIAS_RESID_SPLIT8 = 6, // like 5 with the remainder in ONE byte (ptx::split8_*): `out` is the tiled uint8 lo plane.  3 instead
+                            // of 4 bytes per element read and written by the two HBM-bound residual GEMMs.
+  EPI_BIAS_RESID_DIRECT = 7, // same data as 5 (bf16 hi + bf16 lo planes, row major), different access: thread = row end to end.
+                            // Each thread reads and writes its own row's 32 columns of a chunk as 64 contiguous bytes per
+                            // plane (two 256-bit accesses = full sectors), so there is no shared-memory transpose, no
+                            // __syncwarp, and the row statistics need no shuffles.
 };
 
 struct Params {
@@ -322,16 +328,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
     const uint32_t cvs0 = ptx::smem_u32(smem + SL::CV_OFFSET + ew * 2 * CV_BYTES);   // two buffers: scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
-    constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT);
-    constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT);
+    constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT || EPI == EPI_BIAS_RESID_SPLIT8);
+    constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT || EPI == EPI_BIAS_RESID_SPLIT8);
+    constexpr bool LO8 = (EPI == EPI_BIAS_RESID_SPLIT8);
     auto tile_goff = [&](int t) -> size_t {            // element offset of this lane's first element of a tile (row rr, group ch)
       const int tile = p.reverse ? num_tiles - 1 - t : t;
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
       return size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN + col_half * COLS_PER_WARP + 4 * ch;
     };
-    // 4 residual values at element offset `off`, as raw bits: fp32 x 4, or (hi bf16 x 4, lo bf16 x 4)
-    auto load_res = [&](size_t off) -> uint4 {
-      if constexpr (SPLIT) {
+    // byte offset of the same position in the tiled 8-bit lo plane (chunk 0, row rr): + c * 1024 per chunk, + j * 128 per 4 rows
+    auto tile_loff = [&](int t) -> size_t {
+      const int tile = p.reverse ? num_tiles - 1 - t : t;
+      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
+      return ptx::lo8_offset(size_t(m0 + quarter * 32 + rr), (tile % n_tiles) * BN + col_half * COLS_PER_WARP + 4 * ch, p.N);
+    };
+    // 4 residual values at element offset `off`, as raw bits: fp32 x 4, (hi bf16 x 4, lo bf16 x 4) or (hi bf16 x 4, lo s8 x 4)
+    auto load_res = [&](size_t off, size_t loff) -> uint4 {
+      if constexpr (LO8) {
+        const uint2 h = *reinterpret_cast<const uint2*>(p.out_bf16 + off);
+        const uint32_t l = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.out) + loff);
+        return make_uint4(h.x, h.y, l, 0u);
+      } else if constexpr (SPLIT) {
         const uint2 h = *reinterpret_cast<const uint2*>(p.out_bf16 + off);
         const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + off);
         return make_uint4(h.x, h.y, l.x, l.y);
@@ -360,13 +377,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // issued during a chunk are for the position after next, and the natural order 0, 1, 2, 3 keeps THOSE on the other line.
     auto order = [](int i) { return (SPLIT && NCH == 4 && RD == 1) ? (((i & 1) << 1) | (i >> 1)) : i; };
     uint4 res[RD][8];
+    uint32_t dres[4][8];                                   // EPI_BIAS_RESID_DIRECT: prefetched hi (2 x 32 B) and lo (2 x 32 B) of a chunk
     if constexpr (RESID) {
       if (t_begin < t_end) {
-        const size_t g0 = tile_goff(t_begin);
+        const size_t g0 = tile_goff(t_begin), l0 = LO8 ? tile_loff(t_begin) : 0;
 #pragma unroll
         for (int b = 0; b < RD; ++b)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) res[b][j] = load_res(g0 + order(b) * 32 + size_t(4 * j) * p.N);
+          for (int j = 0; j < 8; ++j) res[b][j] = load_res(g0 + order(b) * 32 + size_t(4 * j) * p.N, l0 + order(b) * 1024 + j * 128);
       }
     }
     // bf16 epilogues with a folded LayerNorm: the per-tile inputs (this warp's slices of ln_s / ln_t and its rows' partial
@@ -419,6 +437,97 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (r[lane] == 0x7fc12345u) reinterpret_cast<float*>(p.out)[0] = 1.f;   // keep the loads alive
         }
         release_acc(as);
+      } else if constexpr (EPI == EPI_BIAS_RESID_DIRECT) {
+        // thread = row.  Bias (+ the next layer's conditioning vector) of the warp's 128 columns is staged once per tile in
+        // warp-private smem and read back as broadcasts; the residual of the next chunk (or of the next tile's first
+        // chunk) is loaded into registers before the current chunk's math, as in the transposed path.
+        const int next_t = t + t_step;
+        const bool have_next = next_t < t_end;
+        auto row_ptr = [&](int tt, const __nv_bfloat16* base) {
+          int rb, nb;
+          tile_rn(tt, rb, nb);
+          return base + size_t(rb + lane) * p.N + nb;
+        };
+        __nv_bfloat16* hi_row = const_cast<__nv_bfloat16*>(row_ptr(t, p.out_bf16));
+        __nv_bfloat16* lo_row = const_cast<__nv_bfloat16*>(row_ptr(t, reinterpret_cast<const __nv_bfloat16*>(p.out)));
+        {
+          const int vl = lane < COLS_PER_WARP / 4 ? lane : 0;
+          float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + vl);
+          if (p.cond) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase) + vl);
+            b4.x += cv.x; b4.y += cv.y; b4.z += cv.z; b4.w += cv.w;
+          }
+          __syncwarp();                                    // the previous tile's reads of the staged vector are done
+          if (lane < COLS_PER_WARP / 4)
+            st_shared_v4(cvs0 + lane * 16, __float_as_uint(b4.x), __float_as_uint(b4.y), __float_as_uint(b4.z), __float_as_uint(b4.w));
+          __syncwarp();
+        }
+        auto order = [](int i) { return NCH == 4 ? (((i & 1) << 1) | (i >> 1)) : i; };   // chunks 0, 2, 1, 3: see the transposed path
+        if (it == 0) {
+          ptx::ld_global_v8(hi_row + order(0) * 32, dres[0]);
+          ptx::ld_global_v8(hi_row + order(0) * 32 + 16, dres[1]);
+          ptx::ld_global_v8(lo_row + order(0) * 32, dres[2]);
+          ptx::ld_global_v8(lo_row + order(0) * 32 + 16, dres[3]);
+        }
+        float rsum = 0.f, rsq = 0.f;
+        ptx::mbar_wait_parked(&acc_full[as], aphase);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = order(ci);
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, r);
+          uint32_t cur[4][8];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) cur[a][b] = dres[a][b];
+          if (ci + 1 < NCH) {
+            ptx::ld_global_v8(hi_row + order(ci + 1) * 32, dres[0]);
+            ptx::ld_global_v8(hi_row + order(ci + 1) * 32 + 16, dres[1]);
+            ptx::ld_global_v8(lo_row + order(ci + 1) * 32, dres[2]);
+            ptx::ld_global_v8(lo_row + order(ci + 1) * 32 + 16, dres[3]);
+          } else if (have_next) {
+            const __nv_bfloat16* nh = row_ptr(next_t, p.out_bf16);
+            const __nv_bfloat16* nl = row_ptr(next_t, reinterpret_cast<const __nv_bfloat16*>(p.out));
+            ptx::ld_global_v8(nh + order(0) * 32, dres[0]);
+            ptx::ld_global_v8(nh + order(0) * 32 + 16, dres[1]);
+            ptx::ld_global_v8(nl + order(0) * 32, dres[2]);
+            ptx::ld_global_v8(nl + order(0) * 32 + 16, dres[3]);
+          }
+          ptx::tmem_ld_wait();
+          if (ci + 1 == NCH) release_acc(as);
+          uint32_t oh[16], ol[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {                    // 4 columns: hi / lo pair words 2g, 2g + 1 of the chunk
+            const uint4 bu = ld_shared_v4(cvs0 + (c * 32 + 4 * g) * 4);
+            const uint32_t h0 = cur[g >> 2][(2 * g) & 7], h1 = cur[g >> 2][(2 * g + 1) & 7];
+            const uint32_t l0 = cur[2 + (g >> 2)][(2 * g) & 7], l1 = cur[2 + (g >> 2)][(2 * g + 1) & 7];
+            float4 o;
+            o.x = __uint_as_float(r[4 * g]) + ((__uint_as_float(h0 << 16) + __uint_as_float(l0 << 16)) + __uint_as_float(bu.x));
+            o.y = __uint_as_float(r[4 * g + 1]) + ((__uint_as_float(h0 & 0xffff0000u) + __uint_as_float(l0 & 0xffff0000u)) + __uint_as_float(bu.y));
+            o.z = __uint_as_float(r[4 * g + 2]) + ((__uint_as_float(h1 << 16) + __uint_as_float(l1 << 16)) + __uint_as_float(bu.z));
+            o.w = __uint_as_float(r[4 * g + 3]) + ((__uint_as_float(h1 & 0xffff0000u) + __uint_as_float(l1 & 0xffff0000u)) + __uint_as_float(bu.w));
+            const uint32_t n0 = ptx::pack_bf16x2(o.x, o.y), n1 = ptx::pack_bf16x2(o.z, o.w);
+            oh[2 * g] = n0;
+            oh[2 * g + 1] = n1;
+            ol[2 * g] = ptx::pack_bf16x2(o.x - __uint_as_float(n0 << 16), o.y - __uint_as_float(n0 & 0xffff0000u));
+            ol[2 * g + 1] = ptx::pack_bf16x2(o.z - __uint_as_float(n1 << 16), o.w - __uint_as_float(n1 & 0xffff0000u));
+            rsum += (o.x + o.y) + (o.z + o.w);
+            rsq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          }
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            ptx::st_global_v8(hi_row + c * 32 + 16 * hlf, oh[8 * hlf], oh[8 * hlf + 1], oh[8 * hlf + 2], oh[8 * hlf + 3], oh[8 * hlf + 4],
+                              oh[8 * hlf + 5], oh[8 * hlf + 6], oh[8 * hlf + 7]);
+            ptx::st_global_v8(lo_row + c * 32 + 16 * hlf, ol[8 * hlf], ol[8 * hlf + 1], ol[8 * hlf + 2], ol[8 * hlf + 3], ol[8 * hlf + 4],
+                              ol[8 * hlf + 5], ol[8 * hlf + 6], ol[8 * hlf + 7]);
+          }
+        }
+        if (p.stats_out) {
+          const int parts = n_tiles * 2, part = n_tile * 2 + col_half;
+          *reinterpret_cast<float2*>(p.stats_out + (size_t(rbase + lane) * parts + part) * 2) = make_float2(rsum, rsq);
+        }
       } else if constexpr (RESID || EPI == EPI_STORE_F32) {
         // fp32 path.  Read phase: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte column
         // group lane%8): every global access is 4 full 128-byte lines per warp instruction (4 x 64 bytes per array
@@ -431,6 +540,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int next_t = t + t_step;
         const bool have_next = next_t < t_end;
         const size_t gnext = have_next ? tile_goff(next_t) : 0;
+        const size_t loff = LO8 ? tile_loff(t) : 0, lnext = (LO8 && have_next) ? tile_loff(next_t) : 0;
         float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
         if constexpr (RESID) {
 #pragma unroll
@@ -450,6 +560,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // position ci + RD of the walk: a later chunk of this tile, or one of the next tile's first RD chunks
           const bool more = (ci + RD < NCH) || have_next;
           const size_t gn = (ci + RD < NCH) ? goff + order(ci + RD) * 32 : gnext + order(ci + RD - NCH) * 32;
+          const size_t ln = (ci + RD < NCH) ? loff + order(ci + RD) * 1024 : lnext + order(ci + RD - NCH) * 1024;
           auto& resb = res[ci % RD];                           // buffer of this position (NCH is a multiple of RD)
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
@@ -467,9 +578,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
             if constexpr (RESID) {
               const uint4 rb = resb[j];
-              if (more) resb[j] = load_res(gn + size_t(4 * j) * p.N);
+              if (more) resb[j] = load_res(gn + size_t(4 * j) * p.N, ln + j * 128);
               float4 rv;
-              if constexpr (SPLIT) {
+              if constexpr (LO8) {
+                rv = ptx::split8_decode(rb.x, rb.y, rb.z);
+              } else if constexpr (SPLIT) {
                 rv = make_float4(__uint_as_float(rb.x << 16) + __uint_as_float(rb.z << 16),
                                  __uint_as_float(rb.x & 0xffff0000u) + __uint_as_float(rb.z & 0xffff0000u),
                                  __uint_as_float(rb.y << 16) + __uint_as_float(rb.w << 16),
@@ -480,7 +593,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               o.x += rv.x + add.x; o.y += rv.y + add.y; o.z += rv.z + add.z; o.w += rv.w + add.w;
             }
             const size_t eoff = goff + size_t(4 * j) * p.N + c * 32;
-            if constexpr (SPLIT) {
+            if constexpr (LO8) {
+              uint32_t h0, h1, l8;
+              ptx::split8_encode(o, h0, h1, l8);
+              *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(h0, h1);
+              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out) + loff + c * 1024 + j * 128) = l8;
+            } else if constexpr (SPLIT) {
               const uint32_t h0 = ptx::pack_bf16x2(o.x, o.y), h1 = ptx::pack_bf16x2(o.z, o.w);
               *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(h0, h1);
               *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + eoff) =

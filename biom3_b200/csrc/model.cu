@@ -183,7 +183,7 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 template <int EPI>
 void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                  const gemm::Params& p, int num_sms, cudaStream_t st, int rd = 1) {
-  constexpr bool kResid = (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT);
+  constexpr bool kResid = (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT || EPI == gemm::EPI_BIAS_RESID_SPLIT8);
   if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, tc, p, num_sms, st);
   else if (pair) {
     if constexpr (kResid) {
@@ -207,6 +207,8 @@ cudaError_t init_kernel_attributes_impl() {
   SET_GEMM(gemm::EPI_QKV_HEADMAJOR)
   SET_GEMM(gemm::EPI_BIAS_RESID_F32)
   SET_GEMM(gemm::EPI_BIAS_RESID_SPLIT)
+  SET_GEMM(gemm::EPI_BIAS_RESID_SPLIT8)
+  SET_GEMM(gemm::EPI_BIAS_RESID_DIRECT)
   SET_GEMM(gemm::EPI_BIAS_GELU_BF16)
   SET_GEMM(gemm::EPI_STORE_BF16)
   SET_GEMM(gemm::EPI_STORE_F32)
@@ -219,6 +221,7 @@ cudaError_t init_kernel_attributes_impl() {
   if (e != cudaSuccess) return e;
   SET_RD2(gemm::EPI_BIAS_RESID_F32)
   SET_RD2(gemm::EPI_BIAS_RESID_SPLIT)
+  SET_RD2(gemm::EPI_BIAS_RESID_SPLIT8)
 #undef SET_RD2
 #define SET_ARES(EPI)                                                                                            \
   e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>,                           \
@@ -299,6 +302,13 @@ struct biom3_model {
   float* u = nullptr;                           // fp32 residual stream (fp32-class mode, or BIOM3_SPLIT_RESID=0)
   bf16* u_lo = nullptr;                         // split residual stream: u = a (hi, bf16) + u_lo (bf16)
   bool split_resid = true;
+  bool lo8 = false;                             // split stream: remainder as a signed byte of hi's ulp in a tiled plane (BIOM3_LO8=1).
+                                                // 20 % fewer HBM bytes in out-proj, 12 % in FF2, all tests green — and SLOWER
+                                                // (out-proj 1.37 -> 1.63 ms/step, step 9.89 -> 10.30 ms): the residual epilogue is
+                                                // bound by its own instruction stream, not by HBM
+  bool resid_direct = false;                    // residual epilogues: thread = row with 256-bit accesses, no smem transpose
+                                                // (BIOM3_RESID_DIRECT=1).  Fewer instructions, no __syncwarp, no shuffles — and
+                                                // SLOWER: out-proj 1.34 -> 1.63 ms/step (32 distinct lines per warp access)
   bf16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
   float *Yh = nullptr, *Ytmp = nullptr, *Y = nullptr, *cvec = nullptr;
   uint8_t* state = nullptr;
@@ -479,7 +489,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const bool split = m->precision == 0 && m->split_resid;      // residual stream stored as bf16 hi + lo
   LAUNCH(C_OTHER, launch_k(k::cond_build_kernel, dim3(std::max(1, JD / 4 / 256), B), dim3(256), 0, st,
                       m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
-  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a, split ? m->u_lo : nullptr,
+  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a, split ? m->u_lo : nullptr, int(m->lo8),
                                                               m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
@@ -578,9 +588,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     const bool cl = Mc > 0 && j == depth - 1;   // compact last layer: the rest of the step runs on the selected rows only
     if (cl) {
       LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
-                               m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc));
+                               m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc, int(m->lo8)));
       r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_OUT, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
       p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
@@ -591,12 +601,12 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
         LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_FF2, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
       continue;
     }
     if (split) {
       r.out = m->u_lo;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_OUT, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
     } else {
       LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
     }
@@ -622,14 +632,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.cond_stride = JD;
       if (split) {
         r.out = m->u_lo + row0 * D;
-        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+        LAUNCH(C_FF2, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
       } else {
         LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       }
     }
   }
   k::HeadArgs ha{};
-  ha.u = split ? nullptr : m->u; ha.u_hi = Mc ? m->a_c : m->a; ha.u_lo = Mc ? m->ulo_c : m->u_lo; ha.compact = Mc ? 1 : 0; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
+  ha.u = split ? nullptr : m->u; ha.u_hi = Mc ? m->a_c : m->a; ha.u_lo = Mc ? m->ulo_c : m->u_lo; ha.compact = Mc ? 1 : 0; ha.lo8 = (split && m->lo8) ? 1 : 0; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
   ha.logits_out = logits_out; ha.state = sample ? m->state : nullptr; ha.inv_path = m->inv_path; ha.ctl = m->ctl;
   ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
   const int ntok = sample ? B * group : M;
@@ -706,6 +716,8 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_LO8")) m->lo8 = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_RESID_DIRECT")) m->resid_direct = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
@@ -1229,6 +1241,16 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
       p.out_bf16 = reinterpret_cast<bf16*>(out);
       p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
       launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
+    case gemm::EPI_BIAS_RESID_DIRECT:     // same planes as 5
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      p.out_bf16 = reinterpret_cast<bf16*>(out);
+      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
+      launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_BIAS_RESID_SPLIT8:     // out = bf16 hi plane [M][N] followed by the tiled uint8 lo plane (M * N bytes)
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      p.out_bf16 = reinterpret_cast<bf16*>(out);
+      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
+      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -541,9 +541,11 @@ def test_generate_denoised_sampled_single_sequence_vs_reference_fixture():
                                        sampling_path=path)
 
 
+@pytest.mark.parametrize('epi', [5, 7])
 @pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
-def test_gemm_split_residual_epilogue(bn, pair):
-    """Epilogue 5: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place."""
+def test_gemm_split_residual_epilogue(bn, pair, epi):
+    """Epilogues 5 / 7: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place (5: accumulator
+    transposed through shared memory, coalesced accesses; 7: thread = row, 256-bit accesses)."""
     from biom3_b200 import engine
     g = torch.Generator().manual_seed(9)
     M, N, K = 1024, 512, 512
@@ -556,7 +558,51 @@ def test_gemm_split_residual_epilogue(bn, pair):
     r0 = planes[0].float() + planes[1].float()
     assert rel_err(r0, R) < 1e-5                                  # the split itself keeps 16 significant bits
     ref = r0 + A.float() @ W.float().t() + bias
-    engine.gemm_test(A, W, bias, 5, bn, out=planes, pair=pair)
+    engine.gemm_test(A, W, bias, epi, bn, out=planes, pair=pair)
     got = planes[0].float() + planes[1].float()
     assert rel_err(got, ref) < 2e-5
     assert torch.equal(planes[0], got.bfloat16()) or rel_err(planes[0].float(), ref) < 4e-3   # hi plane = bf16(R)
+
+
+def _lo8_encode(R):
+    """torch restatement of ptx::split8_encode + the tiled lo plane [M/32][N/32][32][32] (ptx.cuh)."""
+    M, N = R.shape
+    hi = R.bfloat16()
+    E = (hi.view(torch.int16).to(torch.int32) >> 7) & 0xff
+    q = torch.round(torch.ldexp(R - hi.float(), 142 - E)).clamp(-127, 127)
+    q = torch.where(E >= 16, q, torch.zeros_like(q)).to(torch.int8)
+    return hi, q.view(M // 32, 32, N // 32, 32).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+def _lo8_decode(hi, lo_tiled):
+    M, N = hi.shape
+    E = (hi.view(torch.int16).to(torch.int32) >> 7) & 0xff
+    q = lo_tiled.view(M // 32, N // 32, 32, 32).permute(0, 2, 1, 3).reshape(M, N).float()
+    return hi.float() + torch.where(E >= 16, torch.ldexp(q, E - 142), torch.zeros_like(q))
+
+
+@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
+def test_gemm_split8_residual_epilogue(bn, pair):
+    """Epilogue 6: residual stream as a bf16 hi plane + a tiled plane of signed 8-bit remainders (units of ulp(hi) / 256)."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(10)
+    M, N, K = 1024, 512, 512
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    R = (torch.randn(M, N, generator=g) * 3.0).cuda()
+    hi, lo = _lo8_encode(R)
+    r0 = _lo8_decode(hi, lo)
+    assert rel_err(r0, R) < 2e-5                                  # 16 significant bits in 3 bytes (2^-16 = 1.5e-5)
+    buf = torch.empty(3 * M * N, dtype=torch.uint8, device='cuda')
+    buf[:2 * M * N].view(torch.bfloat16).view(M, N).copy_(hi)
+    buf[2 * M * N:].view(torch.int8).copy_(lo)
+    ref = r0 + A.float() @ W.float().t() + bias
+    engine.gemm_test(A, W, bias, 6, bn, out=buf, pair=pair)
+    hi2 = buf[:2 * M * N].view(torch.bfloat16).view(M, N)
+    got = _lo8_decode(hi2, buf[2 * M * N:].view(torch.int8))
+    assert rel_err(got, ref) < 4e-5
+    assert torch.equal(hi2, got.bfloat16()) or rel_err(hi2.float(), ref) < 4e-3   # hi plane = bf16(R)
+    # the kernel's encoding of its own result is the canonical one
+    hi3, lo3 = _lo8_encode(got)
+    assert torch.equal(hi3, hi2)

@@ -158,7 +158,9 @@ def stage_stages():
     print('hid rel_err:', rel_err(hid, hid_ref))
     u2 = u1 + F.linear(hid_ref, sd[p + '1.fn.fn.w2.weight'], sd[p + '1.fn.fn.w2.bias'])
     ab = eng.debug_buffer('a', (B, L, D), torch.bfloat16).float()
-    if os.environ.get('BIOM3_SPLIT_RESID', '1') != '0':          # residual stream stored as bf16 hi ('a') + lo
+    if os.environ.get('BIOM3_SPLIT_RESID', '1') != '0' and os.environ.get('BIOM3_LO8', '1') != '0':
+        ud = ab                                                  # hi plane only (the 8-bit tiled lo plane is not decoded here)
+    elif os.environ.get('BIOM3_SPLIT_RESID', '1') != '0':        # residual stream stored as bf16 hi ('a') + lo
         ud = ab + eng.debug_buffer('u_lo', (B, L, D), torch.bfloat16).float()
     else:
         ud = eng.debug_buffer('u', (B, L, D), torch.float32)
