@@ -90,9 +90,25 @@ struct Params {
                            // hi.hi, hi.lo, lo.hi (3K/BK blocks, fp32 accumulate) = the product to ~2^-16 relative
   int tma_store;           // bf16 epilogues: 0 = smem transpose + coalesced st.global, 1 = smem block + TMA store (tmap_c, 64B
                            // swizzle), 2 = no staging, two 256-bit stores per thread and chunk (thread = row)
+  int nt_shift, l_shift, d_shift;   // log2 of N / BN, of L and of the QKV head-block width N / 3 when those are powers of two, else -1
+                           // (set by fill_shifts(); the per-tile index arithmetic then costs shifts instead of ~25-instruction
+                           // integer divisions, which were 17 % of the QKV GEMM's executed instructions)
   int no_pipe;             // 1 = load the per-tile epilogue vectors / statistics at the point of use (A/B switch, BIOM3_EPI_PIPE=0)
   int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
 };
+
+__host__ __device__ constexpr int log2_or_neg(int v) {
+  if (v <= 0 || (v & (v - 1)) != 0) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+// call after M / N / K / L are set
+inline void fill_shifts(Params& p, int bn) {
+  p.nt_shift = log2_or_neg(p.N / bn);
+  p.l_shift = log2_or_neg(p.L);
+  p.d_shift = (p.N % 3 == 0) ? log2_or_neg(p.N / 3) : -1;
+}
 
 template <int BN, int STAGES, bool CG2, bool ARES = false>
 struct SmemLayout {
@@ -165,6 +181,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_tiles = (p.M / TILE_M) * n_tiles;
   const int nk = p.K / BK;
   const int k_blocks = p.split3 ? 3 * nk : nk;
+  // tile -> (row block, column tile); rows -> (sample, position)
+  auto tile_mb = [&](int tile) { int r; if (p.nt_shift >= 0) r = tile >> p.nt_shift; else r = tile / n_tiles; return r; };
+  auto tile_nt = [&](int tile) { int r; if (p.nt_shift >= 0) r = tile & (n_tiles - 1); else r = tile % n_tiles; return r; };
+  auto row_b = [&](int row) { int r; if (p.l_shift >= 0) r = row >> p.l_shift; else r = row / p.L; return r; };
+  auto row_l = [&](int row) { int r; if (p.l_shift >= 0) r = row & (p.L - 1); else r = row % p.L; return r; };
   // Tile walk of this worker, t = t_begin, t_begin + t_step, ... < t_end.  Round robin normally; ARES: a contiguous run,
   // so that consecutive tiles are consecutive column tiles of the same row block (tile = row block * n_tiles + column tile).
   int t_begin = worker, t_step = n_workers, t_end = num_tiles;
@@ -220,11 +241,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t run = 0;                                    // ARES: row-block runs started so far
       for (int t = t_begin; t < t_end; t += t_step) {
         const int tile = p.reverse ? num_tiles - 1 - t : t;
-        const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
-        const int n0 = (tile % n_tiles) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
+        const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
+        const int n0 = tile_nt(tile) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
         if constexpr (ARES) {
-          const bool new_mb = tile / n_tiles != cur_mb;
-          if (new_mb) { cur_mb = tile / n_tiles; ++run; }
+          const bool new_mb = tile_mb(tile) != cur_mb;
+          if (new_mb) { cur_mb = tile_mb(tile); ++run; }
           for (int kb = 0; kb < nk; ++kb) {
             if (new_mb) {
               // slot kb of the resident block is free once the previous run's last tile has consumed it
@@ -272,11 +293,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         if constexpr (ARES) {
-          const int mb = (p.reverse ? num_tiles - 1 - t : t) / n_tiles;
+          const int mb = tile_mb(p.reverse ? num_tiles - 1 - t : t);
           const bool new_mb = mb != cur_mb;
           if (new_mb) { cur_mb = mb; ++run; }
           // the run's last tile hands the resident A k-blocks back, one by one, behind its own MMAs
-          const bool last_of_run = t + 1 >= t_end || (p.reverse ? num_tiles - 2 - t : t + 1) / n_tiles != mb;
+          const bool last_of_run = t + 1 >= t_end || tile_mb(p.reverse ? num_tiles - 2 - t : t + 1) != mb;
           for (int kb = 0; kb < nk; ++kb) {
             if (new_mb) ptx::mbar_wait(&a_full[kb], (run & 1) ^ 1);      // run r (1-based) waits completion r
             ptx::mbar_wait(&full_bar[stage], phase);
@@ -333,14 +354,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr bool LO8 = (EPI == EPI_BIAS_RESID_SPLIT8);
     auto tile_goff = [&](int t) -> size_t {            // element offset of this lane's first element of a tile (row rr, group ch)
       const int tile = p.reverse ? num_tiles - 1 - t : t;
-      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
-      return size_t(m0 + quarter * 32 + rr) * p.N + (tile % n_tiles) * BN + col_half * COLS_PER_WARP + 4 * ch;
+      const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
+      return size_t(m0 + quarter * 32 + rr) * p.N + tile_nt(tile) * BN + col_half * COLS_PER_WARP + 4 * ch;
     };
     // byte offset of the same position in the tiled 8-bit lo plane (chunk 0, row rr): + c * 1024 per chunk, + j * 128 per 4 rows
     auto tile_loff = [&](int t) -> size_t {
       const int tile = p.reverse ? num_tiles - 1 - t : t;
-      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
-      return ptx::lo8_offset(size_t(m0 + quarter * 32 + rr), (tile % n_tiles) * BN + col_half * COLS_PER_WARP + 4 * ch, p.N);
+      const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
+      return ptx::lo8_offset(size_t(m0 + quarter * 32 + rr), tile_nt(tile) * BN + col_half * COLS_PER_WARP + 4 * ch, p.N);
     };
     // 4 residual values at element offset `off`, as raw bits: fp32 x 4, (hi bf16 x 4, lo bf16 x 4) or (hi bf16 x 4, lo s8 x 4)
     auto load_res = [&](size_t off, size_t loff) -> uint4 {
@@ -396,8 +417,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float4 pst[2];                                        // prefetched partial statistics of this thread's row
     auto tile_rn = [&](int t, int& rbase_o, int& nbase_o) {
       const int tile = p.reverse ? num_tiles - 1 - t : t;
-      rbase_o = (tile / n_tiles) * TILE_M + int(cta_rank) * BM + quarter * 32;
-      nbase_o = (tile % n_tiles) * BN + col_half * COLS_PER_WARP;
+      rbase_o = tile_mb(tile) * TILE_M + int(cta_rank) * BM + quarter * 32;
+      nbase_o = tile_nt(tile) * BN + col_half * COLS_PER_WARP;
     };
     auto prefetch_tile = [&](int t, uint32_t buf) {
       int rb, nb;
@@ -418,11 +439,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int tile = p.reverse ? num_tiles - 1 - t : t;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * BM;
-      const int n_tile = tile % n_tiles;
+      const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
+      const int n_tile = tile_nt(tile);
       const int rbase = m0 + quarter * 32;                 // first of this warp's 32 rows
       const int nbase = n_tile * BN + col_half * COLS_PER_WARP;
-      const int bidx = rbase / p.L;                        // 32-row blocks never straddle samples (L % 128 == 0)
+      const int bidx = row_b(rbase);                       // 32-row blocks never straddle samples (L % 128 == 0)
       const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
 
       if (p.debug_skip == 1 || p.debug_skip == 2) {
@@ -693,7 +714,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         size_t row_stride, chunk_stride;                   // elements between rows of a block / between chunks
         if constexpr (EPI == EPI_QKV_HEADMAJOR) {
           const int D = p.N / 3;
-          const int which = nbase / D, h0 = (nbase % D) >> 5, l0 = rbase % p.L;
+          int which, hrem;
+          if (p.d_shift >= 0) { which = nbase >> p.d_shift; hrem = nbase & (D - 1); }
+          else { which = nbase / D; hrem = nbase % D; }
+          const int h0 = hrem >> 5, l0 = row_l(rbase);
           dst0 = reinterpret_cast<__nv_bfloat16*>(p.out) + ((((size_t(which) * p.Bsz + bidx) * p.H + h0) * p.L + l0) << 5);
           row_stride = 32;
           chunk_stride = size_t(p.L) << 5;
@@ -706,7 +730,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if constexpr (EPI == EPI_QKV_HEADMAJOR) {
           const int D = p.N / 3;
           tma_c0 = 0;
-          tma_c1 = (((nbase / D) * p.Bsz + bidx) * p.H + ((nbase % D) >> 5)) * p.L + rbase % p.L;
+          int which, hrem;
+          if (p.d_shift >= 0) { which = nbase >> p.d_shift; hrem = nbase & (D - 1); }
+          else { which = nbase / D; hrem = nbase % D; }
+          tma_c1 = ((which * p.Bsz + bidx) * p.H + (hrem >> 5)) * p.L + row_l(rbase);
         }
         ptx::mbar_wait_parked(&acc_full[as], aphase);
         ptx::tc_fence_after();

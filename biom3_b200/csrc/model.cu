@@ -123,8 +123,10 @@ constexpr int ARES_STAGES = 4;     // weight-ring stages of the A-resident varia
 
 // A-resident pair-tiled launch (bf16 epilogues, K <= 512): contiguous tile runs per CTA pair
 template <int EPI>
-void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p,
+void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p_in,
                       int num_sms, cudaStream_t st) {
+  gemm::Params p = p_in;
+  gemm::fill_shifts(p, 256);
   const int smem = gemm::SmemLayout<256, ARES_STAGES, true, true>::TOTAL;
   const int tiles = (p.M / 256) * (p.N / 256);
   const int workers = num_sms / 2;
@@ -148,8 +150,10 @@ void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 // launch only; the caller checks cudaGetLastError()
 template <int BN, int EPI, bool CG2, int RD = 1>
-void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p,
+void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p_in,
                    int num_sms, cudaStream_t st) {
+  gemm::Params p = p_in;
+  gemm::fill_shifts(p, BN);
   constexpr int STAGES = gemm_stages<BN, CG2>();
   const int smem = gemm::SmemLayout<BN, STAGES, CG2>::TOTAL;
   const int tiles = (p.M / (CG2 ? 256 : 128)) * (p.N / BN);
