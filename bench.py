@@ -353,12 +353,19 @@ def main():
     ap.add_argument('--impl', type=str, default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
+    # stdout must carry exactly one JSON line: libraries that write to file descriptor 1 behind Python's back (NCCL prints
+    # its version banner there) are sent to stderr, and print() is pointed at the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if a.impl == 'reference':
         run_reference_arm(a)
     else:
         import __graft_entry__
         __graft_entry__.build()
         run_cuda_arm(a)
+    real_stdout.flush()
 
 
 if __name__ == '__main__':
