@@ -1,13 +1,17 @@
 #!/bin/bash
+# Round-end verification on one B200 (run through gpurun): GPU parity suite, smoke, the bench line, and the ncu launch list of
+# the bench command.  Results land in gpurun_out/.
 set -x
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_shift_full.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_shift_full.log
-tail -5 gpurun_out/pytest_shift_full.log
-timeout 300 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum --clock-control none --launch-skip 118 --launch-count 7 --csv --log-file gpurun_out/inst_counts.csv python tools/ncu_step.py > /dev/null 2>&1
-grep -v "^==" gpurun_out/inst_counts.csv | cut -d, -f5,13- | head -20
-for i in 1 2; do
-  timeout 300 python tools/ab_step.py 384 2>/dev/null | tail -1 >> gpurun_out/ab_shift.jsonl
-done
-cat gpurun_out/ab_shift.jsonl
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_full.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu_full.log
+tail -4 gpurun_out/pytest_gpu_full.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke.log
+tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+echo "bench exit $?"
+cat gpurun_out/bench_final.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+echo "ncu exit $?"
