@@ -335,6 +335,47 @@ def test_facilitator_vs_reference_fixture():
     assert rel_err(got, torch.from_numpy(z['z_c'])) < 1e-4
 
 
+def test_cli_flow_facilitator_to_sequences_end_to_end():
+    """BASELINE.json configs[3] in miniature, through the reference-facing entry points only: Facilitator z_t -> z_c on the
+    GPU, then batch_stage3_generate_sequences (prompt x replica-batch units, one random path per sample, the sampler loop, ids ->
+    strings with the special tokens stripped).  The result dictionary has the reference's shape, is repeatable under
+    torch.manual_seed like the reference, and its strings are exactly what the token trajectories of the same units decode to."""
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    from biom3_b200.Stage1_source.model import Facilitator
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+    from biom3_b200.Stage3_source import sampling_analysis as samp
+    args = synthetic.stage3_args(**dict(SMALL, text_emb_dim=64), num_replicas=3, batch_size_sample=2)
+    args.device = 'cuda'
+    fac = Facilitator(64, 128, 64, dropout=0.0)
+    fac.load_state_dict(synthetic.facilitator_state_dict(64, 128, seed=3))
+    z_t = torch.randn(2, 64, generator=torch.Generator().manual_seed(5)) * 1.45
+    z_c = fac(z_t.cuda()).cpu()
+    assert z_c.shape == (2, 64) and torch.isfinite(z_c).all()
+    model = mod.get_model(args, (32, 32), 29)
+    model.load_state_dict(synthetic.random_state_dict(args, seed=11, perturb_norm=True))
+    model.eval()
+    torch.manual_seed(1234)
+    d1 = cli.batch_stage3_generate_sequences(args, model, [z for z in z_c])        # the list-of-tensors form (reference :79-81)
+    torch.manual_seed(1234)
+    d2 = cli.batch_stage3_generate_sequences(args, model, z_c)
+    assert d1 == d2
+    assert sorted(d1) == ['replica_0', 'replica_1', 'replica_2'] and all(len(v) == 2 for v in d1.values())
+    alphabet = set(''.join(t for t in synthetic.TOKENS if len(t) == 1))
+    for v in d1.values():
+        for seq in v:
+            assert isinstance(seq, str) and 0 < len(seq) <= 256 and set(seq) <= alphabet
+    # replay the first unit (prompt 0, replicas 0-1) by hand with the same RNG draws: same strings
+    torch.manual_seed(1234)
+    L = args.diffusion_steps
+    paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for bs in (2, 1, 2, 1)]     # every unit's paths are drawn first
+    states, times = samp.batch_generate_denoised_sampled(args=args, model=model, extract_digit_samples=torch.zeros(2, L),
+                                                         extract_time=torch.zeros(2).long(),
+                                                         extract_digit_label=z_c[0].unsqueeze(0).repeat(2, 1), sampling_path=paths[0])
+    assert len(states) == L and len(times) == L
+    for i in range(2):
+        assert cli.clean_sequence(synthetic.TOKENS, states[-1][i, 0]) == d1[f'replica_{i}'][0]
+
+
 def test_full_config_short_decode_vs_oracle():
     """stage3_config.json shape (16 layers, d 512, L 1024), B = 2, first 10 denoising steps, explicit noise:
     token trajectory identical to the CPU oracle (the oracle's own race margins are reported on failure)."""
