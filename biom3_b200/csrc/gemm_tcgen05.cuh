@@ -13,12 +13,14 @@
 //                 version is bound by the SM's L2->smem ingest (~43 B/clk measured, 48 KB per 512 MMA cycles);
 //                 the pair needs 32 KB per CTA for the same MMA work.
 //
-// ARES = true (CTA pairs, K <= 512, bf16 epilogues): the A row block stays RESIDENT in shared memory.  These GEMMs run at the
-// L2 throughput cap (ncu: ~11.9 TB/s of L2->SM + SM->L2 traffic on the QKV GEMM, the ~6300 B/clk LTS limit), so bytes
-// through L2 are what bounds them: a 256 x 256 tile with K = 512 pulls 256 KB of A + 256 KB of W through L2 and writes
-// 128 KB.  A worker therefore walks a CONTIGUOUS run of tiles (consecutive column tiles of one 256-row block), loads
-// the block's A once (8 k-blocks x 16 KB per CTA, one full / empty barrier pair per k-block so the next row block's
-// A streams in behind the last column tile's MMAs) and only W goes through the 4-stage ring: A traffic / n_tiles.
+// ARES = true (CTA pairs, K <= 512, bf16 epilogues; optional, BIOM3_ARES=1): the A row block stays RESIDENT in shared memory.
+// A 256 x 256 tile with K = 512 pulls 256 KB of A + 256 KB of W through L2 and writes 128 KB, and under ncu the QKV GEMM
+// moves ~11.9 TB/s through L2, close to the ~6300 B/clk LTS limit — the hypothesis was that L2 bytes bound these GEMMs.
+// In this variant a worker walks a CONTIGUOUS run of tiles (consecutive column tiles of one 256-row block), loads the
+// block's A once (8 k-blocks x 16 KB per CTA, one full / empty barrier pair per k-block so the next row block's A
+// streams in behind the last column tile's MMAs) and only W goes through a 4-stage ring: A traffic / n_tiles.  It is
+// bit-identical to the streaming kernel and measured NO faster (3.92 vs 3.81 us per K = 512 tile, step unchanged), so
+// L2 traffic is not the bound; the streaming ring stays the default.
 //
 // Fusions (the reference runs each as separate library / element-wise kernels; block structure from
 // linear-attention-transformer, called at /root/reference/Stage3_source/cond_diff_transformer_layer.py:171):
@@ -45,7 +47,8 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 __host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || (epi >= 3 && epi <= 7)) ? 8 : 16; }
 // First epilogue warp.  RD = 2 (two residual chunks prefetched, 64 registers) does not fit the 168 registers a 10-warp CTA
 // gets, so that variant pads the two control warps to a full warpgroup (warps 2, 3 idle) and moves registers with
-// setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the 384 x 168 the CTA was launched with (an inc beyond the pool would block forever).
+// setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the
+// 384 x 168 the CTA was launched with (an inc beyond the pool would block forever).
 __host__ __device__ constexpr int epi_warp0(int rd) { return rd == 2 ? 4 : 2; }
 constexpr int ARES_NK = 8;         // k-blocks of the resident A row block (K <= 512)
 
@@ -59,11 +62,11 @@ enum Epi : int {
                             // `out_bf16` is hi (the array the next GEMM reads as its A operand), `out` is lo.  Same
                             // bytes read, 2 instead of 6 bytes per element written; R keeps 16 significant bits.
   EPI_BIAS_RESID_SPLIT8 = 6, // like 5 with the remainder in ONE byte (ptx::split8_*): `out` is the tiled uint8 lo plane.  3 instead
-                            // of 4 bytes per element read and written by the two HBM-bound residual GEMMs.
+                            // of 4 bytes per element read and written by the residual GEMMs; measured slower (optional).
   EPI_BIAS_RESID_DIRECT = 7, // same data as 5 (bf16 hi + bf16 lo planes, row major), different access: thread = row end to end.
                             // Each thread reads and writes its own row's 32 columns of a chunk as 64 contiguous bytes per
                             // plane (two 256-bit accesses = full sectors), so there is no shared-memory transpose, no
-                            // __syncwarp, and the row statistics need no shuffles.
+                            // __syncwarp, and the row statistics need no shuffles; measured slower (optional).
 };
 
 struct Params {
