@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libbiom3_b200.so')
+# BIOM3_LIB: an alternative build of the same library (A/B of compile-time options, see build.py --variant); still CUDA only
+LIB_PATH = os.environ.get('BIOM3_LIB') or os.path.join(HERE, 'libbiom3_b200.so')
 
 # every symbol include/biom3_b200.h declares
 SYMBOLS = [

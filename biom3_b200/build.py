@@ -40,5 +40,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines) -> str:
+    """A second copy of the library with extra -D options, biom3_b200/libbiom3_b200.<name>.so, for A/B runs of compile-time
+    choices (select it with BIOM3_LIB=<path>)."""
+    out = os.path.join(HERE, f'libbiom3_b200.{name}.so')
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', out, SRC, '-lcudart']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f'nvcc failed building {out}')
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose=True))
+    if '--variant' in sys.argv:           # python -m biom3_b200.build --variant ew8 BIOM3_BF16_EPI_WARPS=8
+        i = sys.argv.index('--variant')
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force='--force' in sys.argv, verbose=True))

@@ -41,10 +41,21 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
                                   // (the next tile's vectors are fetched with cp.async while this tile is processed)
 
 // Epilogue warps per CTA.  The fp32 residual epilogues use 8 (two per TMEM lane quarter, 128 columns each, 168
-// registers for the residual prefetch); the bf16 epilogues are latency-bound chains (TMEM load -> fused math ->
-// smem transpose -> store) and use 16 (four per quarter, 64 columns each) so the chains of different warps overlap.
+// registers for the residual prefetch).  The bf16 epilogues are latency-bound chains (TMEM load -> fused math -> smem
+// transpose -> store): the GELU epilogue (FF1) uses 16 warps (four per quarter, 64 columns each) so the chains of different
+// warps overlap; the QKV epilogue has almost no math per element, its cost is the ~244 instructions of per-tile set-up each
+// warp executes, and it is 6 % faster with 8 warps of four chunks (A/B of compile-time variants, `tools/ab_variant.sh`:
+// QKV 1.80 -> 1.69 ms per step with 8 warps, FF1 2.56 -> 2.69 ms, hence the mixed default).
 // The A-resident variant has 16 KB of staging left: 8 warps x 2 KB.
-__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) { return (ares || (epi >= 3 && epi <= 7)) ? 8 : 16; }
+#ifndef BIOM3_BF16_EPI_WARPS
+#define BIOM3_BF16_EPI_WARPS 16      // GELU / plain bf16-store epilogues; compile-time A/B: python -m biom3_b200.build --variant ew8 BIOM3_BF16_EPI_WARPS=8
+#endif
+#ifndef BIOM3_QKV_EPI_WARPS
+#define BIOM3_QKV_EPI_WARPS 8
+#endif
+__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) {
+  return (ares || (epi >= 3 && epi <= 7)) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
+}
 // First epilogue warp.  RD = 2 (two residual chunks prefetched, 64 registers) does not fit the 168 registers a 10-warp CTA
 // gets, so that variant pads the two control warps to a full warpgroup (warps 2, 3 idle) and moves registers with
 // setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the
@@ -138,6 +149,22 @@ __device__ __forceinline__ float gelu_erf_half(float h) {
   float th;
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h * poly));
   return fmaf(h, th, h);
+}
+
+// 1 / sqrt(var + eps) of the folded LayerNorm.  IEEE by default (~30 instructions per tile and thread); the compile-time
+// variant BIOM3_RSTD_RSQRT=1 uses the 2-ulp MUFU.RSQ for A/B runs.
+#ifndef BIOM3_RSTD_RSQRT
+#define BIOM3_RSTD_RSQRT 0
+#endif
+#ifndef BIOM3_MMA_PARKED
+#define BIOM3_MMA_PARKED 0       // 1: the MMA warp's per-k-block wait for the operands parks instead of polling
+#endif
+__device__ __forceinline__ float row_rstd(float v) {
+#if BIOM3_RSTD_RSQRT
+  return rsqrtf(v);
+#else
+  return 1.0f / sqrtf(v);
+#endif
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -318,7 +345,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           continue;
         }
         for (int kb = 0; kb < k_blocks; ++kb) {
+#if BIOM3_MMA_PARKED
+          ptx::mbar_wait_parked(&full_bar[stage], phase);
+#else
           ptx::mbar_wait(&full_bar[stage], phase);
+#endif
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t da = ptx::umma_desc_sw128(sa);
@@ -679,7 +710,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             sm += pst[1].z; q += pst[1].w;
           }
           mean = sm / float(p.K);
-          rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
+          rstd = row_rstd(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
           ptx::cp_async_wait<0>();
           __syncwarp();
           if (t + t_step < t_end) prefetch_tile(t + t_step, cvs0 + ((it + 1) & 1) * CV_BYTES);
@@ -706,7 +737,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               q += v.y;
             }
             mean = sm / float(p.K);
-            rstd = 1.0f / sqrtf(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
+            rstd = row_rstd(fmaxf(q / float(p.K) - mean * mean, 0.f) + 1e-5f);
           }
           __syncwarp();
         }
