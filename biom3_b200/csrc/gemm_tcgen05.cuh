@@ -36,7 +36,7 @@ namespace gemm {
 constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STG_TOTAL = 32768;  // epilogue staging: one 32 x 32 block per warp (fp32: 8 warps x 4 KB, bf16: 16 warps x 2 KB)
+// epilogue staging: one 32 x 32 block per warp (fp32: 4 KB, bf16: 2 KB), see epi_stg_bytes()
 constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of every warp's column range, double buffered
                                   // (the next tile's vectors are fetched with cp.async while this tile is processed)
 
@@ -124,17 +124,24 @@ inline void fill_shifts(Params& p, int bn) {
   p.d_shift = (p.N % 3 == 0) ? log2_or_neg(p.N / 3) : -1;
 }
 
-template <int BN, int STAGES, bool CG2, bool ARES = false>
+// Shared memory of one CTA: [resident A block (ARES)] [operand ring] [epilogue staging] [per-column epilogue vectors].
+// Staging and vector space follow the epilogue (EPI), so that the kernels that need less of them can afford a deeper ring.
+__host__ __device__ constexpr bool epi_is_f32(int epi) { return epi >= 3 && epi <= 7; }
+__host__ __device__ constexpr int epi_stg_bytes(int epi, bool ares) { return epi_warps(epi, ares) * (epi_is_f32(epi) ? 4096 : 2048); }
+__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2 || epi == 7) ? CV_TOTAL : 0; }
+
+template <int BN, int STAGES, bool CG2, bool ARES, int EPI>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;         // weight rows staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int A_RES_BYTES = ARES ? ARES_NK * A_BYTES : 0;   // resident A row block, in front of the ring
   static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES_TOTAL = ARES ? STG_TOTAL / 2 : STG_TOTAL;
+  static constexpr int STG_BYTES_TOTAL = epi_stg_bytes(EPI, ARES);
   static constexpr int STG_OFFSET = A_RES_BYTES + STAGES * STAGE_BYTES;
   static constexpr int CV_OFFSET = STG_OFFSET + STG_BYTES_TOTAL;
-  static constexpr int TOTAL = CV_OFFSET + CV_TOTAL + 1024;   // + alignment slack
+  static constexpr int TOTAL = CV_OFFSET + epi_cv_bytes(EPI) + 1024;   // + alignment slack
+  static_assert(TOTAL <= 232448 - 512, "more than the 227 KB a CTA can have (512 bytes left for the static barriers)");
 };
 
 // erf-GELU, x * Phi(x), evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))): the three coefficients are a
@@ -184,7 +191,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   static_assert(RD == 1 || RD == 2, "residual prefetch depth");
   static_assert(!ARES || (CG2 && BN == 256 && (EPI == EPI_STORE_BF16 || EPI == EPI_QKV_HEADMAJOR || EPI == EPI_BIAS_GELU_BF16)),
                 "the A-resident variant is pair-tiled with a bf16 epilogue");
-  using SL = SmemLayout<BN, STAGES, CG2, ARES>;
+  using SL = SmemLayout<BN, STAGES, CG2, ARES, EPI>;
   constexpr int EPI_WARPS = epi_warps(EPI, ARES);
   constexpr uint32_t EPI_WARP0 = epi_warp0(RD);
   constexpr int STG_BYTES = SL::STG_BYTES_TOTAL / EPI_WARPS;

@@ -117,8 +117,23 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-template <int BN, bool CG2>
-constexpr int gemm_stages() { return CG2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : 5); }
+// Operand-ring depth.  Pair tiling, 256-wide tiles: 5 stages of 32 KB; the QKV epilogue (8 warps, 16 KB of staging) and the residual
+// epilogues (no per-column vectors) leave room for a sixth (compile-time A/B: BIOM3_QKV_STAGES / BIOM3_RESID_STAGES).
+#ifndef BIOM3_QKV_STAGES
+#define BIOM3_QKV_STAGES 5
+#endif
+#ifndef BIOM3_RESID_STAGES
+#define BIOM3_RESID_STAGES 5
+#endif
+template <int BN, bool CG2, int EPI>
+constexpr int gemm_stages() {
+  if (CG2 && BN == 256) {
+    if (EPI == gemm::EPI_QKV_HEADMAJOR && gemm::epi_warps(EPI) == 8) return BIOM3_QKV_STAGES;
+    if (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT || EPI == gemm::EPI_BIAS_RESID_SPLIT8) return BIOM3_RESID_STAGES;
+    return 5;
+  }
+  return CG2 ? 7 : (BN == 256 ? 3 : 5);
+}
 constexpr int ARES_STAGES = 4;     // weight-ring stages of the A-resident variant (gemm_tcgen05.cuh)
 
 // A-resident pair-tiled launch (bf16 epilogues, K <= 512): contiguous tile runs per CTA pair
@@ -127,7 +142,7 @@ void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
                       int num_sms, cudaStream_t st) {
   gemm::Params p = p_in;
   gemm::fill_shifts(p, 256);
-  const int smem = gemm::SmemLayout<256, ARES_STAGES, true, true>::TOTAL;
+  const int smem = gemm::SmemLayout<256, ARES_STAGES, true, true, EPI>::TOTAL;
   const int tiles = (p.M / 256) * (p.N / 256);
   const int workers = num_sms / 2;
   const int grid = (tiles < workers ? tiles : workers) * 2;
@@ -154,8 +169,8 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
                    int num_sms, cudaStream_t st) {
   gemm::Params p = p_in;
   gemm::fill_shifts(p, BN);
-  constexpr int STAGES = gemm_stages<BN, CG2>();
-  const int smem = gemm::SmemLayout<BN, STAGES, CG2>::TOTAL;
+  constexpr int STAGES = gemm_stages<BN, CG2, EPI>();
+  const int smem = gemm::SmemLayout<BN, STAGES, CG2, false, EPI>::TOTAL;
   const int tiles = (p.M / (CG2 ? 256 : 128)) * (p.N / BN);
   const int workers = CG2 ? num_sms / 2 : num_sms;
   const int grid = (tiles < workers ? tiles : workers) * (CG2 ? 2 : 1);
@@ -203,9 +218,9 @@ constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024
 cudaError_t init_kernel_attributes_impl() {
   cudaError_t e;
 #define SET_GEMM1(BN, EPI, CG2)                                                                                  \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, gemm_stages<BN, CG2>(), EPI, CG2>,                        \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, gemm_stages<BN, CG2, EPI>(), EPI, CG2>,                   \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<BN, gemm_stages<BN, CG2>(), CG2>::TOTAL);                            \
+                           gemm::SmemLayout<BN, gemm_stages<BN, CG2, EPI>(), CG2, false, EPI>::TOTAL);           \
   if (e != cudaSuccess) return e;
 #define SET_GEMM(EPI) SET_GEMM1(256, EPI, false) SET_GEMM1(128, EPI, false) SET_GEMM1(256, EPI, true)
   SET_GEMM(gemm::EPI_QKV_HEADMAJOR)
@@ -219,9 +234,9 @@ cudaError_t init_kernel_attributes_impl() {
 #undef SET_GEMM1
 #undef SET_GEMM
 #define SET_RD2(EPI)                                                                                             \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, gemm_stages<256, true>(), EPI, true, false, 2>,          \
+  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, gemm_stages<256, true, EPI>(), EPI, true, false, 2>,     \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<256, gemm_stages<256, true>(), true>::TOTAL);                        \
+                           gemm::SmemLayout<256, gemm_stages<256, true, EPI>(), true, false, EPI>::TOTAL);       \
   if (e != cudaSuccess) return e;
   SET_RD2(gemm::EPI_BIAS_RESID_F32)
   SET_RD2(gemm::EPI_BIAS_RESID_SPLIT)
@@ -230,7 +245,7 @@ cudaError_t init_kernel_attributes_impl() {
 #define SET_ARES(EPI)                                                                                            \
   e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>,                           \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<256, ARES_STAGES, true, true>::TOTAL);                               \
+                           gemm::SmemLayout<256, ARES_STAGES, true, true, EPI>::TOTAL);                          \
   if (e != cudaSuccess) return e;
   SET_ARES(gemm::EPI_STORE_BF16)
   SET_ARES(gemm::EPI_QKV_HEADMAJOR)
