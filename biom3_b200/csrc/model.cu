@@ -483,6 +483,16 @@ void run_y_mlp(biom3_model* m, const float* y_c, int B, cudaStream_t st) {
   k::cond_transpose_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->Ytmp, m->Y, B, D, depth);
 }
 
+// Residual update of the split (hi, lo) stream: the epilogue variant is a model-level choice (gemm_tcgen05.cuh, Epi 5 / 6 / 7)
+void launch_resid_split(biom3_model* m, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& r, cudaStream_t st) {
+  if (m->lo8)
+    launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
+  else if (m->resid_direct)
+    launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
+  else
+    launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
+}
+
 // One per-step forward over the resident state.  sample: draw + unmask (decode); else write logits.
 // t_per_sample != nullptr -> forward API (arbitrary step per sample); else the device step counter.
 cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, float* logits_out, bool sample,
@@ -609,7 +619,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
                                m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc, int(m->lo8)));
       r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
-      LAUNCH(C_OUT, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att_c, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
+      LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att_c, m->tm_wo[in], r, st));
       p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
@@ -620,12 +630,12 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
         LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
-      LAUNCH(C_FF2, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid_c, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
+      LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid_c, m->tm_w2[in], r, st));
       continue;
     }
     if (split) {
       r.out = m->u_lo;
-      LAUNCH(C_OUT, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
+      LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att, m->tm_wo[in], r, st));
     } else {
       LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
     }
@@ -651,7 +661,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.cond_stride = JD;
       if (split) {
         r.out = m->u_lo + row0 * D;
-        LAUNCH(C_FF2, (m->lo8 ? launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : m->resid_direct ? launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth) : launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth)));
+        LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid, m->tm_w2[in], r, st));
       } else {
         LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
       }
