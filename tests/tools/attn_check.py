@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attention kernels vs a torch fp32 reference on random head-major qkv (run on the GPU box)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from biom3_b200 import engine

@@ -4,12 +4,12 @@ oracle's functional forward with its state dict moved to cuda: cuBLAS / cuDNN / 
 inference, and the same under bf16 autocast), full forward over all positions + draw at every position + the cross-sample
 unmask write + the per-step host copies, B = 64.  A bounded number of denoising steps, extrapolated to 1024 (per-step cost is
 step independent).  Measurement tool only: nothing here is on the product path.
-    python tools/eager_bar.py [steps]"""
+    python tests/tools/eager_bar.py [steps]"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

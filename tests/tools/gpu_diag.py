@@ -2,7 +2,7 @@
 """Bring-up diagnostics on a B200: runs each stage in its own subprocess (a hang or fault in one
 does not take the others down) and prints numeric detail, not just pass/fail.
 
-    python tools/gpu_diag.py [stage ...]      # stages: gemm sampler stages forward decode perf
+    python tests/tools/gpu_diag.py [stage ...]      # stages: gemm sampler stages forward decode perf
 """
 from __future__ import annotations
 
@@ -11,7 +11,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
