@@ -14,7 +14,7 @@ SYMBOLS = [
     'biom3_create', 'biom3_destroy', 'biom3_last_error', 'biom3_set_weight', 'biom3_finalize_weights',
     'biom3_forward', 'biom3_decode', 'biom3_sample_all', 'biom3_unmask', 'biom3_gemm_test',
     'biom3_profile_step', 'biom3_launches_per_step', 'biom3_debug_copy', 'biom3_facilitator', 'biom3_attention_test',
-    'biom3_set_precision',
+    'biom3_set_precision', 'biom3_random_paths',
 ]
 
 
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.biom3_attention_test.restype = i32
     lib.biom3_set_precision.argtypes = [vp, i32]
     lib.biom3_set_precision.restype = i32
+    lib.biom3_random_paths.argtypes = [C.c_uint64, i32, i32, vp, vp]
+    lib.biom3_random_paths.restype = i32
     lib.biom3_launches_per_step.argtypes = [vp]
     lib.biom3_launches_per_step.restype = i32
     _lib = lib

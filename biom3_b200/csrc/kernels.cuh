@@ -165,6 +165,47 @@ __device__ __forceinline__ float philox_exp1(unsigned long long seed, int step, 
   return -__logf(uu) + 1e-30f;
 }
 
+// ---------------------------------------------------------------- sampling paths on the device
+// One uniformly random permutation of 0..L-1 per row: sort L Philox keys (64 bits, ties broken by index, so the result
+// is a permutation for every seed) with a bitonic network in shared memory.  Replaces the per-sample
+// `torch.randperm(args.diffusion_steps)` of /root/reference/run_ProteoScribe_sample.py:103-105 when the caller asks for
+// device-side paths; not bit-compatible with torch's generator (like the on-device noise).
+// One block per row; N = next power of two >= L (padding keys are +inf and sort to the end).
+__global__ void __launch_bounds__(1024)
+random_paths_kernel(unsigned long long seed, long long* __restrict__ path, int L, int N) {
+  extern __shared__ unsigned long long rp_keys[];          // [N] keys, then [N] uint32 indices
+  uint32_t* idx = reinterpret_cast<uint32_t*>(rp_keys + N);
+  const int row = blockIdx.x;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < L) {
+      const uint4 r = philox4x32_10(make_uint4(uint32_t(i), uint32_t(row), 0x70617468u, 0u), make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+      k = (static_cast<unsigned long long>(r.x) << 32) | r.y;
+      if (k == ~0ull) k -= 1;                               // keep real keys below the padding
+    }
+    rp_keys[i] = k;
+    idx[i] = uint32_t(i);
+  }
+  __syncthreads();
+  for (int size = 2; size <= N; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));          // index of the lower element of pair i
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long ka = rp_keys[lo], kb = rp_keys[hi];
+        const uint32_t ia = idx[lo], ib = idx[hi];
+        const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+        if (a_gt_b == up) {
+          rp_keys[lo] = kb; rp_keys[hi] = ka;
+          idx[lo] = ib; idx[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < L; i += blockDim.x) path[size_t(row) * L + i] = static_cast<long long>(idx[i]);
+}
+
 // ---------------------------------------------------------------- categorical draw (one warp, lane = class)
 // p = softmax(logits); p /= sum(p); token = argmax(p / q), ties -> lowest class id.
 // The two sums run sequentially over c = 0..C-1 (the order the fp32 CPU reference accumulates in).

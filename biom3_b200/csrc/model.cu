@@ -1147,6 +1147,22 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
   return BIOM3_OK;
 }
 
+int biom3_random_paths(uint64_t seed, int B, int L, int64_t* path, void* stream) {
+  if (!path || B < 1 || L < 1 || L > 8192) return fail(BIOM3_ERR_INVALID, "bad random_paths argument (1 <= L <= 8192)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
+  int N = 1;
+  while (N < L) N <<= 1;
+  const size_t smem = size_t(N) * 12;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(k::random_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12); });
+  k::random_paths_kernel<<<B, std::min(1024, std::max(32, N / 2)), smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<unsigned long long>(seed), reinterpret_cast<long long*>(path), L, N);
+  CU_OK(cudaGetLastError());
+  return BIOM3_OK;
+}
+
 int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int B, int L, int C, void* stream) {
   if (!logits || !noise || !tok || B < 1 || L < 1 || C < 2 || C > 32) return fail(BIOM3_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -133,6 +133,19 @@ class Engine:
         return {n: getattr(prof, n) for n, _ in _lib.StepProfile._fields_}
 
 
+def random_paths(B: int, L: int, seed: int, device) -> torch.Tensor:
+    """One uniformly random permutation of 0..L-1 per row, drawn on the device -> int64 [B, L] (cuda)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('biom3_b200 has no CPU path: random_paths needs a CUDA device')
+    path = torch.empty(B, L, device=device, dtype=torch.int64)
+    with torch.cuda.device(device):
+        _lib.check(lib.biom3_random_paths(C.c_uint64(int(seed) & (2 ** 64 - 1)), B, L, _ptr(path),
+                                          C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return path
+
+
 def sample_all(logits: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
     """K11: token at every position.  logits fp32 [B, C, L], noise fp32 [B*L, C] (cuda) -> int64 [B, L]."""
     lib = _lib.load()

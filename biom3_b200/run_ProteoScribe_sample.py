@@ -69,7 +69,13 @@ def batch_stage3_generate_sequences(args, model, z_t):
     rows = min(args.batch_size_sample, args.num_replicas)
     local = torch.zeros(len(mine), rows, L, dtype=torch.uint8, device=args.device)
     # every rank draws ALL paths in unit order so the result does not depend on the number of GPUs
-    paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for (_, _, bs) in units]
+    if getattr(args, 'b200_device_paths', False):
+        # permutations drawn on the GPU (biom3_random_paths), one Philox seed per unit taken from torch's global generator
+        from . import engine as _engine
+        seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in units]
+        paths = [_engine.random_paths(bs, L, sd, args.device).cpu() for (_, _, bs), sd in zip(units, seeds)]
+    else:
+        paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for (_, _, bs) in units]
     for slot, uid in enumerate(mine):
         p, _, bs = units[uid]
         z = z_t[p].unsqueeze(0).repeat(bs, 1)

@@ -89,6 +89,11 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
  * logits device fp32 [B][C][L]; noise device fp32 [B*L][C]; tok device int64 [B][L] (out). */
 int biom3_sample_all(const float* logits, const float* noise, int64_t* tok, int B, int L, int C, void* stream);
 
+/* Device-side replacement for the per-sample `torch.randperm(args.diffusion_steps)` sampling paths
+ * (run_ProteoScribe_sample.py:103-105): one uniformly random permutation of 0..L-1 per row (sorted Philox keys).
+ * path device int64 [B][L] (out), L <= 8192.  Deterministic in (seed, row); not torch's generator stream. */
+int biom3_random_paths(uint64_t seed, int B, int L, int64_t* path, void* stream);
+
 /* Replaces the unmask write `state[:, 0, loc] = tok[:, loc]` (sampling_analysis.py:254-256).
  * tok, state device int64 [B][L]; path device int64 [B][L]; step = current time index. */
 int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B, int L, int group, int step,

@@ -189,3 +189,9 @@ def test_extract_samples_with_labels():
     assert len(out['sample']) == 3 and out['sample'][0].tolist() == [4, 5, 6] and out['sample'][2].tolist() == [1, 1, 1]
     out = samp.extract_samples_with_labels([(torch.arange(6).reshape(2, 3), torch.tensor([1, 0]))], 1, 5, pad_included=True)
     assert len(out['sample']) == 1 and out['sample'][0].tolist() == [0, 1, 2]
+
+
+def test_random_paths_has_no_cpu_path():
+    from biom3_b200 import engine
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        engine.random_paths(2, 128, 1, 'cpu')

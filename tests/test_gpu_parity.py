@@ -335,6 +335,41 @@ def test_facilitator_vs_reference_fixture():
     assert rel_err(got, torch.from_numpy(z['z_c'])) < 1e-4
 
 
+@pytest.mark.parametrize('B,L', [(1, 128), (7, 1024), (64, 1024), (3, 1000), (2, 4096)])
+def test_device_random_paths_are_permutations(B, L):
+    """biom3_random_paths: every row a permutation of 0..L-1 (any L, padded to a power of two inside), deterministic in the
+    seed, rows and seeds differ, and position 0 lands uniformly (mean rank over many rows ~ (L - 1) / 2)."""
+    from biom3_b200 import engine
+    p1 = engine.random_paths(B, L, 42, 'cuda')
+    p2 = engine.random_paths(B, L, 42, 'cuda')
+    p3 = engine.random_paths(B, L, 43, 'cuda')
+    assert p1.dtype == torch.int64 and p1.shape == (B, L)
+    assert torch.equal(p1, p2) and not torch.equal(p1, p3)
+    assert torch.equal(p1.sort(dim=1).values, torch.arange(L, device='cuda').expand(B, L))
+    if B > 1:
+        assert not torch.equal(p1[0], p1[1])
+    big = engine.random_paths(4096, 256, 7, 'cuda')
+    where0 = (big == 0).float().argmax(dim=1).float()
+    assert abs(where0.mean().item() - 127.5) < 6.0               # sigma of the mean = 73.9 / 64 = 1.15
+
+
+def test_cli_flow_with_device_paths():
+    """args.b200_device_paths: the CLI draws the sampling paths on the GPU; same result contract, repeatable under torch.manual_seed."""
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+    args = synthetic.stage3_args(**dict(SMALL, text_emb_dim=64), num_replicas=3, batch_size_sample=2, b200_device_paths=True)
+    args.device = 'cuda'
+    model = mod.get_model(args, (32, 32), 29)
+    model.load_state_dict(synthetic.random_state_dict(args, seed=11, perturb_norm=True))
+    model.eval()
+    z_c = synthetic.synthetic_z_c(2, 64, seed=4)
+    torch.manual_seed(99)
+    d1 = cli.batch_stage3_generate_sequences(args, model, z_c)
+    torch.manual_seed(99)
+    d2 = cli.batch_stage3_generate_sequences(args, model, z_c)
+    assert d1 == d2 and sorted(d1) == ['replica_0', 'replica_1', 'replica_2'] and all(len(v) == 2 for v in d1.values())
+
+
 def test_cli_flow_facilitator_to_sequences_end_to_end():
     """BASELINE.json configs[3] in miniature, through the reference-facing entry points only: Facilitator z_t -> z_c on the
     GPU, then batch_stage3_generate_sequences (prompt x replica-batch units, one random path per sample, the sampler loop, ids ->
