@@ -367,6 +367,12 @@ struct biom3_model {
   bool attn_overlap = false;                    // measured: no gain (the two kernels do not co-reside), kept as a switch
   cudaGraphExec_t graph_exec = nullptr;
   int graph_B = -1, graph_group = -1;
+  // forward API: the ~100 launches of one forward replayed as a graph too (B = 1 is launch bound: 1.64 ms un-graphed); the graph
+  // writes logits into an internal buffer that is then copied to the caller's pointer.  BIOM3_FWD_GRAPH=0: plain launches.
+  bool fwd_graph = true;
+  cudaGraphExec_t fwd_exec = nullptr;
+  int fwd_B = -1;
+  float* logits_buf = nullptr;                  // [max_batch][C][L], allocated at the first forward
   std::vector<void*> allocs;
   int launches_per_step = 0;
   // fp32-class mode (biom3_set_precision(m, 1) before finalize): split [hi | lo] weights and fp32 activations
@@ -753,6 +759,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_EPI_PIPE")) m->epi_pipe = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_ARES")) m->a_res = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_RESID_DEPTH")) m->resid_depth = atoi(e) == 2 ? 2 : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
@@ -769,6 +776,7 @@ void biom3_destroy(biom3_model* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->fwd_exec) cudaGraphExecDestroy(m->fwd_exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   if (m->side_stream) cudaStreamDestroy(m->side_stream);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -993,7 +1001,33 @@ int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const floa
   k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(x), m->state, n);
   k::i64_to_i32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), m->t_i32, B);
   run_y_mlp(m, y_c, B, st);
-  CU_OK(run_step(m, B, 0, m->t_i32, logits, false, false, st, nullptr, nullptr));
+  if (!m->fwd_graph) {
+    CU_OK(run_step(m, B, 0, m->t_i32, logits, false, false, st, nullptr, nullptr));
+    CU_OK(cudaGetLastError());
+    return BIOM3_OK;
+  }
+  const size_t C = m->cfg.num_classes;
+  if (!m->logits_buf) {
+    int r2 = dev_alloc(m, &m->logits_buf, size_t(m->max_batch) * C * L);
+    if (r2) return r2;
+  }
+  if (!m->fwd_exec || m->fwd_B != B) {
+    if (m->fwd_exec) {
+      cudaGraphExecDestroy(m->fwd_exec);
+      m->fwd_exec = nullptr;
+    }
+    cudaGraph_t graph;
+    CU_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = run_step(m, B, 0, m->t_i32, m->logits_buf, false, false, m->cap_stream, nullptr, nullptr);
+    cudaError_t e2 = cudaStreamEndCapture(m->cap_stream, &graph);
+    if (e != cudaSuccess) return fail(BIOM3_ERR_CUDA, std::string("forward capture: ") + cudaGetErrorString(e));
+    CU_OK(e2);
+    CU_OK(cudaGraphInstantiate(&m->fwd_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    m->fwd_B = B;
+  }
+  CU_OK(cudaGraphLaunch(m->fwd_exec, st));
+  CU_OK(cudaMemcpyAsync(logits, m->logits_buf, size_t(B) * C * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }
