@@ -295,8 +295,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tma_load_2d_cg2(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          continue;
-        }
+        } else
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
@@ -349,8 +348,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (kb == nk - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          continue;
-        }
+        } else
         for (int kb = 0; kb < k_blocks; ++kb) {
 #if BIOM3_MMA_PARKED
           ptx::mbar_wait_parked(&full_bar[stage], phase);
