@@ -106,20 +106,45 @@ class _LazyTimes(Sequence):
         return np.full((self._b, 1), self._s + i, dtype=np.int64)
 
 
+class _FinalState(Sequence):
+    """``mask_realization_list`` of a ``final_only`` call: it has the reference's length, but only the last entry (the
+    one run_ProteoScribe_sample.py:121 reads) was brought back from the device."""
+
+    def __init__(self, tokens_u8: np.ndarray, n: int):
+        self._tok, self._n = tokens_u8, n          # [B, L] uint8 (host)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice) or i not in (-1, self._n - 1):
+            raise IndexError('final_only=True keeps only the last state; call without it for the whole trajectory')
+        return self._tok.astype(np.int64)[:, None, :]
+
+
 def _pinned(t: torch.Tensor) -> torch.Tensor:
     t = t.contiguous()
     return t if t.is_cuda or t.is_pinned() else t.pin_memory()
 
 
+def default_noise_seed(device) -> int:
+    """Philox seed for the on-device Exp(1) draws when the caller gives none: one draw from the CUDA generator of
+    ``device`` — the generator the reference's ``OneHotCategorical.sample()`` consumes on its CUDA device
+    (sampling_analysis.py:251), so ``torch.manual_seed`` makes a run repeatable as it does for the reference, and
+    torch's CPU generator (the reference's ``torch.randperm`` paths, run_ProteoScribe_sample.py:108) is left alone."""
+    return int(torch.randint(0, 2 ** 62, (1,), device=device).item())
+
+
 @torch.no_grad()
 def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_time, extract_digit_label,
                                     sampling_path, noise: Optional[torch.Tensor] = None,
-                                    seed: Optional[int] = None):
-    """Reference signature (:204-211) plus two optional keywords:
+                                    seed: Optional[int] = None, final_only: bool = False):
+    """Reference signature (:204-211) plus three optional keywords:
 
-    noise  explicit Exp(1) draws [T, B*L, C] (parity runs); default: drawn on the device.
-    seed   Philox seed for the on-device draws; default: taken from torch's global CPU generator,
-           so ``torch.manual_seed`` makes a run repeatable just as it does for the reference.
+    noise       explicit Exp(1) draws [T, B*L, C] (parity runs); default: drawn on the device.
+    seed        Philox seed for the on-device draws; default: ``default_noise_seed`` (CUDA generator).
+    final_only  bring back only the final state (64 KB instead of the 64 MB trajectory at B = 64): the returned
+                list has the reference's length but only ``[-1]`` can be read.
     """
     assert extract_digit_samples.size(0) == extract_digit_label.size(0) == sampling_path.size(0) == \
         extract_time.size(0), "Mismatched batch dimensions"
@@ -132,8 +157,8 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
     L = eng.L
     start = int(extract_time.reshape(-1)[0].item())          # the reference assumes one shared start step
     steps = max(0, int(args.diffusion_steps) - start)
-    if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if seed is None and noise is None:
+        seed = default_noise_seed(dev)
     y_c = _pinned(extract_digit_label.float()).to(dev, non_blocking=True)
     path = _pinned(sampling_path.long()).to(dev, non_blocking=True)
     x0 = extract_digit_samples
@@ -143,7 +168,12 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
     if noise is not None:
         noise = _pinned(noise.float()).to(dev, non_blocking=True)
     tokens, traj = eng.decode(y_c, path, state0=state0, start_step=start, num_steps=steps, group=B,
-                              noise=noise, seed=seed, want_traj=True)
+                              noise=noise, seed=seed or 0, want_traj=not final_only)
+    if final_only:
+        host = torch.empty((B, L), dtype=torch.uint8, pin_memory=True)
+        host.copy_(tokens.to(torch.uint8), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return _FinalState(host.numpy(), steps), _LazyTimes(start, steps, B)
     host = torch.empty(traj.shape, dtype=torch.uint8, pin_memory=True)
     host.copy_(traj, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()

@@ -14,8 +14,12 @@ SYMBOLS = [
     'biom3_create', 'biom3_destroy', 'biom3_last_error', 'biom3_set_weight', 'biom3_finalize_weights',
     'biom3_forward', 'biom3_decode', 'biom3_sample_all', 'biom3_unmask', 'biom3_gemm_test',
     'biom3_profile_step', 'biom3_launches_per_step', 'biom3_debug_copy', 'biom3_facilitator', 'biom3_attention_test',
-    'biom3_set_precision', 'biom3_random_paths',
+    'biom3_set_precision', 'biom3_random_paths', 'biom3_debug_noise',
+    'biom3_facilitator_create', 'biom3_facilitator_forward', 'biom3_facilitator_destroy',
 ]
+
+# BIOM3_DTYPE_* of include/biom3_b200.h
+DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_F64 = 0, 1, 2, 3
 
 
 class Config(C.Structure):
@@ -50,7 +54,7 @@ def load() -> C.CDLL:
     lib.biom3_destroy.restype = None
     lib.biom3_last_error.argtypes = []
     lib.biom3_last_error.restype = C.c_char_p
-    lib.biom3_set_weight.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.biom3_set_weight.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
     lib.biom3_set_weight.restype = i32
     lib.biom3_finalize_weights.argtypes = [vp]
     lib.biom3_finalize_weights.restype = i32
@@ -76,6 +80,14 @@ def load() -> C.CDLL:
     lib.biom3_set_precision.restype = i32
     lib.biom3_random_paths.argtypes = [C.c_uint64, i32, i32, vp, vp]
     lib.biom3_random_paths.restype = i32
+    lib.biom3_debug_noise.argtypes = [u64, i32, i32, i32, i32, vp, vp]
+    lib.biom3_debug_noise.restype = i32
+    lib.biom3_facilitator_create.argtypes = [i32, i32, i32, vp, C.c_float, vp, vp, C.c_float, vp, i32, C.POINTER(vp)]
+    lib.biom3_facilitator_create.restype = i32
+    lib.biom3_facilitator_forward.argtypes = [vp, vp, i32, vp, vp]
+    lib.biom3_facilitator_forward.restype = i32
+    lib.biom3_facilitator_destroy.argtypes = [vp]
+    lib.biom3_facilitator_destroy.restype = None
     lib.biom3_launches_per_step.argtypes = [vp]
     lib.biom3_launches_per_step.restype = i32
     _lib = lib

@@ -1135,4 +1135,317 @@ local_attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bflo
   if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
 }
 
+
+// ================================================================================================
+// Windowed softmax attention on tcgen05, NS independent streams per CTA (template; round 2).
+// The persistent schedule of variant 3 with its shape made a compile-time choice:
+//   NS   streams per CTA (2 or 4).  A stream = TMA producer warp + MMA issuer warp + four softmax warps (one thread per
+//        query row, warp w of the four owns TMEM lanes 32 w ..), 512 / NS tensor-memory columns and its own smem ring;
+//        it walks every NS-th item of the CTA.  The softmax warps of different streams that share an SMSP are what
+//        keeps the MUFU pipe (one ex2 per score: the floor of this kernel, 16 per clock per SM measured) busy while a
+//        stream waits for its MMAs, its tensor-memory loads or its barriers.
+//   BK   keys per block (64 or 32): S_g = Q K_g^T is 128 x BK, three S / P slots per stream.
+//   POLY every POLY-th exponential is evaluated on the FMA / ALU pipes (Cody-Waite + cubic), 0 = all on MUFU.
+// TMEM per stream: S / P slots at 0, BK, 2 BK; O buffers (32 columns each) from 3 BK.
+//   NS = 2, BK = 64: 192 + 2 x 32 = 256 columns;  NS = 4, BK = 32: 96 + 32 = 128 columns.
+// ================================================================================================
+template <int NS, int BK>
+struct MsCfg {
+  static constexpr int NST = NS == 2 ? 3 : 2;               // K/V ring stages per stream (tiles of 128 keys)
+  static constexpr int NOB = NS == 2 ? 2 : 1;               // O accumulators per stream
+  static constexpr int SB = WIN / BK;                       // blocks per K/V tile
+  static constexpr int TM_STREAM = 512 / NS;
+  static constexpr int TM_O = 3 * BK;
+  static constexpr int THREADS = NS * 6 * 32;
+  static constexpr int STREAM_TILES = 2 + 2 * NST;
+  static constexpr int SMEM_BYTES = NS * STREAM_TILES * TC_TILE + 1024;
+  static_assert(TM_O + NOB * 32 <= TM_STREAM, "tensor memory budget");
+  static_assert((2 * NS) % 4 == 0, "softmax warp w must sit on TMEM lane quarter w % 4");
+};
+
+template <int NST, int NOB>
+struct MsBars {
+  uint64_t q_full[2], q_free[2], kv_full[NST], kv_free[NST], s_full[3], p_ready[3], s_free[3], o_full[NOB], o_free[NOB];
+};
+struct MsCursor {
+  int i, n, t, g, kt, sb, nkt, w, b, h, w_lo;
+  bool valid;
+};
+
+// 2^x for x <= ~8 on the FMA / ALU pipes: round to nearest integer with the 1.5 * 2^23 trick, cubic on [-0.5, 0.5]
+// (relative error 1e-4, far inside the bf16 rounding of P), exponent added to the bit pattern.
+__device__ __forceinline__ float ex2_fma_pipe(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05550411f, 0.24022651f);
+  p = fmaf(p, f, 0.69314718f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int NS, int BK, int POLY>
+__global__ void __launch_bounds__(MsCfg<NS, BK>::THREADS, 1)
+local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
+                          int L, int NL, float scale_log2e, int reverse) {
+  using Cfg = MsCfg<NS, BK>;
+  constexpr int NST = Cfg::NST, NOB = Cfg::NOB, SB = Cfg::SB;
+  const int nw = L / WIN;
+  const int total = nw * B * NL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stream = warp < 2 * NS ? (warp >> 1) : ((warp - 2 * NS) >> 2);
+  const int role = warp < 2 * NS ? (warp & 1) : 2;       // 0 producer, 1 issuer, 2 softmax
+
+  extern __shared__ uint8_t ms_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ms_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + stream * Cfg::STREAM_TILES * TC_TILE;     // 2 tiles
+  uint8_t* sKV = sQ + 2 * TC_TILE;                               // NST x (K tile, V tile)
+  __shared__ MsBars<NST, NOB> bars[NS];
+  __shared__ uint32_t tmem_slot;
+  MsBars<NST, NOB>& bar = bars[stream];
+
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_qkv);
+    for (int s2 = 0; s2 < NS; ++s2) {
+      MsBars<NST, NOB>& x = bars[s2];
+      for (int k = 0; k < 2; ++k) {
+        ptx::mbar_init(&x.q_full[k], 1);
+        ptx::mbar_init(&x.q_free[k], 1);
+      }
+      for (int k = 0; k < NOB; ++k) {
+        ptx::mbar_init(&x.o_full[k], 1);
+        ptx::mbar_init(&x.o_free[k], 4);
+      }
+      for (int k = 0; k < NST; ++k) {
+        ptx::mbar_init(&x.kv_full[k], 1);
+        ptx::mbar_init(&x.kv_free[k], 1);
+      }
+      for (int k = 0; k < 3; ++k) {
+        ptx::mbar_init(&x.s_full[k], 1);
+        ptx::mbar_init(&x.p_ready[k], 4);
+        ptx::mbar_init(&x.s_free[k], 1);
+      }
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot + stream * Cfg::TM_STREAM;
+  ptx::pdl_sync();
+
+  const int nlb = NL * B;
+  auto seek = [&](MsCursor& c) {
+    const int f = int(blockIdx.x) + c.i * int(gridDim.x);
+    c.valid = f < total;
+    if (!c.valid) return;
+    const int ff = reverse ? total - 1 - f : f;
+    c.w = ff / nlb;
+    const int r = ff - c.w * nlb;
+    c.b = r / NL;
+    c.h = r - c.b * NL;
+    c.w_lo = max(c.w - 1, 0);
+    c.nkt = min(c.w + 1, nw - 1) - c.w_lo + 1;
+    c.kt = 0;
+    c.sb = 0;
+  };
+  auto start = [&](MsCursor& c) { c.i = stream; c.n = 0; c.t = 0; c.g = 0; seek(c); };
+  auto advance = [&](MsCursor& c) {
+    ++c.g;
+    if (++c.sb == SB) {
+      c.sb = 0;
+      ++c.t;
+      if (++c.kt == c.nkt) { c.i += NS; ++c.n; seek(c); }
+    }
+  };
+  auto first_block = [](const MsCursor& c) { return c.kt == 0 && c.sb == 0; };
+  auto last_block = [](const MsCursor& c) { return c.kt == c.nkt - 1 && c.sb == SB - 1; };
+
+  if (role == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int plane = B * H * L;
+      MsCursor c;
+      for (start(c); c.valid; advance(c)) {
+        if (c.sb != 0) continue;
+        const int rq = (c.b * H + c.h) * L;
+        if (c.kt == 0) {
+          const int qb = c.n & 1;
+          ptx::mbar_wait_parked(&bar.q_free[qb], ((c.n >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
+          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + c.w * WIN);
+        }
+        const int st = c.t % NST;
+        ptx::mbar_wait_parked(&bar.kv_free[st], ((c.t / NST) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
+        ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (c.w_lo + c.kt) * WIN);
+        ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kt) * WIN);
+      }
+    }
+  } else if (role == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t(BK) >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      auto issue_s = [&](const MsCursor& c) {
+        const int qb = c.n & 1, st = c.t % NST, slot = c.g % 3;
+        if (first_block(c)) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
+        if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[st], (c.t / NST) & 1);
+        ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g / 3) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
+        const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE) + c.sb * BK * 64);
+        ptx::umma_bf16(tmem + slot * BK, dq, dk, IDESC_S, 0);
+        ptx::umma_bf16(tmem + slot * BK, dq + 2, dk + 2, IDESC_S, 1);
+        ptx::umma_commit(&bar.s_full[slot]);
+        if (last_block(c)) ptx::umma_commit(&bar.q_free[qb]);
+      };
+      auto issue_pv = [&](const MsCursor& c) {
+        const int ob = c.n % NOB, st = c.t % NST, slot = c.g % 3;
+        if (first_block(c)) ptx::mbar_wait_parked(&bar.o_free[ob], ((c.n / NOB) & 1) ^ 1);
+        ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g / 3) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE) + c.sb * BK * 64;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks)
+          ptx::umma_bf16_ts(tmem + Cfg::TM_O + ob * 32, tmem + slot * BK + ks * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
+                            !(first_block(c) && ks == 0));
+        ptx::umma_commit(&bar.s_free[slot]);
+        if (c.sb == SB - 1) ptx::umma_commit(&bar.kv_free[st]);
+        if (last_block(c)) ptx::umma_commit(&bar.o_full[ob]);
+      };
+      MsCursor sc, pc;
+      start(sc);
+      start(pc);
+      while (pc.valid) {
+        while (sc.valid && sc.g < pc.g + 3) {
+          issue_s(sc);
+          advance(sc);
+        }
+        issue_pv(pc);
+        advance(pc);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (4 warps per stream)
+    // Online softmax per BK-key block against a lazily updated reference maximum: the first block of an item sets m_ref
+    // to its row maximum; a later block rescales O and the row sum only when its maximum exceeds m_ref by more than 2^8
+    // (P stays <= 256, exact in bf16's range), which real score distributions almost never do.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
+    const int D = H * DH;
+    constexpr float LAZY_LOG2 = 8.0f;
+    float m_ref = 0.f, rs = 0.f;
+    bool pend = false;
+    int p_n = 0;
+    float p_inv = 0.f;
+    __nv_bfloat16* p_dst = nullptr;
+    auto epilogue = [&]() {
+      const int ob = p_n % NOB;
+      ptx::mbar_wait(&bar.o_full[ob], (p_n / NOB) & 1);
+      ptx::tc_fence_after();
+      uint32_t ro[32];
+      ptx::tmem_ld_32x32(lane_base + Cfg::TM_O + ob * 32, ro);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.o_free[ob]);
+      uint4* dst = reinterpret_cast<uint4*>(p_dst);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * p_inv, __uint_as_float(ro[8 * k + 1]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * p_inv, __uint_as_float(ro[8 * k + 3]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
+    };
+    MsCursor c;
+    for (start(c); c.valid; advance(c)) {
+      const int g = c.g, slot = g % 3;
+      const uint32_t t_s = lane_base + slot * BK;
+      ptx::mbar_wait(&bar.s_full[slot], (g / 3) & 1);
+      ptx::tc_fence_after();
+      uint32_t r[BK];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+        ptx::tmem_ld_32x32(t_s, r0);
+        if constexpr (BK == 64) {
+          uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+          ptx::tmem_ld_32x32(t_s + 32, r1);
+        }
+      }
+      ptx::tmem_ld_wait();
+      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < BK / 4; ++k) {
+        b0 = fmaxf(b0, __uint_as_float(r[4 * k]));
+        b1 = fmaxf(b1, __uint_as_float(r[4 * k + 1]));
+        b2 = fmaxf(b2, __uint_as_float(r[4 * k + 2]));
+        b3 = fmaxf(b3, __uint_as_float(r[4 * k + 3]));
+      }
+      const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+      if (first_block(c)) {
+        m_ref = bm;
+        rs = 0.f;
+      } else {
+        const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          const int gp = g - 1;                            // every PV issued so far must have landed in O
+          ptx::mbar_wait(&bar.s_free[gp % 3], (gp / 3) & 1);
+          ptx::tc_fence_after();
+          const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
+          uint32_t ro[32];
+          const uint32_t t_o = lane_base + Cfg::TM_O + (c.n % NOB) * 32;
+          ptx::tmem_ld_32x32(t_o, ro);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
+          ptx::tmem_st_32x32(t_o, ro);
+          ptx::tmem_st_wait();
+          rs *= f;
+          if (need) m_ref = bm;
+        }
+      }
+      const float ms = m_ref * scale_log2e;
+      uint32_t pk[BK / 2];                                 // P (bf16 pairs) over the first BK / 2 of the slot's columns
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < BK / 4; ++k) {
+        const float x0 = fmaf(__uint_as_float(r[4 * k]), scale_log2e, -ms), x1 = fmaf(__uint_as_float(r[4 * k + 1]), scale_log2e, -ms);
+        const float x2 = fmaf(__uint_as_float(r[4 * k + 2]), scale_log2e, -ms), x3 = fmaf(__uint_as_float(r[4 * k + 3]), scale_log2e, -ms);
+        const float p0 = fast_ex2(x0), p1 = fast_ex2(x1), p2 = fast_ex2(x2);
+        const float p3 = (POLY > 0 && (k % (POLY / 4 > 0 ? POLY / 4 : 1)) == 0) ? ex2_fma_pipe(x3) : fast_ex2(x3);
+        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        pk[2 * k] = ptx::pack_bf16x2(p0, p1);
+        pk[2 * k + 1] = ptx::pack_bf16x2(p2, p3);
+      }
+      rs += (s0 + s1) + (s2 + s3);
+      if constexpr (BK == 64) ptx::tmem_st_32x32(t_s, pk);
+      else ptx::tmem_st_32x16(t_s, pk);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+      if (first_block(c) && pend) {
+        epilogue();
+        pend = false;
+      }
+      if (last_block(c)) {
+        pend = true;
+        p_n = c.n;
+        p_inv = 1.f / rs;
+        p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH;
+      }
+    }
+    if (pend) epilogue();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
+}
+
 }  // namespace attn

@@ -156,13 +156,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-// Exp(1) draw for (step, flat position, class): -log(u), u in (0, 1]
+// Exp(1) draw for (step, flat position, class) by inversion: q = -log1p(-v), v uniform on the open interval (0, 1).
+// v = (w + 1/2) 2^-32 from one 32-bit Philox word, capped at the largest float below 1, so q is finite and strictly
+// positive (1.2e-10 <= q <= 16.7): no draw can win the argmax(p / q) race by being zero, negative or infinite.  IEEE
+// log1pf (not the fast-math logarithm) keeps the small draws — the ones that win races — accurate to an ulp.
+// oracle/philox.py restates this stream on the CPU; biom3_debug_noise() exports it for the parity tests.
 __device__ __forceinline__ float philox_exp1(unsigned long long seed, int step, int pos, int c) {
   const uint4 r = philox4x32_10(make_uint4(uint32_t(pos), uint32_t(step), uint32_t(c >> 2), 0u),
                                 make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  const float uu = (float(w[c & 3] >> 8) + 1.0f) * (1.0f / 16777216.0f);
-  return -__logf(uu) + 1e-30f;
+  const float v = fminf(fmaf(float(w[c & 3]), 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
+  return -log1pf(-v);
+}
+
+// Test hook (biom3_debug_noise): the Exp(1) draws head_kernel consumes at `step`, as noise[pos][c], pos = b * L + l
+__global__ void debug_noise_kernel(unsigned long long seed, int step, int n_pos, int C, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pos * C) out[i] = philox_exp1(seed, step, i / C, i % C);
 }
 
 // ---------------------------------------------------------------- sampling paths on the device
@@ -594,8 +604,8 @@ sgemm_bias_act_kernel(const float* __restrict__ A, const float* __restrict__ W, 
   for (int k0 = 0; k0 < K; k0 += 16) {
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i >> 4, c = i & 15;
-      sa[c][r] = (m0 + r < M) ? A[size_t(m0 + r) * K + k0 + c] : 0.f;
-      sb[c][r] = (n0 + r < N) ? W[size_t(n0 + r) * K + k0 + c] : 0.f;
+      sa[c][r] = (m0 + r < M && k0 + c < K) ? A[size_t(m0 + r) * K + k0 + c] : 0.f;     // K need not be a multiple of 16
+      sb[c][r] = (n0 + r < N && k0 + c < K) ? W[size_t(n0 + r) * K + k0 + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll

@@ -2,6 +2,7 @@
 // See include/biom3_b200.h for the contract and the reference interfaces each entry point replaces.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
@@ -266,18 +267,55 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+#define SET_MS(NS, BK, POLY)                                                                                     \
+  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<NS, BK, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           attn::MsCfg<NS, BK>::SMEM_BYTES);                                                     \
+  if (e != cudaSuccess) return e;
+  SET_MS(2, 64, 0) SET_MS(4, 32, 0) SET_MS(4, 32, 4) SET_MS(4, 32, 8) SET_MS(2, 64, 8)
+#undef SET_MS
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::sample_all_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            2 * 32 * k::SAMPLE_TILE * int(sizeof(float)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k::random_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
   return e;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so the opt-ins are tracked per device (a process may hold
+// engines on several GPUs); a failure is returned to the caller and not cached, so a later call retries.
 cudaError_t init_kernel_attributes() {
-  static std::once_flag once;
-  static cudaError_t result = cudaSuccess;
-  std::call_once(once, [] { result = init_kernel_attributes_impl(); });
-  return result;
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = init_kernel_attributes_impl();
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
+// windowed attention, multi-stream template (attention.cuh): variant 4 = <2, 64, 0> (the round-1 schedule), 5 = <4, 32, 0>,
+// 6 = <4, 32, 4>, 7 = <4, 32, 8>, 8 = <2, 64, 8>
+void launch_local_ms(int variant, const CUtensorMap& tm, bf16* out, int B, int H, int L, int NL, float scale_log2e, int reverse,
+                     int num_sms, cudaStream_t st) {
+  const int grid = std::min(num_sms, (L / attn::WIN) * NL * B);
+#define MS_CASE(V, NS, BK, POLY)                                                                                  \
+  case V:                                                                                                         \
+    launch_k(attn::local_attention_ms_kernel<NS, BK, POLY>, dim3(grid), dim3(attn::MsCfg<NS, BK>::THREADS),       \
+             size_t(attn::MsCfg<NS, BK>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse);           \
+    break;
+  switch (variant) {
+    MS_CASE(4, 2, 64, 0)
+    MS_CASE(5, 4, 32, 0)
+    MS_CASE(6, 4, 32, 4)
+    MS_CASE(7, 4, 32, 8)
+    default:
+    MS_CASE(8, 2, 64, 8)
+  }
+#undef MS_CASE
 }
 
 enum Cat { C_QKV, C_OUT, C_FF1, C_FF2, C_LOCAL, C_LINEAR, C_LN, C_EMBED, C_HEAD, C_OTHER, C_COUNT };
@@ -307,6 +345,7 @@ struct biom3_model {
   bool use_pair = true;                         // CTA-pair (cta_group::2) GEMM tiling when M % 256 == 0
   bool finalized = false;
   std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;   // as passed to biom3_set_weight (error messages)
   // weights
   bf16 *Wqkv = nullptr, *Wo = nullptr, *W1 = nullptr, *W2 = nullptr;
   float *ln_s_qkv = nullptr, *ln_t_qkv = nullptr, *ln_s_ff = nullptr, *ln_t_ff = nullptr;   // folded LayerNorms
@@ -385,6 +424,11 @@ struct biom3_model {
   CUtensorMap tm_wqkv2[2]{}, tm_wo2[2]{}, tm_w1s[2]{}, tm_w2s[2]{};
 };
 
+struct biom3_facilitator_t {
+  int device = 0, in_dim = 0, hid_dim = 0, out_dim = 0, hid_rows = 0;
+  float *w0 = nullptr, *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *hid = nullptr;   // weight norm folded
+};
+
 namespace {
 
 template <typename T>
@@ -401,8 +445,12 @@ int get_w(biom3_model* m, const std::string& key, size_t numel, const std::vecto
   auto it = m->host_w.find(key);
   if (it == m->host_w.end()) return fail(BIOM3_ERR_STATE, "missing weight: " + key);
   if (it->second.size() != numel)
-    return fail(BIOM3_ERR_STATE, "size mismatch for " + key + ": got " + std::to_string(it->second.size()) +
-                                     ", expected " + std::to_string(numel));
+  {
+    std::string shp;
+    for (int64_t d : m->host_shape[key]) shp += (shp.empty() ? "[" : ", ") + std::to_string(d);
+    return fail(BIOM3_ERR_STATE, "size mismatch for " + key + ": got " + std::to_string(it->second.size()) + " elements " + shp +
+                                     "], expected " + std::to_string(numel));
+  }
   *out = &it->second;
   return BIOM3_OK;
 }
@@ -596,7 +644,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), lst, m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
     if (NL > 0) {
-      if (m->attn_tc == 3)
+      if (m->attn_tc >= 4)
+        LAUNCH(C_LOCAL, launch_local_ms(m->attn_tc, m->tm_qkv_attn, m->att, B, H, L, NL, scale_log2e, adir, m->num_sms, st));
+      else if (m->attn_tc == 3)
         LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc3_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
                                  dim3(attn::TC3_THREADS), size_t(attn::TC3_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
                                  scale_log2e, adir));
@@ -785,10 +835,49 @@ void biom3_destroy(biom3_model* m) {
   delete m;
 }
 
-int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t numel) {
-  if (!m || !key || !data || numel <= 0) return fail(BIOM3_ERR_INVALID, "bad set_weight argument");
+int biom3_set_weight(biom3_model* m, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!m || !key || !data || !shape || ndim < 0 || ndim > 8) return fail(BIOM3_ERR_INVALID, "bad set_weight argument");
   if (m->finalized) return fail(BIOM3_ERR_STATE, "weights already finalized");
-  m->host_w[key] = std::vector<float>(data, data + numel);
+  size_t esz = 0;
+  switch (dtype) {
+    case BIOM3_DTYPE_F32: esz = 4; break;
+    case BIOM3_DTYPE_BF16: case BIOM3_DTYPE_F16: esz = 2; break;
+    case BIOM3_DTYPE_F64: esz = 8; break;
+    default: return fail(BIOM3_ERR_INVALID, std::string("unsupported dtype code for ") + key);
+  }
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) return fail(BIOM3_ERR_INVALID, std::string("negative extent for ") + key);
+    numel *= shape[i];
+  }
+  if (numel <= 0) return fail(BIOM3_ERR_INVALID, std::string("empty tensor for ") + key);
+  // host or device pointer: device (and managed) memory is staged through one host copy
+  cudaPointerAttributes pa{};
+  const bool on_device = cudaPointerGetAttributes(&pa, data) == cudaSuccess &&
+                         (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+  cudaGetLastError();                                   // an unregistered host pointer is not an error
+  std::vector<uint8_t> staged;
+  const uint8_t* src = static_cast<const uint8_t*>(data);
+  if (on_device) {
+    staged.resize(size_t(numel) * esz);
+    CU_OK(cudaMemcpy(staged.data(), data, staged.size(), cudaMemcpyDeviceToHost));
+    src = staged.data();
+  }
+  std::vector<float> w(static_cast<size_t>(numel));
+  for (int64_t i = 0; i < numel; ++i) {
+    switch (dtype) {
+      case BIOM3_DTYPE_F32: w[i] = reinterpret_cast<const float*>(src)[i]; break;
+      case BIOM3_DTYPE_F64: w[i] = float(reinterpret_cast<const double*>(src)[i]); break;
+      case BIOM3_DTYPE_BF16: {
+        const uint32_t bits = uint32_t(reinterpret_cast<const uint16_t*>(src)[i]) << 16;
+        memcpy(&w[i], &bits, 4);
+        break;
+      }
+      default: w[i] = __half2float(reinterpret_cast<const __half*>(src)[i]); break;
+    }
+  }
+  m->host_w[key] = std::move(w);
+  m->host_shape[key] = std::vector<int64_t>(shape, shape + ndim);
   return BIOM3_OK;
 }
 
@@ -913,6 +1002,7 @@ int biom3_finalize_weights(biom3_model* m) {
     return fail(BIOM3_ERR_STATE, "unexpected keys in state dict: got " + std::to_string(m->host_w.size()) +
                                      " tensors, expected " + std::to_string(expected));
   m->host_w.clear();
+  m->host_shape.clear();
 
   // workspace, sized for max_batch
   if (m->precision == 0 && m->split_resid) {
@@ -1049,6 +1139,7 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
     k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(state0), m->state, n);
   else
     CU_OK(cudaMemsetAsync(m->state, 0, n, st));
+  CU_OK(cudaMemsetAsync(m->inv_path, 0, size_t(n) * sizeof(int), st));   // a non-permutation row falls back to location 0, like argmax of an all-false mask
   k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L);
   run_y_mlp(m, y_c, B, st);
   set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed);
@@ -1144,15 +1235,15 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
   return BIOM3_OK;
 }
 
-int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
-                      const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream) {
-  if (!z_t || !w0_v || !b0 || !w1_v || !b1 || !z_c || P < 1 || in_dim < 1 || hid_dim < 1 || out_dim < 1)
+int biom3_facilitator_create(int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g, const float* b0,
+                             const float* w1_v, float w1_g, const float* b1, int device, biom3_facilitator_t** out) {
+  if (!w0_v || !b0 || !w1_v || !b1 || !out || in_dim < 1 || hid_dim < 1 || out_dim < 1)
     return fail(BIOM3_ERR_INVALID, "bad facilitator argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // weight_norm(dim=None): W = g * V / ||V||_F with a scalar g -> fold into the weights once
+  CU_OK(cudaSetDevice(device));
+  // weight_norm(dim=None): W = g * V / ||V||_F with a scalar g -> folded into the weights once, here
   auto fold = [](const float* v, float g, size_t n) {
     double ss = 0.0;
     for (size_t i = 0; i < n; ++i) ss += double(v[i]) * double(v[i]);
@@ -1163,21 +1254,77 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
   };
   const std::vector<float> w0 = fold(w0_v, w0_g, size_t(hid_dim) * in_dim);
   const std::vector<float> w1 = fold(w1_v, w1_g, size_t(out_dim) * hid_dim);
-  float *d_w0, *d_b0, *d_w1, *d_b1, *d_h;
-  CU_OK(cudaMalloc(&d_w0, w0.size() * sizeof(float)));
-  CU_OK(cudaMalloc(&d_b0, hid_dim * sizeof(float)));
-  CU_OK(cudaMalloc(&d_w1, w1.size() * sizeof(float)));
-  CU_OK(cudaMalloc(&d_b1, out_dim * sizeof(float)));
-  CU_OK(cudaMalloc(&d_h, size_t(P) * hid_dim * sizeof(float)));
-  CU_OK(cudaMemcpyAsync(d_w0, w0.data(), w0.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(cudaMemcpyAsync(d_b0, b0, hid_dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(cudaMemcpyAsync(d_w1, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(cudaMemcpyAsync(d_b1, b1, out_dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  sgemm(z_t, d_w0, d_b0, d_h, P, hid_dim, in_dim, 2, st);       // Linear + exact erf-GELU (dropout p = 0 at eval)
-  sgemm(d_h, d_w1, d_b1, z_c, P, out_dim, hid_dim, 0, st);
+  biom3_facilitator_t* f = new biom3_facilitator_t();
+  f->device = device; f->in_dim = in_dim; f->hid_dim = hid_dim; f->out_dim = out_dim;
+  cudaError_t e = cudaMalloc(&f->w0, w0.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->b0, hid_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->w1, w1.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->b1, out_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(f->w0, w0.data(), w0.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(f->b0, b0, hid_dim * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(f->w1, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(f->b1, b1, out_dim * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    biom3_facilitator_destroy(f);
+    return fail(BIOM3_ERR_CUDA, std::string("facilitator upload: ") + cudaGetErrorString(e));
+  }
+  *out = f;
+  return BIOM3_OK;
+}
+
+void biom3_facilitator_destroy(biom3_facilitator_t* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  cudaDeviceSynchronize();
+  cudaFree(f->w0); cudaFree(f->b0); cudaFree(f->w1); cudaFree(f->b1); cudaFree(f->hid);
+  delete f;
+}
+
+int biom3_facilitator_forward(biom3_facilitator_t* f, const float* z_t, int P, float* z_c, void* stream) {
+  if (!f || !z_t || !z_c || P < 1) return fail(BIOM3_ERR_INVALID, "bad facilitator argument");
+  CU_OK(cudaSetDevice(f->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P > f->hid_rows) {                                    // hidden activation [P][hid], grown on demand
+    CU_OK(cudaStreamSynchronize(st));
+    cudaFree(f->hid);
+    f->hid = nullptr;
+    f->hid_rows = 0;
+    CU_OK(cudaMalloc(&f->hid, size_t(P) * f->hid_dim * sizeof(float)));
+    f->hid_rows = P;
+  }
+  sgemm(z_t, f->w0, f->b0, f->hid, P, f->hid_dim, f->in_dim, 2, st);      // Linear + exact erf-GELU (dropout p = 0 at eval)
+  sgemm(f->hid, f->w1, f->b1, z_c, P, f->out_dim, f->hid_dim, 0, st);
   CU_OK(cudaGetLastError());
-  CU_OK(cudaStreamSynchronize(st));                              // host vectors and temporaries die with this call
-  cudaFree(d_w0); cudaFree(d_b0); cudaFree(d_w1); cudaFree(d_b1); cudaFree(d_h);
+  return BIOM3_OK;
+}
+
+int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
+                      const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream) {
+  int dev = 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
+  CU_OK(cudaGetDevice(&dev));
+  biom3_facilitator_t* f = nullptr;
+  int r = biom3_facilitator_create(in_dim, hid_dim, out_dim, w0_v, w0_g, b0, w1_v, w1_g, b1, dev, &f);
+  if (r) return r;
+  r = biom3_facilitator_forward(f, z_t, P, z_c, stream);
+  if (r == BIOM3_OK && cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess)
+    r = fail(BIOM3_ERR_CUDA, "facilitator: stream synchronize failed");
+  biom3_facilitator_destroy(f);
+  return r;
+}
+
+int biom3_debug_noise(uint64_t seed, int step, int B, int L, int C, float* out, void* stream) {
+  if (!out || step < 0 || B < 1 || L < 1 || C < 1 || C > 32) return fail(BIOM3_ERR_INVALID, "bad debug_noise argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BIOM3_ERR_CUDA, "no CUDA device: biom3_b200 has no CPU path");
+  const long long n = static_cast<long long>(B) * L * C;
+  if (n > INT_MAX) return fail(BIOM3_ERR_INVALID, "debug_noise: B * L * C too large");
+  k::debug_noise_kernel<<<unsigned((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<unsigned long long>(seed), step, B * L, C, out);
+  CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }
 
@@ -1189,8 +1336,7 @@ int biom3_random_paths(uint64_t seed, int B, int L, int64_t* path, void* stream)
   int N = 1;
   while (N < L) N <<= 1;
   const size_t smem = size_t(N) * 12;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(k::random_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12); });
+  CU_OK(init_kernel_attributes());
   k::random_paths_kernel<<<B, std::min(1024, std::max(32, N / 2)), smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<unsigned long long>(seed), reinterpret_cast<long long*>(path), L, N);
   CU_OK(cudaGetLastError());
@@ -1233,11 +1379,16 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   if (NL > 0) {
-    if (variant >= 1 && variant <= 3) {
+    if (variant >= 1) {
       CUtensorMap tm;
       int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
       if (r) return r;
-      if (variant == 3) {
+      if (variant >= 4) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        launch_local_ms(variant, tm, o, B, H, L, NL, scale_log2e, 0, sms, st);
+      } else if (variant == 3) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1274,14 +1425,9 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
     return fail(BIOM3_ERR_INVALID, "A-resident tiling needs pair tiling, K <= 512 and a bf16 epilogue");
   if (pair && (block_n != 256 || M % 256)) return fail(BIOM3_ERR_INVALID, "pair tiling needs block_n == 256 and M % 256 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static cudaDeviceProp prop;
-  static bool have_prop = false;
-  if (!have_prop) {
-    int dev = 0;
-    CU_OK(cudaGetDevice(&dev));
-    CU_OK(cudaGetDeviceProperties(&prop, dev));
-    have_prop = true;
-  }
+  int gemm_dev = 0, sms = 0;
+  CU_OK(cudaGetDevice(&gemm_dev));
+  CU_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gemm_dev));
   CUtensorMap ta, tb;
   int r;
   if ((r = make_tmap(&ta, A, M, split3 ? 2 * K : K, 128))) return r;
@@ -1290,7 +1436,6 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   p.split3 = split3;
   p.M = M; p.N = N; p.K = K; p.b_row_offset = 0; p.out = out; p.bias = bias; p.cond = nullptr; p.cond_stride = 0;
   p.L = M; p.H = 1; p.Bsz = 1;
-  const int sms = prop.multiProcessorCount;
   if (const char* e = getenv("BIOM3_EPI_SKIP")) p.debug_skip = atoi(e);
   CUtensorMap tc;
   memset(&tc, 0, sizeof(tc));

@@ -23,6 +23,10 @@ def config_from_args(args: Namespace) -> _lib.Config:
         reversible=int(bool(getattr(args, 'transformer_reversible', False))))
 
 
+_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16,
+           torch.float64: _lib.DTYPE_F64}
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -57,8 +61,14 @@ class Engine:
         try:
             _lib.check(self.lib.biom3_set_precision(self.handle, self.PRECISIONS[precision]))
             for key, t in state_dict.items():
-                t = t.detach().to('cpu', torch.float32).contiguous()
-                _lib.check(self.lib.biom3_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+                # host or device memory, fp32 / bf16 / fp16 / fp64 as stored: the library stages and converts
+                t = t.detach()
+                if t.dtype not in _DTYPES:
+                    t = t.float()
+                t = t.contiguous()
+                shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
+                _lib.check(self.lib.biom3_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()), _DTYPES[t.dtype],
+                                                     shape, t.dim()))
             _lib.check(self.lib.biom3_finalize_weights(self.handle))
         except Exception:
             self.close()
@@ -144,6 +154,20 @@ def random_paths(B: int, L: int, seed: int, device) -> torch.Tensor:
         _lib.check(lib.biom3_random_paths(C.c_uint64(int(seed) & (2 ** 64 - 1)), B, L, _ptr(path),
                                           C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
     return path
+
+
+def device_noise(seed: int, step: int, B: int, L: int, C_: int, device) -> torch.Tensor:
+    """Test hook (biom3_debug_noise): the Exp(1) draws a decode with ``noise=None`` consumes at time index ``step`` under
+    ``seed`` -> fp32 [B*L, C] on the device."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('biom3_b200 has no CPU path: device_noise needs a CUDA device')
+    out = torch.empty(B * L, C_, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        _lib.check(lib.biom3_debug_noise(C.c_uint64(int(seed) & (2 ** 64 - 1)), int(step), B, L, C_, _ptr(out),
+                                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return out
 
 
 def sample_all(logits: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:

@@ -53,11 +53,17 @@ def clean_sequence(tokens, ids) -> str:
 
 
 @torch.no_grad()
-def batch_stage3_generate_sequences(args, model, z_t):
+def batch_stage3_generate_sequences(args, model, z_t, unit_paths=None, unit_noise=None, unit_seeds=None):
     """Reference semantics (:60-126): for every prompt, num_replicas sequences in batches of
     batch_size_sample, one fresh random permutation path per sample; returns
     {'replica_i': [sequence for each prompt]}.  Units run on this rank's GPU; with several ranks
-    they are sharded and gathered."""
+    they are sharded and gathered.
+
+    Everything random is drawn up front, for ALL units and in unit order, on every rank — first the sampling paths
+    (torch's CPU generator, like the reference's ``torch.randperm``, :108), then one Philox seed per unit for the
+    on-device Exp(1) noise — so a unit's tokens depend on its index only, not on the number of GPUs or on which rank
+    runs it.  Parity hooks (tests): ``unit_paths[u]`` int64 [bs, L], ``unit_noise[u]`` fp32 [L, bs*L, C] explicit
+    Exp(1) draws, ``unit_seeds[u]`` Philox seeds, each indexed by unit id."""
     if isinstance(z_t, list) and all(isinstance(item, torch.Tensor) for item in z_t):
         z_t = torch.stack(z_t)
     rank, world, _ = bdist.env_rank_world()
@@ -68,20 +74,28 @@ def batch_stage3_generate_sequences(args, model, z_t):
     mine = bdist.units_for_rank(len(units), rank, world)
     rows = min(args.batch_size_sample, args.num_replicas)
     local = torch.zeros(len(mine), rows, L, dtype=torch.uint8, device=args.device)
-    # every rank draws ALL paths in unit order so the result does not depend on the number of GPUs
-    if getattr(args, 'b200_device_paths', False):
+    device_paths = unit_paths is None and getattr(args, 'b200_device_paths', False)
+    if unit_paths is not None:
+        paths = list(unit_paths)
+    elif device_paths:
         # permutations drawn on the GPU (biom3_random_paths), one Philox seed per unit taken from torch's global generator
-        from . import engine as _engine
-        seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in units]
-        paths = [_engine.random_paths(bs, L, sd, args.device).cpu() for (_, _, bs), sd in zip(units, seeds)]
+        path_seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in units]
+        paths = [None] * len(units)
     else:
         paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for (_, _, bs) in units]
+    if unit_seeds is None and unit_noise is None:
+        unit_seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in units]
     for slot, uid in enumerate(mine):
         p, _, bs = units[uid]
         z = z_t[p].unsqueeze(0).repeat(bs, 1)
+        if device_paths:
+            from . import engine as _engine
+            paths[uid] = _engine.random_paths(bs, L, path_seeds[uid], args.device)
         states, _ = Stage3_sample_tools.batch_generate_denoised_sampled(
             args=args, model=model, extract_digit_samples=torch.zeros(bs, L),
-            extract_time=torch.zeros(bs).long(), extract_digit_label=z, sampling_path=paths[uid])
+            extract_time=torch.zeros(bs).long(), extract_digit_label=z, sampling_path=paths[uid],
+            noise=None if unit_noise is None else unit_noise[uid],
+            seed=None if unit_seeds is None else unit_seeds[uid], final_only=True)
         local[slot, :bs] = torch.from_numpy(states[-1][:, 0, :].astype(np.uint8)).to(args.device)
     allt = bdist.gather_unit_tokens(local, mine, len(units), rows).cpu().numpy()
     design_sequence_dict = {f'replica_{ii}': [] for ii in range(args.num_replicas)}
@@ -97,6 +111,8 @@ def parse_arguments(argv=None):
     parser.add_argument('--model_path', type=str, required=True)
     parser.add_argument('--input_path', type=str, required=True)
     parser.add_argument('--output_path', type=str, required=True)
+    parser.add_argument('--seed', type=int, default=None,
+                        help='torch.manual_seed before sampling (the reference never seeds; default: unseeded like it)')
     return parser.parse_args(argv)
 
 
@@ -109,6 +125,8 @@ def main(argv=None):
     config_args.device = f'cuda:{local}'
     embedding_dataset = torch.load(cli.input_path)
     model = prepare_model(args=cli, config_args=config_args)
+    if cli.seed is not None:
+        torch.manual_seed(cli.seed)            # every rank: paths and noise seeds are drawn for all units on every rank
     design_sequence_dict = batch_stage3_generate_sequences(args=config_args, model=model, z_t=embedding_dataset['z_c'])
     if rank == 0:
         torch.save(design_sequence_dict, cli.output_path)

@@ -48,11 +48,17 @@ void biom3_destroy(biom3_model* m);
 const char* biom3_last_error(void);
 
 /* Replaces model.load_state_dict() (run_ProteoScribe_sample.py:51).  `key` is the reference
- * state-dict key ("transformer.x_emb_NN.weight", ...); `data` is HOST fp32, `numel` elements.
- * biom3_finalize_weights() is strict: it fails if a key is missing or has the wrong size.  It casts
- * GEMM weights to bf16, stacks to_q/to_k/to_v, and precomputes the [L][depth][dim] time-conditioning
+ * state-dict key ("transformer.x_emb_NN.weight", ...); `data` points at the tensor's elements in HOST
+ * or DEVICE memory (the library finds out which), `dtype` is one of BIOM3_DTYPE_*, `shape[ndim]` the
+ * tensor's extents (row-major, contiguous).  biom3_finalize_weights() is strict: it fails if a key is
+ * missing, unexpected or has the wrong number of elements.  It casts GEMM weights to bf16, stacks
+ * to_q/to_k/to_v, folds the pre-norm LayerNorms, and precomputes the [L][depth][dim] time-conditioning
  * table (cond_diff_transformer_layer.py:152-154 depends on the step only). */
-int biom3_set_weight(biom3_model* m, const char* key, const float* data, int64_t numel);
+#define BIOM3_DTYPE_F32 0
+#define BIOM3_DTYPE_BF16 1
+#define BIOM3_DTYPE_F16 2
+#define BIOM3_DTYPE_F64 3
+int biom3_set_weight(biom3_model* m, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
 int biom3_finalize_weights(biom3_model* m);
 
 /* Arithmetic of the forward: 0 = bf16 operands, fp32 accumulate and fp32 residual stream (default; logits within
@@ -132,11 +138,24 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
 
 /* Replaces Facilitator.forward (Stage1_source/model.py:473-493; called at run_Facilitator_sample.py:79-83):
  * z_c = W1 . gelu_erf(W0 . z_t + b0) + b1 with weight_norm(dim=None) folded, W = g * V / ||V||_F.
- * z_t device fp32 [P][in_dim]; z_c device fp32 [P][out_dim] (out); weight_v / bias pointers are HOST fp32
- * (state-dict tensors main.0.weight_v [hid][in], main.0.weight_g (scalar), main.0.bias, main.3.*).
- * Synchronous (the stream is synchronised before returning). */
+ * create: weight_v / bias pointers are HOST fp32 (state-dict tensors main.0.weight_v [hid][in], main.0.weight_g
+ * (scalar), main.0.bias, main.3.*); the folded weights are uploaded once and live on the handle.
+ * forward: z_t device fp32 [P][in_dim] -> z_c device fp32 [P][out_dim], asynchronous on `stream`. */
+typedef struct biom3_facilitator_t biom3_facilitator_t;
+int biom3_facilitator_create(int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g, const float* b0,
+                             const float* w1_v, float w1_g, const float* b1, int device, biom3_facilitator_t** out);
+int biom3_facilitator_forward(biom3_facilitator_t* f, const float* z_t, int P, float* z_c, void* stream);
+void biom3_facilitator_destroy(biom3_facilitator_t* f);
+/* One-shot form (create + forward + synchronize + destroy) on the current device. */
 int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_dim, const float* w0_v, float w0_g,
                       const float* b0, const float* w1_v, float w1_g, const float* b1, float* z_c, void* stream);
+
+/* Test hook: the Exp(1) race noise biom3_decode() draws on the device when `noise` is NULL, for one step:
+ * out device fp32 [B*L][C], out[pos][c] = the draw consumed for class c at flat position pos = b * L + l at time
+ * index `step` under `seed` (Philox4x32-10 counter (pos, step, c / 4), inversion q = -log1p(-v); csrc/kernels.cuh).
+ * Feeding these values as explicit `noise` to the CPU oracle reproduces the device decode bit for bit
+ * (tests/test_gpu_parity.py); oracle/philox.py restates the stream independently. */
+int biom3_debug_noise(uint64_t seed, int step, int B, int L, int C, float* out, void* stream);
 
 /* Number of kernel launches one decode step issues (for bench.py's gpu_launches): the count of the most recently
  * captured step graph, or the full-row estimate before the first decode. */

@@ -26,21 +26,37 @@ import torch
 import torch.nn.functional as F
 
 
-def reference_noise_stream(seed: int, steps: int, B: int, L: int, C: int) -> torch.Tensor:
-    """Rebuild, as logical q[step, b*L + l, c], the Exp(1) draws the reference loop consumes from
-    torch's global CPU generator after ``torch.manual_seed(seed)`` (one ``.sample()`` per step).
+def global_generator_noise(steps: int, B: int, L: int, C: int) -> torch.Tensor:
+    """The next ``steps`` Exp(1) draws of the reference loop, taken from torch's global CPU generator in its CURRENT
+    state, as logical q[step, b*L + l, c] (one ``.sample()`` per step).
 
     For B > 1 ``probs.reshape(-1, C)`` inside ``OneHotCategorical.sample`` copies to a contiguous
     [B*L, C] tensor, so the stream fills q row-major.  For B == 1 the permuted [1, L, C] view
     reshapes WITHOUT a copy (strides (1, L)); ``empty_like`` keeps those strides and
     ``exponential_`` fills in memory order, so the stream fills q class-major: q[l, c] =
     stream[c*L + l].  (Probed on torch 2.11 CPU; pinned by tests/test_oracle_vs_reference.py.)"""
-    torch.manual_seed(seed)
     out = []
     for _ in range(steps):
         s = torch.empty(B * L * C).exponential_(1)
         out.append(s.reshape(C, L).t().contiguous() if B == 1 else s.reshape(B * L, C))
     return torch.stack(out)
+
+
+def reference_noise_stream(seed: int, steps: int, B: int, L: int, C: int) -> torch.Tensor:
+    """Rebuild the Exp(1) draws the reference loop consumes after ``torch.manual_seed(seed)``."""
+    torch.manual_seed(seed)
+    return global_generator_noise(steps, B, L, C)
+
+
+def race_margins(logits: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """Relative gap between the winner and the runner-up of the argmax(p / q) race at every position:
+    logits [B, C, L], q [B*L, C] -> [B, L].  A forward within tolerance eps of this one can only flip a token
+    where the margin is of order eps."""
+    B, C, L = logits.shape
+    p = F.softmax(logits, dim=1).permute(0, 2, 1)
+    p = p / p.sum(-1, keepdim=True)
+    top2 = (p.reshape(B * L, C) / q).topk(2, -1).values
+    return ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).reshape(B, L)
 
 
 def sample_tokens(logits: torch.Tensor, q: torch.Tensor) -> torch.Tensor:

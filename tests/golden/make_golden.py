@@ -240,16 +240,132 @@ def inpaint_case(mod, samp, helper):
     print('inpaint_b3', {k: getattr(v, 'shape', v) for k, v in out.items()})
 
 
+class _StopAfter(Exception):
+    pass
+
+
+def full_b64_case(mod, samp):
+    """BASELINE.json configs[1] at its own size: stage3_config.json shape, ONE reference batch of 64 sequences
+    (so the cross-sample unmask write couples 64 x 64 positions per step), LayerNorm affine parameters moved off
+    1 / 0.  The real sampler loop, three steps from the all-mask state (the loop is stopped by an exception raised at
+    the 4th forward call: everything recorded before it is the reference's own work) and its natural last three
+    steps (start = 1021 with a state that already holds 1021 tokens per row).  Per step the fixture keeps the state,
+    and for the 64 x 64 selected (sample, location) pairs the race margin of the reference's own draw; plus a
+    slice of the step-1 logits.  ~3 min of CPU."""
+    from oracle import sampler as osamp
+    args = synthetic.stage3_args()
+    L, C, B = args.diffusion_steps, args.num_classes, 64
+    sd = synthetic.random_state_dict(args, seed=51, perturb_norm=True)
+    model = mod.get_model(args, (32, 32), C)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    z_c = synthetic.synthetic_z_c(1, args.text_emb_dim, seed=52).repeat(B, 1)
+    path = synthetic.synthetic_paths(B, L, seed=53)
+    inv = torch.argsort(path, dim=1)                      # inv[b, t] = location sample b unmasks at step t
+    out = dict(weight_seed=np.int32(51), z_seed=np.int32(52), path_seed=np.int32(53), B=np.int32(B))
+    for tag, start, noise_seed in (('early', 0, 54), ('late', L - 3, 55)):
+        g = torch.Generator().manual_seed(56)
+        toks = torch.randint(1, C, (B, L), generator=g)
+        state0 = torch.where(path < start, toks, torch.zeros_like(toks)).float()
+        seen_x, seen_logits = [], []
+
+        class Recorder(torch.nn.Module):
+            def __init__(self, inner):
+                super().__init__()
+                self.inner = inner
+
+            def forward(self, x, t, y_c):
+                seen_x.append(x.detach().clone())
+                if len(seen_x) == 4:
+                    raise _StopAfter()
+                lg = self.inner(x=x, t=t, y_c=y_c)
+                seen_logits.append(lg.detach().clone())
+                return lg
+
+        torch.manual_seed(noise_seed)
+        final = None
+        try:
+            states, _ = samp.batch_generate_denoised_sampled(
+                args=args, model=Recorder(model).eval(), extract_digit_samples=state0.clone(),
+                extract_time=torch.full((B,), start).long(), extract_digit_label=z_c, sampling_path=path)
+            final = states[-1][:, 0]
+        except _StopAfter:
+            pass
+        T = 3
+        assert len(seen_logits) == T
+        snaps = [sx.numpy() for sx in seen_x[1:]]
+        if final is not None:
+            snaps.append(final)
+        traj = np.stack(snaps[:T]).astype(np.uint8)         # [3, B, L] state after each step
+        noise = osamp.reference_noise_stream(noise_seed, T, B, L, C)
+        margins = np.zeros((T, B, B), dtype=np.float32)
+        for s in range(T):
+            mg = osamp.race_margins(seen_logits[s], noise[s])
+            loc = inv[:, start + s]                         # [B] current location of every sample
+            margins[s] = mg[:, loc].numpy()                 # [b', b] = margin at (sample b', location of sample b)
+            # the recorded trajectory is what these logits + this noise give (the noise stream is the real one)
+            x_in = seen_x[s].clone()
+            tok = osamp.sample_tokens(seen_logits[s], noise[s])
+            x_in[:, loc] = tok[:, loc]
+            assert np.array_equal(x_in.numpy(), traj[s]), (tag, s)
+        out.update({f'{tag}_start': np.int32(start), f'{tag}_noise_seed': np.int32(noise_seed),
+                    f'{tag}_state0': state0.numpy().astype(np.uint8), f'{tag}_traj': traj,
+                    f'{tag}_margins': margins.astype(np.float16)})
+        if tag == 'early':
+            out['early_logits1'] = seen_logits[1][:4, :, ::4].numpy().astype(np.float32)    # step 1, samples 0-3, every 4th position
+        print('full_b64', tag, 'traj', traj.shape, 'min margin', float(margins.min()))
+    np.savez_compressed(os.path.join(HERE, 'full_b64_g64.npz'), **out)
+
+
+def cli_units_case(mod):
+    """a1: the REAL batch_stage3_generate_sequences (run_ProteoScribe_sample.py:60-126; its unused imports
+    pytorch_lightning and Stage3_source.PL_wrapper are stood in) for 2 prompts x 3 replicas in batches of 2 = four
+    units of 2, 1, 2, 1 sequences, at the GPU-testable small shape.  Everything random comes from torch's global CPU
+    generator, seeded once: per unit first the paths (randperm), then 256 steps of Exp(1) draws."""
+    import json
+    for name in ('pytorch_lightning', 'Stage3_source.PL_wrapper'):
+        if name not in sys.modules:
+            sys.modules[name] = mock.MagicMock(name=name)
+    import run_ProteoScribe_sample as ref_cli
+    assert ref_cli.__file__.startswith(REF)
+    over = CASES['gpu_small_b3'][0]
+    args = synthetic.stage3_args(**over, num_replicas=3, batch_size_sample=2)
+    args.device = 'cpu'
+    C = args.num_classes
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    model = mod.get_model(args, (args.image_size, args.image_size), C)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    z_c = synthetic.synthetic_z_c(2, args.text_emb_dim, seed=61)
+    import contextlib
+    import io
+    torch.manual_seed(62)
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = ref_cli.batch_stage3_generate_sequences(args=args, model=model, z_t=z_c)
+    np.savez_compressed(os.path.join(HERE, 'cli_units.npz'), overrides=np.array(repr(over)), weight_seed=np.int32(11),
+                        z_seed=np.int32(61), global_seed=np.int32(62), num_replicas=np.int32(3), batch_size_sample=np.int32(2),
+                        result=np.array(json.dumps(d)))
+    print('cli_units', {k: [len(s) for s in v] for k, v in d.items()})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     mod, samp, helper, ani = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == 'inpaint':
         inpaint_case(mod, samp, helper)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'full_b64':
+        full_b64_case(mod, samp)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'cli_units':
+        cli_units_case(mod)
+        return
     for name in CASES:
         run_case(mod, samp, name)
     inpaint_case(mod, samp, helper)
+    cli_units_case(mod)
     full_config_forward(mod)
+    full_b64_case(mod, samp)
     facilitator_case()
     # key schema of the real model at the stage3_config.json shape
     import json

@@ -402,10 +402,12 @@ def test_cli_flow_facilitator_to_sequences_end_to_end():
     # replay the first unit (prompt 0, replicas 0-1) by hand with the same RNG draws: same strings
     torch.manual_seed(1234)
     L = args.diffusion_steps
-    paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for bs in (2, 1, 2, 1)]     # every unit's paths are drawn first
+    paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for bs in (2, 1, 2, 1)]     # every unit's paths are drawn first,
+    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(4)]                   # then every unit's noise seed
     states, times = samp.batch_generate_denoised_sampled(args=args, model=model, extract_digit_samples=torch.zeros(2, L),
                                                          extract_time=torch.zeros(2).long(),
-                                                         extract_digit_label=z_c[0].unsqueeze(0).repeat(2, 1), sampling_path=paths[0])
+                                                         extract_digit_label=z_c[0].unsqueeze(0).repeat(2, 1), sampling_path=paths[0],
+                                                         seed=seeds[0])
     assert len(states) == L and len(times) == L
     for i in range(2):
         assert cli.clean_sequence(synthetic.TOKENS, states[-1][i, 0]) == d1[f'replica_{i}'][0]
@@ -682,3 +684,293 @@ def test_gemm_split8_residual_epilogue(bn, pair):
     # the kernel's encoding of its own result is the canonical one
     hi3, lo3 = _lo8_encode(got)
     assert torch.equal(hi3, hi2)
+
+
+# ---------------------------------------------------------------- the on-device noise (the path bench.py times) under the oracle
+def test_device_noise_matches_oracle_philox():
+    """biom3_debug_noise exports the Exp(1) draws of the decode's own Philox path; oracle/philox.py restates them on the CPU
+    (integer part exact by construction; the float32 -log1p(-v) may differ from libm in the last place)."""
+    from biom3_b200 import engine
+    from oracle import philox
+    B, L, C = 3, 256, 29
+    for seed, step in ((123, 0), (2 ** 40 + 17, 255), (0, 7)):
+        got = engine.device_noise(seed, step, B, L, C, 'cuda').cpu().numpy()
+        ref = philox.exp1_stream(seed, step, B * L, C)
+        assert got.shape == ref.shape and (got > 0).all() and np.isfinite(got).all()
+        ulp = np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 2, ulp.max()
+        assert (ulp == 0).mean() > 0.9            # CUDA log1pf is accurate to 1 ulp, the oracle rounds correctly
+
+
+def test_device_noise_distribution_ks_and_token_chi_square():
+    """The stream the timed path consumes is Exp(1) (KS), and tokens drawn with it by the device sampler follow softmax
+    (chi-square on a peaked and a flat row)."""
+    from scipy import stats
+    from biom3_b200 import engine
+    C, n = 29, 1 << 16
+    q = engine.device_noise(99, 5, 64, 1024, C, 'cuda')
+    qs = q.double().cpu().numpy().ravel()
+    assert stats.kstest(qs[:: 7], 'expon').pvalue > 1e-3
+    assert abs(qs.mean() - 1.0) < 2e-3 and abs((qs < 1e-3).mean() / 1e-3 - 1.0) < 0.1
+    g = torch.Generator().manual_seed(1)
+    for scale in (0.5, 3.0):
+        logit = torch.randn(C, generator=g) * scale
+        logits = logit.view(1, C, 1).expand(64, C, 1024).contiguous().cuda()
+        tok = engine.sample_all(logits, q).view(-1).cpu().numpy()
+        p = torch.softmax(logit.double(), 0).numpy()
+        counts = np.bincount(tok, minlength=C).astype(np.float64)
+        keep = p * n >= 5
+        chi2 = ((counts[keep] - p[keep] * n) ** 2 / (p[keep] * n)).sum()
+        assert stats.chi2.sf(chi2, int(keep.sum()) - 1) > 1e-3, (scale, chi2)
+
+
+def test_decode_with_device_noise_equals_oracle_fed_the_exported_stream():
+    """The benchmarked configuration (noise=NULL, Philox seed) under the oracle: the device decode drawing its own noise
+    == the device decode fed the exported stream as explicit noise (strictly) == the CPU oracle fed that stream."""
+    from biom3_b200 import engine
+    from oracle import sampler as osamp
+    B, L, C, seed = 3, 256, 29, 20261019
+    args, sd, eng, orc = make(SMALL, B, seed=21)
+    z = synthetic.synthetic_z_c(1, 64, seed=4).repeat(B, 1)
+    path = synthetic.synthetic_paths(B, L, seed=6)
+    own, traj_own = eng.decode(z.cuda(), path.cuda(), seed=seed, want_traj=True)
+    noise = torch.stack([engine.device_noise(seed, t, B, L, C, 'cuda') for t in range(L)])
+    fed, traj_fed = eng.decode(z.cuda(), path.cuda(), noise=noise, want_traj=True)
+    assert torch.equal(traj_own, traj_fed) and torch.equal(own, fed)
+    margins = []
+    states, _ = osamp.decode(orc, torch.zeros(B, L), torch.zeros(B).long(), z, path, noise.cpu(), L,
+                             logits_hook=lambda i, lg: margins.append(osamp.race_margins(lg, noise[i].cpu()).numpy()))
+    _assert_traj(traj_own.cpu().numpy().astype(np.int64), np.stack(states)[:, :, 0], margins)
+    # resumed decode: the stream is indexed by the absolute time index, not by the call's first step
+    part, _ = eng.decode(z.cuda(), path.cuda(), state0=traj_own[99].long(), start_step=100, seed=seed)
+    assert torch.equal(part, own)
+
+
+# ---------------------------------------------------------------- BASELINE configs[1] at its own size
+def _full_b64():
+    z = np.load(os.path.join(GOLDEN, 'full_b64_g64.npz'))
+    args = synthetic.stage3_args()
+    sd = synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True)
+    B = int(z['B'])
+    y = synthetic.synthetic_z_c(1, 512, seed=int(z['z_seed'])).repeat(B, 1)
+    path = synthetic.synthetic_paths(B, 1024, seed=int(z['path_seed']))
+    return z, args, sd, B, y, path
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_full_shape_b64_g64_vs_reference_fixture(precision):
+    """stage3_config.json shape, ONE reference batch of 64 (64 x 64 unmask writes per step, 4096-row last-layer
+    compaction), LayerNorm gamma / beta off their defaults (the folded LayerNorm at d = 512), against the REAL reference
+    loop (tests/golden/make_golden.py full_b64): its first three steps and its last three.  Teacher-forced per step (the
+    device starts every step from the reference's state), so one flipped draw cannot cascade: fp32 mode must be
+    identical; bf16 mode may differ only at draws whose reference race margin is below the logits tolerance."""
+    from biom3_b200.engine import Engine
+    from oracle import sampler as osamp
+    z, args, sd, B, y, path = _full_b64()
+    L, C = 1024, 29
+    eng = Engine(args, sd, torch.device('cuda'), B, precision=precision)
+    inv = torch.argsort(path, dim=1).numpy()
+    yc, pc = y.cuda(), path.cuda()
+    for tag in ('early', 'late'):
+        start = int(z[f'{tag}_start'])
+        ref = z[f'{tag}_traj'].astype(np.int64)                      # [3, B, L]
+        noise = osamp.reference_noise_stream(int(z[f'{tag}_noise_seed']), 3, B, L, C).cuda()
+        prev = z[f'{tag}_state0'].astype(np.int64)
+        flips = 0
+        for s in range(3):
+            tok, _ = eng.decode(yc, pc, state0=torch.from_numpy(prev).cuda(), start_step=start + s, num_steps=1,
+                                noise=noise[s:s + 1].contiguous())
+            got = tok.cpu().numpy()
+            neq = np.argwhere(got != ref[s])
+            for b, l in neq:
+                src = np.nonzero(inv[:, start + s] == l)[0]          # the write came from sample(s) whose location is l
+                assert len(src) > 0, f'{tag} step {s}: position ({b}, {l}) changed but is nobody\'s current location'
+                m = float(z[f'{tag}_margins'][s, b, src[0]])
+                assert precision == 'bf16' and m < LOGIT_TOL, \
+                    f'{tag} step {s} ({precision}): token at ({b}, {l}) is {got[b, l]}, reference {ref[s, b, l]}, margin {m}'
+            flips += len(neq)
+            prev = ref[s]
+        assert flips <= 12, flips                                     # 12288 draws per case; expected ~1e-3 of them near a tie
+    if precision == 'fp32':
+        # free running from the all-mask state: identical to the reference, three steps
+        noise = osamp.reference_noise_stream(int(z['early_noise_seed']), 3, B, L, C).cuda()
+        _, traj = eng.decode(yc, pc, num_steps=3, noise=noise, want_traj=True)
+        assert np.array_equal(traj.cpu().numpy(), z['early_traj'])
+
+
+@pytest.mark.parametrize('precision,tol', [('bf16', LOGIT_TOL), ('fp32', FP32_TOL)])
+def test_forward_full_shape_b64_perturbed_layernorm(precision, tol):
+    """Logits of the real reference forward at B = 64 on the state after its first step (t = 1), perturbed LayerNorms."""
+    from biom3_b200.engine import Engine
+    z, args, sd, B, y, path = _full_b64()
+    eng = Engine(args, sd, torch.device('cuda'), B, precision=precision)
+    x = torch.from_numpy(z['early_traj'][0].astype(np.int64)).cuda()
+    got = eng.forward(x, torch.full((B,), 1).cuda(), y.cuda())[:4, :, ::4].cpu()
+    ref = torch.from_numpy(z['early_logits1'])
+    assert rel_err(got, ref) < tol
+    # per element, relative to the probability itself (rel_err above is max-abs over max-abs)
+    pg, pr = torch.softmax(got.double(), 1), torch.softmax(ref.double(), 1)
+    assert ((pg - pr).abs() / pr).max().item() < (3e-2 if precision == 'bf16' else 3e-4)
+
+
+# ---------------------------------------------------------------- a1 / f2: the two CLIs against real-reference fixtures
+def test_cli_units_vs_reference_fixture():
+    """batch_stage3_generate_sequences against the REAL reference function (fixture cli_units.npz): 2 prompts x 3 replicas
+    in batches of 2 -> units of 2, 1, 2, 1 sequences.  The reference draws, per unit, the paths and then 256 steps of noise
+    from one seeded CPU generator; the test replays those draws and hands them to the CLI through its parity hooks."""
+    import json
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+    from oracle import sampler as osamp
+    z = np.load(os.path.join(GOLDEN, 'cli_units.npz'))
+    over = ast.literal_eval(str(z['overrides']))
+    args = synthetic.stage3_args(**over, num_replicas=int(z['num_replicas']), batch_size_sample=int(z['batch_size_sample']))
+    args.device = 'cuda'
+    model = mod.get_model(args, (32, 32), 29)
+    model.load_state_dict(synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True))
+    model.eval()
+    z_c = synthetic.synthetic_z_c(2, args.text_emb_dim, seed=int(z['z_seed']))
+    L, C = args.diffusion_steps, 29
+    torch.manual_seed(int(z['global_seed']))
+    paths, noise = [], []
+    for bs in (2, 1, 2, 1):
+        paths.append(torch.stack([torch.randperm(L) for _ in range(bs)]))
+        noise.append(osamp.global_generator_noise(L, bs, L, C))
+    got = cli.batch_stage3_generate_sequences(args, model, z_c, unit_paths=paths, unit_noise=noise)
+    assert got == json.loads(str(z['result']))
+
+
+def test_run_facilitator_sample_pt_round_trip(tmp_path):
+    """run_Facilitator_sample.py:76-121 as a drop-in: config JSON + state-dict file + {'z_t': ...} .pt in, the same dict
+    plus 'z_c' out; z_c equals the REAL Facilitator's (fixture), and the file feeds run_ProteoScribe_sample's loader."""
+    import json
+    from biom3_b200 import run_Facilitator_sample as fcli
+    z = np.load(os.path.join(GOLDEN, 'facilitator_p16.npz'))
+    (tmp_path / 'stage2_config.json').write_text(json.dumps(dict(emb_dim=512, hid_dim=1024, dropout=0.0, seed=42)))
+    torch.save(synthetic.facilitator_state_dict(512, 1024, seed=int(z['weight_seed'])), tmp_path / 'fac.bin')
+    torch.save({'z_t': torch.from_numpy(z['z_t']), 'z_p': torch.zeros(16, 512), 'note': 'kept'}, tmp_path / 'in.pt')
+    out = fcli.main(['--json_path', str(tmp_path / 'stage2_config.json'), '--model_path', str(tmp_path / 'fac.bin'),
+                     '--input_data_path', str(tmp_path / 'in.pt'), '--output_data_path', str(tmp_path / 'out.pt')])
+    disk = torch.load(tmp_path / 'out.pt')
+    assert sorted(disk) == ['note', 'z_c', 'z_p', 'z_t'] and disk['note'] == 'kept'
+    assert disk['z_c'].device.type == 'cpu' and disk['z_c'].dtype == torch.float32 and disk['z_c'].shape == (16, 512)
+    assert torch.equal(disk['z_c'], out['z_c']) and torch.equal(disk['z_t'], torch.from_numpy(z['z_t']))
+    assert rel_err(disk['z_c'], torch.from_numpy(z['z_c'])) < 1e-4
+
+
+def test_facilitator_handle_is_cached_and_follows_weight_updates():
+    from biom3_b200.Stage1_source.model import Facilitator
+    model = Facilitator(100, 72, 100, dropout=0.0)               # dims that are not multiples of 16 (sgemm K tail)
+    sd = synthetic.facilitator_state_dict(100, 72, seed=5)
+    model.load_state_dict(sd)
+    x = torch.randn(5, 100, generator=torch.Generator().manual_seed(1))
+
+    def ref(sd, x):
+        w0 = sd['main.0.weight_g'] * sd['main.0.weight_v'] / sd['main.0.weight_v'].norm()
+        w1 = sd['main.3.weight_g'] * sd['main.3.weight_v'] / sd['main.3.weight_v'].norm()
+        return torch.nn.functional.gelu(x @ w0.t() + sd['main.0.bias']) @ w1.t() + sd['main.3.bias']
+
+    y1 = model(x.cuda()).cpu()
+    h1 = model._handle.value
+    assert rel_err(y1, ref(sd, x)) < 1e-5
+    assert torch.equal(model(x.cuda()).cpu(), y1) and model._handle.value == h1          # second call: same handle
+    sd2 = synthetic.facilitator_state_dict(100, 72, seed=6)
+    model.load_state_dict(sd2)
+    y2 = model(x).cpu()                                                                   # host input -> host output
+    assert rel_err(y2, ref(sd2, x)) < 1e-5 and not torch.equal(y1, y2)
+
+
+# ---------------------------------------------------------------- boundary details
+def test_weights_from_device_memory_and_other_dtypes():
+    """biom3_set_weight takes host or device pointers and fp32 / fp64 / bf16 / fp16 storage."""
+    from biom3_b200.engine import Engine
+    B = 2
+    args = synthetic.stage3_args(**SMALL)
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 29, (B, 256), generator=g).cuda()
+    t = torch.tensor([5, 200]).cuda()
+    zc = synthetic.synthetic_z_c(B, 64, seed=4).cuda()
+    base = Engine(args, sd, torch.device('cuda'), B).forward(x, t, zc)
+    dev = Engine(args, {k: v.cuda() for k, v in sd.items()}, torch.device('cuda'), B).forward(x, t, zc)
+    f64 = Engine(args, {k: v.double() for k, v in sd.items()}, torch.device('cuda'), B).forward(x, t, zc)
+    assert torch.equal(base, dev) and torch.equal(base, f64)
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    b16 = Engine(args, {k: v.cuda() for k, v in sd16.items()}, torch.device('cuda'), B).forward(x, t, zc)
+    same = Engine(args, {k: v.float() for k, v in sd16.items()}, torch.device('cuda'), B).forward(x, t, zc)
+    assert torch.equal(b16, same)
+    bad = dict(sd)
+    bad['transformer.out.bias'] = torch.zeros(30)
+    with pytest.raises(RuntimeError, match=r'size mismatch for transformer.out.bias.*\[30\]'):
+        Engine(args, bad, torch.device('cuda'), B)
+
+
+@pytest.mark.parametrize('offset', [4.0, 16.0])
+def test_folded_layernorm_with_a_common_row_offset(offset):
+    """The folded LayerNorm feeds the GEMM bf16(u) of the raw residual stream; mean and rstd are applied afterwards, so
+    the rounding error of u scales with |row mean| / std.  A residual stream with a common offset of 4 std
+    still meets the bf16 logits bound; DESIGN.md states the limit."""
+    B = 2
+    args = synthetic.stage3_args(**SMALL)
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    sd['transformer.x_emb_NN.weight'] = sd['transformer.x_emb_NN.weight'] + offset * 1.7     # std of the embedded row ~ 1.7
+    from biom3_b200.engine import Engine
+    from oracle.model import OracleModel
+    eng, orc = Engine(args, sd, torch.device('cuda'), B), OracleModel(args, sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 29, (B, 256), generator=g)
+    t = torch.tensor([5, 200])
+    zc = synthetic.synthetic_z_c(B, 64, seed=4)
+    err = rel_err(eng.forward(x.cuda(), t.cuda(), zc.cuda()).cpu(), orc(x, t, zc))
+    print(f'folded LayerNorm, row offset {offset} std: logits rel err {err:.2e}')
+    assert err < (LOGIT_TOL if offset <= 4.0 else 4 * LOGIT_TOL)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_engines_on_two_devices_in_one_process():
+    """The kernel attribute opt-ins (dynamic shared memory) are per device: a second engine on another GPU of the same
+    process must work."""
+    from biom3_b200.engine import Engine
+    B = 2
+    args = synthetic.stage3_args(**SMALL)
+    sd = synthetic.random_state_dict(args, seed=11, perturb_norm=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 29, (B, 256), generator=g)
+    t = torch.tensor([5, 200])
+    zc = synthetic.synthetic_z_c(B, 64, seed=4)
+    outs = []
+    for d in (0, 1):
+        dev = torch.device('cuda', d)
+        eng = Engine(args, sd, dev, B)
+        outs.append(eng.forward(x.to(dev), t.to(dev), zc.to(dev)).cpu())
+        path = synthetic.synthetic_paths(B, 256, seed=8).to(dev)
+        tok, _ = eng.decode(zc.to(dev), path, seed=5)
+        outs.append(tok.cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_cli_world_2_equals_world_1(tmp_path):
+    """the same units give the same tokens whatever the number of GPUs.  The CLI under torchrun with two
+    ranks (units round-robin, NCCL all-gather of the token ids) against the same CLI in this process."""
+    import json
+    import subprocess
+    import sys
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    cfg = vars(synthetic.stage3_args(**dict(SMALL, text_emb_dim=64), num_replicas=5, batch_size_sample=2))
+    (tmp_path / 'cfg.json').write_text(json.dumps(cfg))
+    args = synthetic.stage3_args(**cfg)
+    torch.save(synthetic.random_state_dict(args, seed=11, perturb_norm=True), tmp_path / 'model.bin')
+    torch.save({'z_c': synthetic.synthetic_z_c(3, 64, seed=4)}, tmp_path / 'z.pt')
+    common = ['--json_path', str(tmp_path / 'cfg.json'), '--model_path', str(tmp_path / 'model.bin'),
+              '--input_path', str(tmp_path / 'z.pt'), '--seed', '321']
+    one = cli.main(common + ['--output_path', str(tmp_path / 'one.pt')])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29577', '-m', 'biom3_b200.run_ProteoScribe_sample']
+                         + common + ['--output_path', str(tmp_path / 'two.pt')], cwd=root, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    two = torch.load(tmp_path / 'two.pt')
+    assert sorted(one) == [f'replica_{i}' for i in range(5)] and all(len(v) == 3 for v in one.values())
+    assert one == two

@@ -79,3 +79,53 @@ def test_schema_matches_reference_count():
 def test_convert_num_to_char_fixture():
     with open(os.path.join(GOLDEN, 'convert_num_to_char.txt')) as f:
         assert f.read() == ''.join(synthetic.TOKENS)
+
+
+def test_full_b64_fixture_forward_and_sampler_step():
+    """BASELINE configs[1] fixture (stage3 shape, one batch of 64, perturbed LayerNorms, the REAL loop): the oracle forward
+    on four of its sequences reproduces the recorded step-1 logits (the forward has no cross-sample op), and the
+    fixture's own bookkeeping holds: a step changes a row only at the 64 current locations of its batch."""
+    z = np.load(os.path.join(GOLDEN, 'full_b64_g64.npz'))
+    args = synthetic.stage3_args()
+    sd = synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True)
+    B, L = int(z['B']), 1024
+    y = synthetic.synthetic_z_c(1, 512, seed=int(z['z_seed'])).repeat(4, 1)
+    x = torch.from_numpy(z['early_traj'][0, :4].astype(np.int64))
+    logits = OracleModel(args, sd)(x, torch.full((4,), 1), y)[:, :, ::4]
+    ref = torch.from_numpy(z['early_logits1'])
+    assert (logits - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    path = synthetic.synthetic_paths(B, L, seed=int(z['path_seed']))
+    inv = torch.argsort(path, dim=1).numpy()
+    for tag in ('early', 'late'):
+        start = int(z[f'{tag}_start'])
+        prev = z[f'{tag}_state0']
+        assert z[f'{tag}_margins'].shape == (3, B, B) and float(z[f'{tag}_margins'].min()) >= 0
+        for s in range(3):
+            cur = z[f'{tag}_traj'][s]
+            changed = np.nonzero((cur != prev).any(0))[0]
+            assert set(changed.tolist()) <= set(inv[:, start + s].tolist())
+            prev = cur
+
+
+def test_cli_units_fixture_replays_through_the_oracle():
+    """a1 fixture: the REAL batch_stage3_generate_sequences result is what the oracle decodes when it is fed the same
+    per-unit draws of the seeded global generator (paths first, then the unit's noise)."""
+    import json
+    z = np.load(os.path.join(GOLDEN, 'cli_units.npz'))
+    over = ast.literal_eval(str(z['overrides']))
+    args = synthetic.stage3_args(**over)
+    sd = synthetic.random_state_dict(args, seed=int(z['weight_seed']), perturb_norm=True)
+    model = OracleModel(args, sd)
+    z_c = synthetic.synthetic_z_c(2, args.text_emb_dim, seed=int(z['z_seed']))
+    L, C = args.diffusion_steps, args.num_classes
+    want = json.loads(str(z['result']))
+    torch.manual_seed(int(z['global_seed']))
+    for p in range(2):
+        for start, bs in ((0, 2), (2, 1)):
+            path = torch.stack([torch.randperm(L) for _ in range(bs)])
+            noise = osamp.global_generator_noise(L, bs, L, C)
+            states, _ = osamp.decode(model, torch.zeros(bs, L), torch.zeros(bs).long(), z_c[p].repeat(bs, 1), path, noise, L)
+            for i in range(bs):
+                s = ''.join(synthetic.TOKENS[t] for t in states[-1][i, 0])
+                s = s.replace('<START>', '').replace('<END>', '').replace('<PAD>', '')
+                assert s == want[f'replica_{start + i}'][p]
