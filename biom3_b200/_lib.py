@@ -14,7 +14,7 @@ SYMBOLS = [
     'biom3_create', 'biom3_destroy', 'biom3_last_error', 'biom3_set_weight', 'biom3_finalize_weights',
     'biom3_forward', 'biom3_decode', 'biom3_sample_all', 'biom3_unmask', 'biom3_gemm_test',
     'biom3_profile_step', 'biom3_launches_per_step', 'biom3_debug_copy', 'biom3_facilitator', 'biom3_attention_test',
-    'biom3_set_precision', 'biom3_random_paths', 'biom3_debug_noise',
+    'biom3_set_precision', 'biom3_random_paths', 'biom3_debug_noise', 'biom3_debug_trace',
     'biom3_facilitator_create', 'biom3_facilitator_forward', 'biom3_facilitator_destroy',
 ]
 
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     lib.biom3_random_paths.restype = i32
     lib.biom3_debug_noise.argtypes = [u64, i32, i32, i32, i32, vp, vp]
     lib.biom3_debug_noise.restype = i32
+    lib.biom3_debug_trace.argtypes = [vp, i64]
+    lib.biom3_debug_trace.restype = i32
     lib.biom3_facilitator_create.argtypes = [i32, i32, i32, vp, C.c_float, vp, vp, C.c_float, vp, i32, C.POINTER(vp)]
     lib.biom3_facilitator_create.restype = i32
     lib.biom3_facilitator_forward.argtypes = [vp, vp, i32, vp, vp]

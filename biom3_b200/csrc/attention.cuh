@@ -403,6 +403,272 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Linear attention, one CLUSTER of CL CTAs per (global head, sample) (round 2).  Same arithmetic as above; the sequence
+// is split over CL x 4 warps instead of 4, so a (b, h) pair is CL x more CTAs in flight (B = 64: 2048 CTAs at CL = 4
+// instead of 512) and every warp's dependent chain (stream k / v -> merge -> stream q) is CL x shorter: the kernel is
+// latency bound, not byte bound (round 1: 0.47 of the HBM rate at 57 % issue utilisation).
+//   phase A   each warp: exp(k - reference)^T v over its L / (4 CL) rows (mma.sync, lazy column reference)
+//   merge 1   the CTA's four partial (max, denominator, ctx) sets -> one fp32 set in its own shared memory
+//   merge 2   cluster barrier; every CTA reads the CL sets through distributed shared memory -> ctx^T bf16 (q scale folded)
+//   phase B   softmax(q) ctx for its own rows
+// CL is the cluster size of the launch (1, 2, 4 or 8; L % (128 CL) == 0).
+// ------------------------------------------------------------------------------------------------
+constexpr int LINC_PART_FLOATS = DH * DH + 2 * DH;                       // ctx [32][32], max [32], denominator [32]
+constexpr int LINC_SMEM_BYTES = 4 * LIN_WARP_BYTES + LINC_PART_FLOATS * 4 + DH * 64;   // warp partials alias the stage buffers
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  float v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.f32 %0, [ra];\n\t}"
+      : "=f"(v)
+      : "r"(local_addr), "r"(rank)
+      : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __launch_bounds__(128)
+linear_attention_cl_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
+                           int NL, float q_scale, int reverse) {
+  ptx::pdl_sync();
+  const int CL = int(cluster_nctarank()), crank = int(ptx::cluster_ctarank());
+  const int h = NL + int(blockIdx.x) / CL, b = reverse ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
+  const size_t head_stride = size_t(L) * DH;
+  const size_t plane = size_t(B) * H * head_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int rows_per_warp = L / (4 * CL);
+  const int nchunks = rows_per_warp / LIN_CH;
+  const int row_first = (crank * 4 + warp) * rows_per_warp;               // first sequence position of this warp
+  const __nv_bfloat16* qg = qkv + (size_t(b) * H + h) * head_stride + size_t(row_first) * DH;
+  const __nv_bfloat16* kg = qg + plane;
+  const __nv_bfloat16* vg = kg + plane;
+
+  extern __shared__ __align__(128) uint8_t linc_smem[];
+  const uint32_t stage0 = ptx::smem_u32(linc_smem) + warp * LIN_WARP_BYTES;
+  float* pctx = reinterpret_cast<float*>(linc_smem);                       // [4][32][32] + [4][32] + [4][32]: aliases the stages (17 KB of 32)
+  float* pmax = pctx + 4 * DH * DH;
+  float* pden = pmax + 4 * DH;
+  float* part = reinterpret_cast<float*>(linc_smem + 4 * LIN_WARP_BYTES);  // this CTA's merged set: ctx, max, denominator
+  uint8_t* ctxT = reinterpret_cast<uint8_t*>(part + LINC_PART_FLOATS);     // [32 e][32 d] bf16, swizzled rows
+
+  // ---------------------------------------------------------------- phase A
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+  float mrun[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+  float den[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+
+  lin_load_chunk(stage0, kg, lane);
+  lin_load_chunk(stage0 + LIN_CH * 64, vg, lane);
+  ptx::cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
+    if (c + 1 < nchunks) {
+      const uint32_t nxt = stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES;
+      lin_load_chunk(nxt, kg + size_t(c + 1) * LIN_CH * DH, lane);
+      lin_load_chunk(nxt + LIN_CH * 64, vg + size_t(c + 1) * LIN_CH * DH, lane);
+      ptx::cp_async_commit();
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
+    }
+    __syncwarp();
+    const uint32_t sk = cur, sv = cur + LIN_CH * 64;
+    uint32_t kr[2][2][4];                          // [k-step][m-tile(d)][a0..a3], raw k as A^T fragments
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+        ptx::ldmatrix_x4_trans(sk + swz(ks * 16 + (lane & 7) + 8 * (lane >> 4), 2 * mt + ((lane >> 3) & 1)),
+                               kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float cm = -INFINITY;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const float2 x0 = bf2_to_f2(kr[ks][mt][hf]), x1 = bf2_to_f2(kr[ks][mt][hf + 2]);
+          cm = fmaxf(cm, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
+        }
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        if (cm > mrun[mt][hf] + LIN_LAZY) {
+          const float f = __expf(mrun[mt][hf] - cm);       // 0 on the first chunk
+          mrun[mt][hf] = cm;
+          den[mt][hf] *= f;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            acc[mt][nt][2 * hf] *= f;
+            acc[mt][nt][2 * hf + 1] *= f;
+          }
+        }
+        const float ml2 = mrun[mt][hf] * LOG2E;
+        float dsum = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            const float2 x = bf2_to_f2(kr[ks][mt][hf + 2 * q2]);
+            const float e0 = fast_ex2(fmaf(x.x, LOG2E, -ml2)), e1 = fast_ex2(fmaf(x.y, LOG2E, -ml2));
+            dsum += e0 + e1;
+            kr[ks][mt][hf + 2 * q2] = ptx::pack_bf16x2(e0, e1);
+          }
+        den[mt][hf] += dsum;
+      }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int ep = 0; ep < 2; ++ep) {
+        uint32_t v0, v1, v2, v3;
+        ptx::ldmatrix_x4_trans(sv + swz(ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4)), v0, v1, v2, v3);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          ptx::mma_bf16_16816(acc[mt][2 * ep], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v0, v1);
+          ptx::mma_bf16_16816(acc[mt][2 * ep + 1], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v2, v3);
+        }
+      }
+    __syncwarp();
+  }
+  // q chunk 0 can start now: it lands in stage 1 of this warp's buffer, beyond the 17 KB the warp partials alias
+  // (the partials occupy the first 17 KB of the 32 KB of stage space = warps 0, 1 and 256 bytes of warp 2: so only
+  // warp 3 may prefetch early; the others wait for the merge)
+  __syncthreads();                                 // every warp is done reading its stages before the partials overwrite them
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float dn = den[mt][hf];
+      dn += __shfl_xor_sync(0xffffffffu, dn, 1);
+      dn += __shfl_xor_sync(0xffffffffu, dn, 2);
+      const int d = 16 * mt + 8 * hf + g;
+      if (t == 0) {
+        pmax[warp * DH + d] = mrun[mt][hf];
+        pden[warp * DH + d] = dn;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* dst = pctx + (size_t(warp) * DH + d) * DH + 8 * nt + 2 * t;
+        dst[0] = acc[mt][nt][2 * hf];
+        dst[1] = acc[mt][nt][2 * hf + 1];
+      }
+    }
+  __syncthreads();
+  // ---------------------------------------------------------------- merge 1: four warps -> this CTA's set
+  for (int idx = threadIdx.x; idx < DH * DH; idx += 128) {
+    const int d = idx >> 5, e = idx & 31;
+    const float m0 = pmax[d], m1 = pmax[DH + d], m2 = pmax[2 * DH + d], m3 = pmax[3 * DH + d];
+    const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    const float f0 = __expf(m0 - mm), f1 = __expf(m1 - mm), f2 = __expf(m2 - mm), f3 = __expf(m3 - mm);
+    part[idx] = pctx[(0 * DH + d) * DH + e] * f0 + pctx[(1 * DH + d) * DH + e] * f1 +
+                pctx[(2 * DH + d) * DH + e] * f2 + pctx[(3 * DH + d) * DH + e] * f3;
+    if (e == 0) {
+      part[DH * DH + d] = mm;
+      part[DH * DH + DH + d] = pden[d] * f0 + pden[DH + d] * f1 + pden[2 * DH + d] * f2 + pden[3 * DH + d] * f3;
+    }
+  }
+  // ---------------------------------------------------------------- merge 2: CL CTAs -> ctx^T (bf16), q scale folded in
+  ptx::cluster_sync_all();                         // also a CTA barrier: the stage buffers are free for q from here on
+  lin_load_chunk(stage0, qg, lane);
+  ptx::cp_async_commit();
+  const uint32_t part_addr = ptx::smem_u32(part);
+  for (int idx = threadIdx.x; idx < DH * DH; idx += 128) {
+    const int d = idx >> 5, e = idx & 31;
+    float mm = -INFINITY;
+    for (int r = 0; r < CL; ++r) mm = fmaxf(mm, ld_dsmem_f32(part_addr + (DH * DH + d) * 4, r));
+    float num = 0.f, dn = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float f = __expf(ld_dsmem_f32(part_addr + (DH * DH + d) * 4, r) - mm);
+      num = fmaf(ld_dsmem_f32(part_addr + idx * 4, r), f, num);
+      dn = fmaf(ld_dsmem_f32(part_addr + (DH * DH + DH + d) * 4, r), f, dn);
+    }
+    *reinterpret_cast<__nv_bfloat16*>(ctxT + swz(e, d >> 3) + (d & 7) * 2) = __float2bfloat16_rn(num / dn * q_scale);
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading the peers' sets; waited for at the end
+  __syncthreads();
+  // ---------------------------------------------------------------- phase B
+  uint32_t cb[4][4];                               // ctx as B fragments: [n-tile(e)][b0 ks0, b1 ks0, b0 ks1, b1 ks1]
+  const uint32_t sc = ptx::smem_u32(ctxT);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+    ptx::ldmatrix_x4(sc + swz(8 * nt + (lane & 7), lane >> 3), cb[nt][0], cb[nt][1], cb[nt][2], cb[nt][3]);
+  const int D = H * DH;
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
+    if (c + 1 < nchunks) {
+      lin_load_chunk(stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES, qg + size_t(c + 1) * LIN_CH * DH, lane);
+      ptx::cp_async_commit();
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {               // 16 query rows each
+      uint32_t qa[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ptx::ldmatrix_x4(cur + swz(mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)), qa[ks][0],
+                         qa[ks][1], qa[ks][2], qa[ks][3]);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float2 x[4];
+        x[0] = bf2_to_f2(qa[0][hf]); x[1] = bf2_to_f2(qa[0][hf + 2]);
+        x[2] = bf2_to_f2(qa[1][hf]); x[3] = bf2_to_f2(qa[1][hf + 2]);
+        float mx = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)),
+                         fmaxf(fmaxf(x[2].x, x[2].y), fmaxf(x[3].x, x[3].y)));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float s = 0.f;
+        const float mxl = mx * LOG2E;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[i].x = fast_ex2(fmaf(x[i].x, LOG2E, -mxl));
+          x[i].y = fast_ex2(fmaf(x[i].y, LOG2E, -mxl));
+          s += x[i].x + x[i].y;
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float inv = 1.f / s;
+        qa[0][hf] = ptx::pack_bf16x2(x[0].x * inv, x[0].y * inv);
+        qa[0][hf + 2] = ptx::pack_bf16x2(x[1].x * inv, x[1].y * inv);
+        qa[1][hf] = ptx::pack_bf16x2(x[2].x * inv, x[2].y * inv);
+        qa[1][hf + 2] = ptx::pack_bf16x2(x[3].x * inv, x[3].y * inv);
+      }
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+        ptx::mma_bf16_16816(o[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], cb[nt][0], cb[nt][1]);
+        ptx::mma_bf16_16816(o[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], cb[nt][2], cb[nt][3]);
+      }
+      const size_t row0 = size_t(b) * L + size_t(row_first) + size_t(c) * LIN_CH + mt * 16 + g;
+      __nv_bfloat16* o0 = out + row0 * D + h * DH + 2 * t;
+      __nv_bfloat16* o1 = o0 + size_t(8) * D;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<uint32_t*>(o0 + nt * 8) = ptx::pack_bf16x2(o[nt][0], o[nt][1]);
+        *reinterpret_cast<uint32_t*>(o1 + nt * 8) = ptx::pack_bf16x2(o[nt][2], o[nt][3]);
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // no CTA leaves while a peer may still read its set
+}
+
+
 // ================================================================================================
 // Local attention on the 5th-generation tensor cores (tcgen05), one CTA (4 warps) per (window, head, sample).
 //   TMA (64B swizzle) stages Q [128 x 32], K_w and V_w [128 x 32] of the 1-3 visible key windows.
@@ -1149,9 +1415,9 @@ local_attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bflo
 // TMEM per stream: S / P slots at 0, BK, 2 BK; O buffers (32 columns each) from 3 BK.
 //   NS = 2, BK = 64: 192 + 2 x 32 = 256 columns;  NS = 4, BK = 32: 96 + 32 = 128 columns.
 // ================================================================================================
-template <int NS, int BK>
+template <int NS, int BK, int NSTO = 0>
 struct MsCfg {
-  static constexpr int NST = NS == 2 ? 3 : 2;               // K/V ring stages per stream (tiles of 128 keys)
+  static constexpr int NST = NSTO > 0 ? NSTO : (NS == 2 ? 3 : 2);   // K/V ring stages per stream (tiles of 128 keys)
   static constexpr int NOB = NS == 2 ? 2 : 1;               // O accumulators per stream
   static constexpr int SB = WIN / BK;                       // blocks per K/V tile
   static constexpr int TM_STREAM = 512 / NS;
@@ -1162,6 +1428,11 @@ struct MsCfg {
   static_assert(TM_O + NOB * 32 <= TM_STREAM, "tensor memory budget");
   static_assert((2 * NS) % 4 == 0, "softmax warp w must sit on TMEM lane quarter w % 4");
 };
+
+// Timeline of CTA 0 (test hook biom3_debug_trace; ABL == 30): [stream][who: 0 issuer, 1 softmax warp 0][block g < 128][event] = clock64()
+//   issuer:  0 before issue_s, 1 S issued, 2 before issue_pv, 3 p_ready seen, 4 PV issued
+//   softmax: 0 loop top, 1 s_full seen, 2 scores loaded, 3 exponentials done, 4 P stored + arrived, 5 after epilogue
+__device__ long long g_ms_trace[2][2][128][6];
 
 template <int NST, int NOB>
 struct MsBars {
@@ -1184,11 +1455,13 @@ __device__ __forceinline__ float ex2_fma_pipe(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int NS, int BK, int POLY>
+// ABL (timing ablations only, results are wrong): 1 = no exponentials (FMA pipe only), 2 = softmax warps only hand the
+// slots on (no tensor-memory traffic, no math): the TMA + MMA + barrier pipeline alone, 3 = no max pass
+template <int NS, int BK, int POLY, int ABL = 0, int NSTO = 0>
 __global__ void __launch_bounds__(MsCfg<NS, BK>::THREADS, 1)
 local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
                           int L, int NL, float scale_log2e, int reverse) {
-  using Cfg = MsCfg<NS, BK>;
+  using Cfg = MsCfg<NS, BK, NSTO>;
   constexpr int NST = Cfg::NST, NOB = Cfg::NOB, SB = Cfg::SB;
   const int nw = L / WIN;
   const int total = nw * B * NL;
@@ -1281,6 +1554,10 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
         }
         const int st = c.t % NST;
         ptx::mbar_wait_parked(&bar.kv_free[st], ((c.t / NST) & 1) ^ 1);
+        if constexpr (ABL == 4) {
+          ptx::mbar_arrive(&bar.kv_full[st]);
+          continue;
+        }
         ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
         ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (c.w_lo + c.kt) * WIN);
         ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kt) * WIN);
@@ -1291,38 +1568,47 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
     if (lane == 0) {
       constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t(BK) >> 3) << 17) | ((128u >> 4) << 24);
       constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      const bool tr = ABL == 30 && blockIdx.x == 0 && stream < 2;
       auto issue_s = [&](const MsCursor& c) {
         const int qb = c.n & 1, st = c.t % NST, slot = c.g % 3;
+        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][0] = clock64();
         if (first_block(c)) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
         if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[st], (c.t / NST) & 1);
         ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g / 3) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
         const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE) + c.sb * BK * 64);
-        ptx::umma_bf16(tmem + slot * BK, dq, dk, IDESC_S, 0);
-        ptx::umma_bf16(tmem + slot * BK, dq + 2, dk + 2, IDESC_S, 1);
+        if constexpr (ABL != 22 && ABL != 23) {
+          ptx::umma_bf16(tmem + slot * BK, dq, dk, IDESC_S, 0);
+          ptx::umma_bf16(tmem + slot * BK, dq + 2, dk + 2, IDESC_S, 1);
+        }
         ptx::umma_commit(&bar.s_full[slot]);
         if (last_block(c)) ptx::umma_commit(&bar.q_free[qb]);
+        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][1] = clock64();
       };
       auto issue_pv = [&](const MsCursor& c) {
         const int ob = c.n % NOB, st = c.t % NST, slot = c.g % 3;
+        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][2] = clock64();
         if (first_block(c)) ptx::mbar_wait_parked(&bar.o_free[ob], ((c.n / NOB) & 1) ^ 1);
         ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g / 3) & 1);
+        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][3] = clock64();
         ptx::tc_fence_after();
         const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE) + c.sb * BK * 64;
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks)
+        for (int ks = 0; ks < ((ABL == 21 || ABL == 23) ? 0 : BK / 16); ++ks)
           ptx::umma_bf16_ts(tmem + Cfg::TM_O + ob * 32, tmem + slot * BK + ks * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
                             !(first_block(c) && ks == 0));
         ptx::umma_commit(&bar.s_free[slot]);
         if (c.sb == SB - 1) ptx::umma_commit(&bar.kv_free[st]);
         if (last_block(c)) ptx::umma_commit(&bar.o_full[ob]);
+        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][4] = clock64();
       };
       MsCursor sc, pc;
       start(sc);
       start(pc);
+      constexpr int AHEAD = (ABL == 7 || ABL == 8) ? 2 : 3;
       while (pc.valid) {
-        while (sc.valid && sc.g < pc.g + 3) {
+        while (sc.valid && sc.g < pc.g + AHEAD) {
           issue_s(sc);
           advance(sc);
         }
@@ -1364,11 +1650,22 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
                             ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
     };
     MsCursor c;
+    const bool tr = ABL == 30 && blockIdx.x == 0 && stream < 2 && quarter == 0 && lane == 0;
     for (start(c); c.valid; advance(c)) {
       const int g = c.g, slot = g % 3;
       const uint32_t t_s = lane_base + slot * BK;
+      if (tr && g < 128) g_ms_trace[stream][1][g][0] = clock64();
       ptx::mbar_wait(&bar.s_full[slot], (g / 3) & 1);
+      if (tr && g < 128) g_ms_trace[stream][1][g][1] = clock64();
       ptx::tc_fence_after();
+      if constexpr (ABL == 2 || ABL == 4 || ABL == 8 || ABL >= 20) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+        if (first_block(c) && pend) { epilogue(); pend = false; }
+        if (last_block(c)) { pend = true; p_n = c.n; p_inv = 1.f; p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH; }
+        continue;
+      }
       uint32_t r[BK];
       {
         uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
@@ -1379,6 +1676,7 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
         }
       }
       ptx::tmem_ld_wait();
+      if (tr && g < 128) g_ms_trace[stream][1][g][2] = clock64();
       float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
       for (int k = 0; k < BK / 4; ++k) {
@@ -1387,13 +1685,13 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
         b2 = fmaxf(b2, __uint_as_float(r[4 * k + 2]));
         b3 = fmaxf(b3, __uint_as_float(r[4 * k + 3]));
       }
-      const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+      const float bm = ABL == 3 ? __uint_as_float(r[0]) : fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
       if (first_block(c)) {
         m_ref = bm;
         rs = 0.f;
       } else {
         const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
+        if (ABL != 3 && __any_sync(0xffffffffu, need)) {
           const int gp = g - 1;                            // every PV issued so far must have landed in O
           ptx::mbar_wait(&bar.s_free[gp % 3], (gp / 3) & 1);
           ptx::tc_fence_after();
@@ -1417,29 +1715,381 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
       for (int k = 0; k < BK / 4; ++k) {
         const float x0 = fmaf(__uint_as_float(r[4 * k]), scale_log2e, -ms), x1 = fmaf(__uint_as_float(r[4 * k + 1]), scale_log2e, -ms);
         const float x2 = fmaf(__uint_as_float(r[4 * k + 2]), scale_log2e, -ms), x3 = fmaf(__uint_as_float(r[4 * k + 3]), scale_log2e, -ms);
-        const float p0 = fast_ex2(x0), p1 = fast_ex2(x1), p2 = fast_ex2(x2);
-        const float p3 = (POLY > 0 && (k % (POLY / 4 > 0 ? POLY / 4 : 1)) == 0) ? ex2_fma_pipe(x3) : fast_ex2(x3);
+        const float p0 = ABL == 1 ? x0 : fast_ex2(x0), p1 = ABL == 1 ? x1 : fast_ex2(x1), p2 = ABL == 1 ? x2 : fast_ex2(x2);
+        const float p3 = ABL == 1 ? x3 : (POLY > 0 && (k % (POLY / 4 > 0 ? POLY / 4 : 1)) == 0) ? ex2_fma_pipe(x3) : fast_ex2(x3);
         s0 += p0; s1 += p1; s2 += p2; s3 += p3;
         pk[2 * k] = ptx::pack_bf16x2(p0, p1);
         pk[2 * k + 1] = ptx::pack_bf16x2(p2, p3);
       }
       rs += (s0 + s1) + (s2 + s3);
+      if (tr && g < 128) g_ms_trace[stream][1][g][3] = clock64() + (__float_as_int(rs) & 0);
       if constexpr (BK == 64) ptx::tmem_st_32x32(t_s, pk);
       else ptx::tmem_st_32x16(t_s, pk);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+      if (tr && g < 128) g_ms_trace[stream][1][g][4] = clock64();
       if (first_block(c) && pend) {
         epilogue();
         pend = false;
       }
+      if (tr && g < 128) g_ms_trace[stream][1][g][5] = clock64();
       if (last_block(c)) {
         pend = true;
         p_n = c.n;
         p_inv = 1.f / rs;
         p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH;
       }
+    }
+    if (pend) epilogue();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
+}
+
+
+// ================================================================================================
+// Windowed softmax attention on tcgen05, round 2 schedule ("v5"): two streams per CTA as in variant 3, but every
+// stream now has TWO single-thread MMA issuers and lean, division-free control loops.
+//
+// Why (profiles/r02_attn_trace_ms_issuer_bound.log, profiles/r02_attn_ablations.log): a clock64 timeline of variant 3
+// showed the softmax warps idle ~1250 of every ~1450 cycles per 64-key block, waiting for scores; removing ALL
+// exponentials did not change the kernel time (85 us -> 85 us) and removing the softmax work altogether only took it
+// to 70 us.  The one thread per stream that issued both S = Q K^T and O += P V spent ~365 cycles per S (2 MMAs),
+// ~560 per PV (4 MMAs) and ~300 on cursor arithmetic per block: with 128 x 64 x 16 MMAs (16-32 tensor-pipe cycles each)
+// the serial issue path, not the tensor pipe, the MUFU pipe or TMA, bounded the kernel.
+//
+//   warp 3s+0   TMA producer of stream s: Q (double buffered) and K/V tiles (ring of NST stages), 64-byte swizzle
+//   warp 3s+1   S issuer:  waits for the slot (s_free) and the tile, issues S_g = Q K_g^T, commits s_full; runs ahead of
+//               the PV issuer as far as the three S / P slots allow
+//   warp 3s+2   PV issuer: waits for P_g (p_ready), issues O (+)= P_g V_g with P read from TMEM, commits s_free
+//               (and kv_free / o_full at tile / item ends)
+//   warps 6..13 softmax: four warps per stream, one thread per query row (unchanged arithmetic: block maximum, exp2
+//               against a lazily rescaled reference maximum, bf16 P written over the slot's own S columns)
+// Descriptors are built once per tile (low word = address >> 4, the high word is a constant); ring slots and barrier
+// phases are carried incrementally.  tcgen05.commit tracks the MMAs of the issuing thread, so each issuer's commits
+// cover exactly its own instructions.
+// TMEM per stream: S / P slots at 0, 64, 128; O buffers at 192, 224.
+// ================================================================================================
+constexpr int V5_THREADS = 14 * 32;
+template <int NST>
+struct V5Cfg {
+  static constexpr int STREAM_TILES = 2 + 2 * NST;
+  static constexpr int SMEM_BYTES = 2 * STREAM_TILES * TC_TILE + 1024;
+};
+template <int NST>
+struct V5Bars {
+  uint64_t q_full[2], q_free[2], kv_full[NST], kv_free[NST], s_full[3], p_ready[3], s_free[3], o_full[2], o_free[2];
+};
+struct V5Item {                      // one (window, sample, head)
+  int w, b, h, w_lo, nkt;
+};
+constexpr uint32_t V5_DESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint32_t v5_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t v5_desc(uint32_t lo) { return (static_cast<uint64_t>(V5_DESC_HI) << 32) | lo; }
+
+// TURNS: the two softmax warps that share an SMSP (same row quarter, different streams) take turns on the MUFU pipe
+// (see the softmax role below); POLY: every POLY-th exponential on the FMA / ALU pipes (0 = none)
+template <int NST, int TRACE, int TURNS = 0, int POLY = 0>
+__global__ void __launch_bounds__(V5_THREADS, 1)
+local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
+                          int L, int NL, float scale_log2e, int reverse) {
+  const int nw = L / WIN;
+  const int total = nw * B * NL, nlb = NL * B;
+  // warp index through a shuffle: provably warp-uniform, so everything derived from it (stream, role, shared-memory and
+  // tensor-memory addresses, descriptors) lives in uniform registers and the single-thread tcgen05 instructions need no
+  // per-lane "waterfall" loop (ELECT / R2UR.BROADCAST / BRA.U.ANY around every UTCHMMA: ~15 dependent instructions each)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int stream = warp < 6 ? warp / 3 : (warp - 6) >> 2;
+  const int role = warp < 6 ? warp % 3 : 3;              // 0 producer, 1 S issuer, 2 PV issuer, 3 softmax
+
+  extern __shared__ uint8_t v5_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v5_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + stream * V5Cfg<NST>::STREAM_TILES * TC_TILE;     // 2 tiles
+  uint8_t* sKV = sQ + 2 * TC_TILE;                                      // NST x (K tile, V tile)
+  __shared__ V5Bars<NST> bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int mufu_turn[4];                  // per row quarter: 0 free, else 1 + the stream whose warp is exponentiating
+  V5Bars<NST>& bar = bars[stream];
+  if (tid < 4) mufu_turn[tid] = 0;
+
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_qkv);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      V5Bars<NST>& x = bars[s2];
+      for (int k = 0; k < 2; ++k) {
+        ptx::mbar_init(&x.q_full[k], 1);
+        ptx::mbar_init(&x.q_free[k], 1);
+        ptx::mbar_init(&x.o_full[k], 1);
+        ptx::mbar_init(&x.o_free[k], 4);
+      }
+      for (int k = 0; k < NST; ++k) {
+        ptx::mbar_init(&x.kv_full[k], 1);
+        ptx::mbar_init(&x.kv_free[k], 1);
+      }
+      for (int k = 0; k < 3; ++k) {
+        ptx::mbar_init(&x.s_full[k], 1);
+        ptx::mbar_init(&x.p_ready[k], 4);
+        ptx::mbar_init(&x.s_free[k], 1);
+      }
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0) + stream * 256;
+  ptx::pdl_sync();
+
+  // the n-th item of this stream: flat index blockIdx.x + (stream + 2 n) gridDim.x, walked window-major
+  auto item = [&](int n, V5Item& it) -> bool {
+    const int f = int(blockIdx.x) + (stream + 2 * n) * int(gridDim.x);
+    if (f >= total) return false;
+    const int ff = reverse ? total - 1 - f : f;
+    it.w = ff / nlb;
+    const int r = ff - it.w * nlb;
+    it.b = r / NL;
+    it.h = r - it.b * NL;
+    it.w_lo = max(it.w - 1, 0);
+    it.nkt = min(it.w + 1, nw - 1) - it.w_lo + 1;
+    return true;
+  };
+
+  if (role == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int plane = B * H * L;
+      V5Item it;
+      uint32_t st = 0, st_ph = 0;
+      for (int n = 0; item(n, it); ++n) {
+        const int rq = (it.b * H + it.h) * L;
+        const int qb = n & 1;
+        ptx::mbar_wait_parked(&bar.q_free[qb], ((n >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
+        ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + it.w * WIN);
+        for (int kt = 0; kt < it.nkt; ++kt) {
+          ptx::mbar_wait_parked(&bar.kv_free[st], st_ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
+          ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (it.w_lo + kt) * WIN);
+          ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (it.w_lo + kt) * WIN);
+          if (++st == NST) { st = 0; st_ph ^= 1; }
+        }
+      }
+    }
+  } else if (role == 1) {
+    // ------------------------------------------------------------------ S issuer (the whole warp walks the loop, one elected lane issues)
+    {
+      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t q_lo0 = v5_desc_lo(ptx::smem_u32(sQ)), kv_lo0 = v5_desc_lo(ptx::smem_u32(sKV));
+      V5Item it;
+      uint32_t st = 0, st_ph = 0, slot = 0, slot_ph = 0;
+      int g = 0;
+      for (int n = 0; item(n, it); ++n) {
+        const int qb = n & 1;
+        ptx::mbar_wait_parked(&bar.q_full[qb], (n >> 1) & 1);
+        const uint32_t q_lo = q_lo0 + qb * (TC_TILE >> 4);
+        for (int kt = 0; kt < it.nkt; ++kt) {
+          ptx::mbar_wait_parked(&bar.kv_full[st], st_ph);
+          const uint32_t k_lo = kv_lo0 + st * (2 * TC_TILE >> 4);
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {
+            if (TRACE && blockIdx.x == 0 && g < 128 && lane == 0) g_ms_trace[stream][0][g][0] = clock64();
+            ptx::mbar_wait_parked(&bar.s_free[slot], slot_ph ^ 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              ptx::umma_bf16(tmem + slot * 64, v5_desc(q_lo), v5_desc(k_lo + sb * 256), IDESC_S, 0);
+              ptx::umma_bf16(tmem + slot * 64, v5_desc(q_lo + 2), v5_desc(k_lo + sb * 256 + 2), IDESC_S, 1);
+              ptx::umma_commit(&bar.s_full[slot]);
+            }
+            __syncwarp();
+            if (TRACE && blockIdx.x == 0 && g < 128 && lane == 0) g_ms_trace[stream][0][g][1] = clock64();
+            if (++slot == 3) { slot = 0; slot_ph ^= 1; }
+            ++g;
+          }
+          if (++st == NST) { st = 0; st_ph ^= 1; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(&bar.q_free[qb]);
+        __syncwarp();
+      }
+    }
+  } else if (role == 2) {
+    // ------------------------------------------------------------------ PV issuer (same pattern)
+    {
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t kv_lo0 = v5_desc_lo(ptx::smem_u32(sKV));
+      V5Item it;
+      uint32_t st = 0, st_ph = 0, slot = 0, slot_ph = 0;
+      int g = 0;
+      for (int n = 0; item(n, it); ++n) {
+        const int ob = n & 1;
+        ptx::mbar_wait_parked(&bar.o_free[ob], ((n >> 1) & 1) ^ 1);
+        const uint32_t t_o = tmem + 192 + ob * 32;
+        for (int kt = 0; kt < it.nkt; ++kt) {
+          ptx::mbar_wait_parked(&bar.kv_full[st], st_ph);               // V of this tile has landed (visible to this thread)
+          const uint32_t v_lo = kv_lo0 + st * (2 * TC_TILE >> 4) + (TC_TILE >> 4);
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {
+            if (TRACE && blockIdx.x == 0 && g < 128 && lane == 0) g_ms_trace[stream][0][g][2] = clock64();
+            ptx::mbar_wait_parked(&bar.p_ready[slot], slot_ph);
+            if (TRACE && blockIdx.x == 0 && g < 128 && lane == 0) g_ms_trace[stream][0][g][3] = clock64();
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                ptx::umma_bf16_ts(t_o, tmem + slot * 64 + ks * 8, v5_desc(v_lo + sb * 256 + ks * 64), IDESC_O,
+                                  (kt | sb | ks) != 0);
+              ptx::umma_commit(&bar.s_free[slot]);
+              if (sb == 1) ptx::umma_commit(&bar.kv_free[st]);
+              if (sb == 1 && kt == it.nkt - 1) ptx::umma_commit(&bar.o_full[ob]);
+            }
+            __syncwarp();
+            if (TRACE && blockIdx.x == 0 && g < 128 && lane == 0) g_ms_trace[stream][0][g][4] = clock64();
+            if (++slot == 3) { slot = 0; slot_ph ^= 1; }
+            ++g;
+          }
+          if (++st == NST) { st = 0; st_ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (4 warps per stream)
+    // Online softmax per 64-key block against a lazily updated reference maximum: the first block of an item sets m_ref
+    // to its row maximum; a later block rescales O and the row sum only when its maximum exceeds m_ref by more than 2^8
+    // (P stays <= 256, exact in bf16's range), which real score distributions almost never do.  The output of item n is
+    // read after the first block of item n + 1 (O is double buffered), when its last PV has long completed.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
+    const int D = H * DH;
+    constexpr float LAZY_LOG2 = 8.0f;
+    const bool tr = TRACE && blockIdx.x == 0 && quarter == 0 && lane == 0;
+    float m_ref = 0.f, rs = 0.f;
+    bool pend = false;
+    int p_n = 0;
+    float p_inv = 0.f;
+    __nv_bfloat16* p_dst = nullptr;
+    auto epilogue = [&]() {
+      const int ob = p_n & 1;
+      ptx::mbar_wait(&bar.o_full[ob], (p_n >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t ro[32];
+      ptx::tmem_ld_32x32(lane_base + 192 + ob * 32, ro);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.o_free[ob]);
+      uint4* dst = reinterpret_cast<uint4*>(p_dst);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * p_inv, __uint_as_float(ro[8 * k + 1]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * p_inv, __uint_as_float(ro[8 * k + 3]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
+    };
+    V5Item it;
+    uint32_t slot = 0, slot_ph = 0;
+    int g = 0;
+    for (int n = 0; item(n, it); ++n) {
+      const int nblk = 2 * it.nkt;
+      for (int blk = 0; blk < nblk; ++blk) {
+        const uint32_t t_s = lane_base + slot * 64;
+        if (tr && g < 128) g_ms_trace[stream][1][g][0] = clock64();
+        ptx::mbar_wait(&bar.s_full[slot], slot_ph);
+        if (tr && g < 128) g_ms_trace[stream][1][g][1] = clock64();
+        ptx::tc_fence_after();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(t_s, r0);
+        ptx::tmem_ld_32x32(t_s + 32, r1);
+        ptx::tmem_ld_wait();
+        if (tr && g < 128) g_ms_trace[stream][1][g][2] = clock64();
+        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          b0 = fmaxf(b0, __uint_as_float(r0[2 * k]));
+          b1 = fmaxf(b1, __uint_as_float(r0[2 * k + 1]));
+          b2 = fmaxf(b2, __uint_as_float(r1[2 * k]));
+          b3 = fmaxf(b3, __uint_as_float(r1[2 * k + 1]));
+        }
+        const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+        if (blk == 0) {
+          m_ref = bm;
+          rs = 0.f;
+        } else {
+          const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
+          if (__any_sync(0xffffffffu, need)) {
+            // every PV issued so far must have landed in O: PV(g - 1)'s commit completes s_free of its slot
+            const uint32_t pslot = slot == 0 ? 2 : slot - 1, pph = slot == 0 ? slot_ph ^ 1 : slot_ph;
+            ptx::mbar_wait(&bar.s_free[pslot], pph);
+            ptx::tc_fence_after();
+            const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
+            uint32_t ro[32];
+            const uint32_t t_o = lane_base + 192 + (n & 1) * 32;
+            ptx::tmem_ld_32x32(t_o, ro);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
+            ptx::tmem_st_32x32(t_o, ro);
+            ptx::tmem_st_wait();
+            rs *= f;
+            if (need) m_ref = bm;
+          }
+        }
+        const float ms = m_ref * scale_log2e;
+        // The exponentials of a block keep the MUFU pipe busy for 512 cycles (64 warp instructions at 4 lanes per clock
+        // per SMSP); everything else a softmax warp does per block (barrier, tensor-memory load and store, maximum) is
+        // ~400 cycles without MUFU work.  Two warps share the SMSP.  Left alone they fall into lockstep — both
+        // exponentiate at half rate, then both idle the pipe (measured: ~1500 cycles per block pair, MUFU 2/3 busy) —
+        // so they take turns instead: a warp that finds its neighbour exponentiating waits for it to finish (bounded:
+        // this is a scheduling hint in shared memory, not a lock) and then has the pipe to itself while the neighbour
+        // does its MUFU-free part.
+        if constexpr (TURNS) {
+          int spins = 0;
+          while (mufu_turn[quarter] == 2 - stream && ++spins < 40) {}        // ~25 cycles per poll, bounded to one block's exponentials
+          __syncwarp();
+          if (lane == 0) mufu_turn[quarter] = 1 + stream;
+        }
+        uint32_t pk[32];                                   // P (bf16 pairs) over the first 32 of the slot's 64 columns
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
+          const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
+          const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
+          const float x3 = fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms);
+          const float p3 = (POLY > 0 && (4 * k + 3) % POLY == 3 % POLY) ? ex2_fma_pipe(x3) : fast_ex2(x3);
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[k] = ptx::pack_bf16x2(p0, p1);
+          pk[16 + k] = ptx::pack_bf16x2(p2, p3);
+        }
+        rs += (s0 + s1) + (s2 + s3);
+        if constexpr (TURNS) {
+          if (lane == 0) mufu_turn[quarter] = 0;
+        }
+        if (tr && g < 128) g_ms_trace[stream][1][g][3] = clock64() + (__float_as_int(rs) & 0);
+        ptx::tmem_st_32x32(t_s, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+        if (tr && g < 128) g_ms_trace[stream][1][g][4] = clock64();
+        if (blk == 0 && pend) {
+          epilogue();
+          pend = false;
+        }
+        if (tr && g < 128) g_ms_trace[stream][1][g][5] = clock64();
+        if (++slot == 3) { slot = 0; slot_ph ^= 1; }
+        ++g;
+      }
+      pend = true;
+      p_n = n;
+      p_inv = 1.f / rs;
+      p_dst = out + (size_t(it.b) * L + size_t(it.w) * WIN + row) * D + it.h * DH;
     }
     if (pend) epilogue();
   }

@@ -206,11 +206,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __shared__ uint64_t a_full[ARES_NK], a_empty[ARES_NK];      // ARES: one pair per resident A k-block
   __shared__ uint32_t tmem_base_slot;
 
-  const uint32_t warp = threadIdx.x >> 5;
+  // The warp index goes through a shuffle so that the compiler can prove it warp-uniform: everything derived from it (roles,
+  // shared- and tensor-memory addresses, descriptors, TMA coordinates) then lives in uniform registers, and the
+  // single-thread tcgen05 / TMA instructions (issued by one ELECTed lane of a converged warp) need no per-lane "waterfall"
+  // loop.  With `threadIdx.x >> 5` and `if (lane == 0)` every UTCHMMA sat in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of
+  // ~17 dependent instructions (~100 cycles per MMA for the issuing thread: measured in the attention kernel's timeline,
+  // profiles/r02_attn_trace_*.log).
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const uint32_t cta_rank = CG2 ? ptx::cluster_ctarank() : 0u;
+  const uint32_t cta_rank = CG2 ? __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) : 0u;
   const bool leader = cta_rank == 0;
   const int worker = CG2 ? int(blockIdx.x >> 1) : int(blockIdx.x);        // tile-walking unit (CTA or CTA pair)
   const int n_workers = CG2 ? int(gridDim.x >> 1) : int(gridDim.x);
@@ -264,15 +270,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   ptx::tc_fence_before();
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
   ptx::pdl_sync();          // everything above touched only this CTA's smem / TMEM
 
   // (setmaxnreg sits at the head of each role branch so that it dominates the code whose register budget it changes)
   if (warp < EPI_WARP0) {
   if constexpr (RD == 2) ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (every CTA)
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (every CTA; converged warp, one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
       int cur_mb = -1;
       uint32_t run = 0;                                    // ARES: row-block runs started so far
@@ -287,12 +293,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (new_mb) {
               // slot kb of the resident block is free once the previous run's last tile has consumed it
               ptx::mbar_wait_parked(&a_empty[kb], (run & 1) ^ 0);      // run r (1-based): parity of completion r - 1
-              if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * SL::A_BYTES);
-              ptx::tma_load_2d_cg2(smem + kb * SL::A_BYTES, &tmap_a, &a_full[kb], kb * BK, m0 + p.a_row_offset);
+              if (ptx::elect_one()) {
+                if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * SL::A_BYTES);
+                ptx::tma_load_2d_cg2(smem + kb * SL::A_BYTES, &tmap_a, &a_full[kb], kb * BK, m0 + p.a_row_offset);
+              }
+              __syncwarp();
             }
             ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::B_BYTES);
-            ptx::tma_load_2d_cg2(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::B_BYTES);
+              ptx::tma_load_2d_cg2(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else
@@ -303,23 +315,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // split3: blocks [0, nk) A_hi.W_hi, [nk, 2nk) A_hi.W_lo, [2nk, 3nk) A_lo.W_hi
           const int ka = (kb < nk ? kb : kb - nk) * BK;
           const int kw = (kb < 2 * nk ? kb : kb - 2 * nk) * BK;
-          if constexpr (CG2) {
-            // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::STAGE_BYTES);
-            ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
-            ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kw, n0);
-          } else {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kw, n0);
+          if (ptx::elect_one()) {
+            if constexpr (CG2) {
+              // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::STAGE_BYTES);
+              ptx::tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
+              ptx::tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], kw, n0);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
+              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], ka, m0 + p.a_row_offset);
+              ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kw, n0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA only when paired)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only when paired; converged warp,
+    // one elected lane issues the MMAs and commits of a k-block)
+    if (leader) {
       uint32_t stage = 0, phase = 0, it = 0;
       int cur_mb = -1;
       uint32_t run = 0;
@@ -340,12 +356,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tc_fence_after();
             const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smem + kb * SL::A_BYTES));
             const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
-            ptx::umma_commit_cg2(&empty_bar[stage], 3);
-            if (last_of_run) ptx::umma_commit_cg2(&a_empty[kb], 3);
-            if (kb == nk - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+              ptx::umma_commit_cg2(&empty_bar[stage], 3);
+              if (last_of_run) ptx::umma_commit_cg2(&a_empty[kb], 3);
+              if (kb == nk - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else
@@ -359,19 +378,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t sa = ptx::smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t da = ptx::umma_desc_sw128(sa);
           const uint64_t db = ptx::umma_desc_sw128(sa + SL::A_BYTES);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-            if constexpr (CG2) ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
-            else ptx::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+              if constexpr (CG2) ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+              else ptx::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
+            }
+            if constexpr (CG2) {
+              ptx::umma_commit_cg2(&empty_bar[stage], 3);     // frees the slot in BOTH CTAs
+              if (kb == k_blocks - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
+            } else {
+              ptx::umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+              if (kb == k_blocks - 1) ptx::umma_commit(&acc_full[as]);
+            }
           }
-          if constexpr (CG2) {
-            ptx::umma_commit_cg2(&empty_bar[stage], 3);     // frees the slot in BOTH CTAs
-            if (kb == k_blocks - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
-          } else {
-            ptx::umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-            if (kb == k_blocks - 1) ptx::umma_commit(&acc_full[as]);
-          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -830,7 +852,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one lane stores
             ptx::fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
               ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
                                 tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
               ptx::tma_store_commit();

@@ -273,6 +273,30 @@ cudaError_t init_kernel_attributes_impl() {
   if (e != cudaSuccess) return e;
   SET_MS(2, 64, 0) SET_MS(4, 32, 0) SET_MS(4, 32, 4) SET_MS(4, 32, 8) SET_MS(2, 64, 8)
 #undef SET_MS
+#define SET_ABL(A)                                                                                               \
+  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           attn::MsCfg<2, 64>::SMEM_BYTES);                                                      \
+  if (e != cudaSuccess) return e;
+  SET_ABL(1) SET_ABL(2) SET_ABL(3) SET_ABL(4) SET_ABL(7) SET_ABL(8) SET_ABL(21) SET_ABL(22) SET_ABL(23) SET_ABL(30)
+#undef SET_ABL
+  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, 0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::MsCfg<2, 64, 6>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::MsCfg<2, 64, 6>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+#define SET_V5(NST, TR)                                                                                         \
+  e = cudaFuncSetAttribute(attn::local_attention_v5_kernel<NST, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           attn::V5Cfg<NST>::SMEM_BYTES);                                                        \
+  if (e != cudaSuccess) return e;
+  SET_V5(3, 0) SET_V5(4, 0) SET_V5(5, 0) SET_V5(6, 0) SET_V5(3, 1)
+#undef SET_V5
+#define SET_V5T(NST, TR, TU, PO)                                                                                \
+  e = cudaFuncSetAttribute(attn::local_attention_v5_kernel<NST, TR, TU, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           attn::V5Cfg<NST>::SMEM_BYTES);                                                        \
+  if (e != cudaSuccess) return e;
+  SET_V5T(5, 0, 1, 0) SET_V5T(5, 1, 1, 0) SET_V5T(5, 0, 1, 4) SET_V5T(5, 0, 1, 8) SET_V5T(5, 0, 0, 4) SET_V5T(5, 1, 1, 4)
+#undef SET_V5T
+  e = cudaFuncSetAttribute(attn::linear_attention_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::LINC_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::sample_all_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -307,7 +331,31 @@ void launch_local_ms(int variant, const CUtensorMap& tm, bf16* out, int B, int H
     launch_k(attn::local_attention_ms_kernel<NS, BK, POLY>, dim3(grid), dim3(attn::MsCfg<NS, BK>::THREADS),       \
              size_t(attn::MsCfg<NS, BK>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse);           \
     break;
+#define V5_CASE(V, NST, TR)                                                                                      \
+  case V:                                                                                                         \
+    launch_k(attn::local_attention_v5_kernel<NST, TR>, dim3(grid), dim3(attn::V5_THREADS), size_t(attn::V5Cfg<NST>::SMEM_BYTES), st, \
+             tm, out, B, H, L, NL, scale_log2e, reverse);                                                        \
+    break;
   switch (variant) {
+    V5_CASE(50, 3, 0) V5_CASE(51, 4, 0) V5_CASE(52, 5, 0) V5_CASE(53, 6, 0) V5_CASE(59, 3, 1)
+#define V5T_CASE(V, NST, TR, TU, PO)                                                                             \
+  case V:                                                                                                         \
+    launch_k(attn::local_attention_v5_kernel<NST, TR, TU, PO>, dim3(grid), dim3(attn::V5_THREADS), size_t(attn::V5Cfg<NST>::SMEM_BYTES), st, \
+             tm, out, B, H, L, NL, scale_log2e, reverse);                                                        \
+    break;
+    V5T_CASE(60, 5, 0, 1, 0) V5T_CASE(69, 5, 1, 1, 0) V5T_CASE(61, 5, 0, 1, 4) V5T_CASE(62, 5, 0, 1, 8) V5T_CASE(63, 5, 0, 0, 4) V5T_CASE(68, 5, 1, 1, 4)
+    case 11: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 1>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 12: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 2>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 14: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 4>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 15: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 0, 6>, dim3(grid), dim3(attn::MsCfg<2, 64, 6>::THREADS), size_t(attn::MsCfg<2, 64, 6>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 16: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 2, 6>, dim3(grid), dim3(attn::MsCfg<2, 64, 6>::THREADS), size_t(attn::MsCfg<2, 64, 6>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 17: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 7>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 18: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 8>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 21: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 21>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 22: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 22>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 23: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 23>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 30: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 30>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
+    case 13: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 3>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
     MS_CASE(4, 2, 64, 0)
     MS_CASE(5, 4, 32, 0)
     MS_CASE(6, 4, 32, 4)
@@ -316,6 +364,25 @@ void launch_local_ms(int variant, const CUtensorMap& tm, bf16* out, int B, int H
     MS_CASE(8, 2, 64, 8)
   }
 #undef MS_CASE
+}
+
+// linear attention, one cluster of `cl` CTAs per (global head, sample)
+void launch_linear_cl(int cl, const bf16* qkv, bf16* out, int B, int H, int L, int NL, float q_scale, int reverse, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((H - NL) * cl, B);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = attn::LINC_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, attn::linear_attention_cl_kernel, qkv, out, B, H, L, NL, q_scale, reverse);
 }
 
 enum Cat { C_QKV, C_OUT, C_FF1, C_FF2, C_LOCAL, C_LINEAR, C_LN, C_EMBED, C_HEAD, C_OTHER, C_COUNT };
@@ -374,7 +441,7 @@ struct biom3_model {
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
-  int attn_tc = 3;                              // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM),
+  int attn_tc = 52;                             // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM),
                                                 // 3 = 2 split into two ping-pong streams per CTA (default; BIOM3_ATTN_TC)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
   int tma_store = 1;                            // bf16 epilogue store path, see gemm::Params::tma_store (BIOM3_TMA_STORE)
@@ -1315,6 +1382,13 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
   return r;
 }
 
+int biom3_debug_trace(void* host_dst, int64_t nbytes) {
+  if (!host_dst || nbytes <= 0) return fail(BIOM3_ERR_INVALID, "bad debug_trace argument");
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpyFromSymbol(host_dst, attn::g_ms_trace, std::min(size_t(nbytes), sizeof(attn::g_ms_trace))));
+  return BIOM3_OK;
+}
+
 int biom3_debug_noise(uint64_t seed, int step, int B, int L, int C, float* out, void* stream) {
   if (!out || step < 0 || B < 1 || L < 1 || C < 1 || C > 32) return fail(BIOM3_ERR_INVALID, "bad debug_noise argument");
   int ndev = 0;
@@ -1374,6 +1448,9 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
     return fail(BIOM3_ERR_INVALID, "bad attention_test argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CU_OK(init_kernel_attributes());
+  int lin_cl = variant / 100;                      // test hook: hundreds digit = cluster size of the linear-attention kernel (0: one CTA)
+  variant %= 100;
+  while (lin_cl > 1 && L % (128 * lin_cl)) lin_cl >>= 1;
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
@@ -1407,8 +1484,10 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
       attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(q, o, B, H, L, scale_log2e, 0);
     }
   }
-  if (H - NL > 0)
-    attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
+  if (H - NL > 0) {
+    if (lin_cl > 0) launch_linear_cl(lin_cl, q, o, B, H, L, NL, q_scale, 0, st);
+    else attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
+  }
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }

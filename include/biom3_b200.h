@@ -157,6 +157,10 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
  * (tests/test_gpu_parity.py); oracle/philox.py restates the stream independently. */
 int biom3_debug_noise(uint64_t seed, int step, int B, int L, int C, float* out, void* stream);
 
+/* Test hook: clock64() timeline of CTA 0 of the last traced local-attention launch (biom3_attention_test variant 30):
+ * int64 [2 streams][2: issuer, softmax warp 0][128 blocks][6 events] (csrc/attention.cuh, g_ms_trace).  Synchronous. */
+int biom3_debug_trace(void* host_dst, int64_t nbytes);
+
 /* Number of kernel launches one decode step issues (for bench.py's gpu_launches): the count of the most recently
  * captured step graph, or the full-row estimate before the first decode. */
 int biom3_launches_per_step(const biom3_model* m);

@@ -21,6 +21,11 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) { uint32_t y; asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ float tanh_f32(float x) { float y; asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 template <int MODE>
 __global__ void bench(float* out, long long* cyc, int rounds, float a, float b) {
   float r[16];
@@ -37,6 +42,10 @@ __global__ void bench(float* out, long long* cyc, int rounds, float a, float b) 
       if (MODE == 2) r[i] = fmaf(r[i], a, b);                                   // FFMA only
       if (MODE == 3) r[i] = ex2_poly(fmaf(r[i], a, b));                         // polynomial exp2
       if (MODE == 5) r[i] = fmaxf(r[i] * a, b);                                 // FMUL + FMNMX
+      if (MODE == 9) r[i] = __uint_as_float(ex2_f16x2(__float_as_uint(r[i])) & 0xbbffbbffu);     // 2 half exponentials per instruction
+      if (MODE == 10) r[i] = __uint_as_float(ex2_bf16x2(__float_as_uint(r[i])) & 0xbf7fbf7fu);   // 2 bf16 exponentials per instruction
+      if (MODE == 11) r[i] = __uint_as_float(tanh_bf16x2(__float_as_uint(r[i])));                // 2 bf16 tanh per instruction
+      if (MODE == 12) r[i] = tanh_f32(r[i]) + a;                                                 // fp32 tanh
     }
     if (MODE == 4) {                                                            // F2FP only
 #pragma unroll
@@ -94,7 +103,7 @@ void run(const char* name, int warps, float ops_per_elem) {
 }
 
 int main() {
-  for (int w : {4, 8, 16, 32}) {
+  for (int w : {8, 16}) {
     printf("---- %d warps per SM (%d per SMSP)\n", w, w / 4);
     run<0>("MUFU.EX2 + FADD", w, 1);
     run<1>("FFMA + MUFU.EX2", w, 1);
@@ -102,6 +111,10 @@ int main() {
     run<5>("FMUL + FMNMX", w, 1);
     run<3>("FFMA + polynomial exp2 (FMA/ALU pipes)", w, 1);
     run<4>("F2FP.BF16 pack (per pair; elements = 2x)", w, 1);
+    run<9>("ex2.approx.f16x2 (elements = 2x shown)", w, 1);
+    run<10>("ex2.approx.ftz.bf16x2 (elements = 2x shown)", w, 1);
+    run<11>("tanh.approx.bf16x2 (elements = 2x shown)", w, 1);
+    run<12>("tanh.approx.f32 + FADD", w, 1);
     run<6>("softmax body: FFMA+EX2+FADD+pack/2", w, 1);
     run<7>("softmax body, 25% polynomial", w, 1);
     run<8>("softmax body, 50% polynomial", w, 1);
