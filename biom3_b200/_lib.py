@@ -82,7 +82,7 @@ def load() -> C.CDLL:
     lib.biom3_random_paths.restype = i32
     lib.biom3_debug_noise.argtypes = [u64, i32, i32, i32, i32, vp, vp]
     lib.biom3_debug_noise.restype = i32
-    lib.biom3_debug_trace.argtypes = [vp, i64]
+    lib.biom3_debug_trace.argtypes = [i32, vp, i64]
     lib.biom3_debug_trace.restype = i32
     lib.biom3_facilitator_create.argtypes = [i32, i32, i32, vp, C.c_float, vp, vp, C.c_float, vp, i32, C.POINTER(vp)]
     lib.biom3_facilitator_create.restype = i32

@@ -13,17 +13,6 @@ namespace attn {
 constexpr int DH = 32;     // head dim (fixed by the kernels; checked at create time)
 constexpr int WIN = 128;   // local window (fixed; checked at create time)
 
-// ------------------------------------------------------------------------------------------------
-// Local attention: query window w attends to key windows w-1, w, w+1 (those that exist), softmax
-// over the real keys only (masked keys get exp() == 0 in the reference, i.e. they are skipped here).
-// One CTA per (window, local head, sample); 8 warps x 16 query rows; mma.sync m16n8k16 bf16.
-// smem rows are 64 B (32 bf16); the 16-byte chunk index is XOR-swizzled with (row >> 1) & 3 so that
-// ldmatrix (8 rows x 16 B) is bank-conflict free.
-// ------------------------------------------------------------------------------------------------
-constexpr int LOCAL_SMEM_BYTES = 7 * WIN * 64;   // Q (1 window) + K (3) + V (3), 64 B per row
-constexpr int LOCAL_CH = 64;                     // keys per online-softmax step (32 fits 4 CTAs / SM but measured 4 % slower)
-constexpr int LOCAL_NT = LOCAL_CH / 8;           // 8-key score tiles per step
-
 // 2^x as a single MUFU.EX2 (exp2f() adds denormal range handling: 3 more instructions per element)
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
@@ -31,132 +20,10 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return y;
 }
 
+// 64-byte rows (32 bf16): the 16-byte chunk index is XOR-swizzled with (row >> 1) & 3 so that ldmatrix (8 rows x 16 B) is
+// bank-conflict free
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
-__global__ void __launch_bounds__(256, LOCAL_CH == 32 ? 4 : 3)
-local_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
-                       float scale_log2e, int reverse) {
-  ptx::pdl_sync();
-  // reverse: walk (sample, window) last-to-first so the QKV rows written last (still in L2) are read first
-  const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,
-            b = reverse ? int(gridDim.z) - 1 - int(blockIdx.z) : int(blockIdx.z);
-  const int nw = L / WIN;
-  const int w_lo = max(w - 1, 0), w_hi = min(w + 1, nw - 1);
-  const int nkeys = (w_hi - w_lo + 1) * WIN;
-  const size_t head_stride = size_t(L) * DH;
-  const size_t plane = size_t(B) * H * head_stride;
-  const __nv_bfloat16* qg = qkv + (size_t(b) * H + h) * head_stride + size_t(w) * WIN * DH;
-  const __nv_bfloat16* kg = qkv + plane + (size_t(b) * H + h) * head_stride + size_t(w_lo) * WIN * DH;
-  const __nv_bfloat16* vg = kg + plane;
-
-  extern __shared__ __align__(128) uint8_t attn_smem[];     // LOCAL_SMEM_BYTES, opt-in dynamic
-  uint8_t* sQ = attn_smem;
-  uint8_t* sK = sQ + WIN * 64;
-  uint8_t* sV = sK + 3 * WIN * 64;
-
-  const int tid = threadIdx.x;
-  const uint32_t sq = ptx::smem_u32(sQ), sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV);
-  for (int i = tid; i < WIN * 4; i += 256) {
-    const int row = i >> 2, ch = i & 3;
-    ptx::cp_async_16(sq + swz(row, ch), qg + row * DH + ch * 8);
-  }
-  for (int i = tid; i < nkeys * 4; i += 256) {
-    const int row = i >> 2, ch = i & 3;
-    ptx::cp_async_16(sk + swz(row, ch), kg + row * DH + ch * 8);
-    ptx::cp_async_16(sv + swz(row, ch), vg + row * DH + ch * 8);
-  }
-  ptx::cp_async_commit();
-  ptx::cp_async_wait<0>();
-  __syncthreads();
-
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int q0 = warp * 16;
-
-  // Q fragments for the two k-steps (d 0..15, 16..31)
-  uint32_t qa[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    const int row = q0 + (lane & 7) + 8 * ((lane >> 3) & 1);
-    const int ch = ks * 2 + (lane >> 4);
-    ptx::ldmatrix_x4(sq + swz(row, ch), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
-  }
-
-  // ldmatrix addresses: the swizzle term depends on the lane only (key rows advance in multiples of 8), so the
-  // per-lane part is computed once and the loop adds compile-time offsets (no integer address math per MMA).
-  const int lrow = lane & 7, lx = (lrow >> 1) & 3;
-  const uint32_t laneK = uint32_t(lrow * 64 + (((lane >> 3) ^ lx) << 4));                       // K: row lrow, chunk lane>>3
-  const uint32_t laneV0 = uint32_t((lrow + 8 * ((lane >> 3) & 1)) * 64 + (((lane >> 4) ^ lx) << 4));   // V: d-chunks 0,1
-  const uint32_t laneV1 = laneV0 ^ 32u;                                                          // V: d-chunks 2,3
-
-  float o[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-  float ol[4] = {0.f, 0.f, 0.f, 0.f};   // row sums, accumulated by the tensor core (every column holds the sum)
-  float m0 = -INFINITY, m1 = -INFINITY;
-
-  for (int kc = 0; kc < nkeys; kc += LOCAL_CH) {
-    const uint32_t kbase = sk + uint32_t(kc) * 64u + laneK, vbase0 = sv + uint32_t(kc) * 64u + laneV0,
-                   vbase1 = sv + uint32_t(kc) * 64u + laneV1;
-    float s[LOCAL_NT][4];
-#pragma unroll
-    for (int nt = 0; nt < LOCAL_NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      uint32_t kb0, kb1, kb2, kb3;
-      ptx::ldmatrix_x4(kbase + nt * 512, kb0, kb1, kb2, kb3);
-      ptx::mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kb0, kb1);
-      ptx::mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kb2, kb3);
-    }
-    float cm0 = -INFINITY, cm1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < LOCAL_NT; ++nt) {
-      cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
-      cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-    const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
-    const float corr0 = fast_ex2((m0 - mn0) * scale_log2e), corr1 = fast_ex2((m1 - mn1) * scale_log2e);
-    m0 = mn0; m1 = mn1;
-    const float ms0 = mn0 * scale_log2e, ms1 = mn1 * scale_log2e;
-#pragma unroll
-    for (int dt = 0; dt < 4; ++dt) {
-      o[dt][0] *= corr0; o[dt][1] *= corr0;
-      o[dt][2] *= corr1; o[dt][3] *= corr1;
-    }
-    ol[0] *= corr0; ol[1] *= corr0; ol[2] *= corr1; ol[3] *= corr1;
-#pragma unroll
-    for (int kk = 0; kk < LOCAL_NT / 2; ++kk) {        // 16 keys per step
-      const uint32_t a0 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk][0], scale_log2e, -ms0)), fast_ex2(fmaf(s[2 * kk][1], scale_log2e, -ms0)));
-      const uint32_t a1 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk][2], scale_log2e, -ms1)), fast_ex2(fmaf(s[2 * kk][3], scale_log2e, -ms1)));
-      const uint32_t a2 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk + 1][0], scale_log2e, -ms0)), fast_ex2(fmaf(s[2 * kk + 1][1], scale_log2e, -ms0)));
-      const uint32_t a3 = ptx::pack_bf16x2(fast_ex2(fmaf(s[2 * kk + 1][2], scale_log2e, -ms1)), fast_ex2(fmaf(s[2 * kk + 1][3], scale_log2e, -ms1)));
-      uint32_t v0, v1, v2, v3;
-      ptx::ldmatrix_x4_trans(vbase0 + kk * 1024, v0, v1, v2, v3);
-      ptx::mma_bf16_16816(o[0], a0, a1, a2, a3, v0, v1);
-      ptx::mma_bf16_16816(o[1], a0, a1, a2, a3, v2, v3);
-      ptx::ldmatrix_x4_trans(vbase1 + kk * 1024, v0, v1, v2, v3);
-      ptx::mma_bf16_16816(o[2], a0, a1, a2, a3, v0, v1);
-      ptx::mma_bf16_16816(o[3], a0, a1, a2, a3, v2, v3);
-      // row sums of the SAME bf16 P the numerator uses: one more MMA against an all-ones B fragment
-      ptx::mma_bf16_16816(ol, a0, a1, a2, a3, 0x3F803F80u, 0x3F803F80u);
-    }
-  }
-  const float inv0 = 1.f / ol[0], inv1 = 1.f / ol[2];
-  const int D = H * DH;
-  const size_t row0 = size_t(b) * L + size_t(w) * WIN + q0 + g;
-  __nv_bfloat16* o0 = out + row0 * D + h * DH + 2 * t;
-  __nv_bfloat16* o1 = o0 + size_t(8) * D;
-#pragma unroll
-  for (int dt = 0; dt < 4; ++dt) {
-    *reinterpret_cast<uint32_t*>(o0 + dt * 8) = ptx::pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
-    *reinterpret_cast<uint32_t*>(o1 + dt * 8) = ptx::pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Linear attention (global heads): q <- softmax_d(q) * dh^-0.5 ; k <- softmax over the L tokens ;
@@ -403,285 +270,8 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Linear attention, one CLUSTER of CL CTAs per (global head, sample) (round 2).  Same arithmetic as above; the sequence
-// is split over CL x 4 warps instead of 4, so a (b, h) pair is CL x more CTAs in flight (B = 64: 2048 CTAs at CL = 4
-// instead of 512) and every warp's dependent chain (stream k / v -> merge -> stream q) is CL x shorter: the kernel is
-// latency bound, not byte bound (round 1: 0.47 of the HBM rate at 57 % issue utilisation).
-//   phase A   each warp: exp(k - reference)^T v over its L / (4 CL) rows (mma.sync, lazy column reference)
-//   merge 1   the CTA's four partial (max, denominator, ctx) sets -> one fp32 set in its own shared memory
-//   merge 2   cluster barrier; every CTA reads the CL sets through distributed shared memory -> ctx^T bf16 (q scale folded)
-//   phase B   softmax(q) ctx for its own rows
-// CL is the cluster size of the launch (1, 2, 4 or 8; L % (128 CL) == 0).
-// ------------------------------------------------------------------------------------------------
-constexpr int LINC_PART_FLOATS = DH * DH + 2 * DH;                       // ctx [32][32], max [32], denominator [32]
-constexpr int LINC_SMEM_BYTES = 4 * LIN_WARP_BYTES + LINC_PART_FLOATS * 4 + DH * 64;   // warp partials alias the stage buffers
-
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
-  float v;
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
-      "ld.shared::cluster.f32 %0, [ra];\n\t}"
-      : "=f"(v)
-      : "r"(local_addr), "r"(rank)
-      : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-
-__global__ void __launch_bounds__(128)
-linear_attention_cl_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
-                           int NL, float q_scale, int reverse) {
-  ptx::pdl_sync();
-  const int CL = int(cluster_nctarank()), crank = int(ptx::cluster_ctarank());
-  const int h = NL + int(blockIdx.x) / CL, b = reverse ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
-  const size_t head_stride = size_t(L) * DH;
-  const size_t plane = size_t(B) * H * head_stride;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int rows_per_warp = L / (4 * CL);
-  const int nchunks = rows_per_warp / LIN_CH;
-  const int row_first = (crank * 4 + warp) * rows_per_warp;               // first sequence position of this warp
-  const __nv_bfloat16* qg = qkv + (size_t(b) * H + h) * head_stride + size_t(row_first) * DH;
-  const __nv_bfloat16* kg = qg + plane;
-  const __nv_bfloat16* vg = kg + plane;
-
-  extern __shared__ __align__(128) uint8_t linc_smem[];
-  const uint32_t stage0 = ptx::smem_u32(linc_smem) + warp * LIN_WARP_BYTES;
-  float* pctx = reinterpret_cast<float*>(linc_smem);                       // [4][32][32] + [4][32] + [4][32]: aliases the stages (17 KB of 32)
-  float* pmax = pctx + 4 * DH * DH;
-  float* pden = pmax + 4 * DH;
-  float* part = reinterpret_cast<float*>(linc_smem + 4 * LIN_WARP_BYTES);  // this CTA's merged set: ctx, max, denominator
-  uint8_t* ctxT = reinterpret_cast<uint8_t*>(part + LINC_PART_FLOATS);     // [32 e][32 d] bf16, swizzled rows
-
-  // ---------------------------------------------------------------- phase A
-  float acc[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
-  float mrun[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
-  float den[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-
-  lin_load_chunk(stage0, kg, lane);
-  lin_load_chunk(stage0 + LIN_CH * 64, vg, lane);
-  ptx::cp_async_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
-    if (c + 1 < nchunks) {
-      const uint32_t nxt = stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES;
-      lin_load_chunk(nxt, kg + size_t(c + 1) * LIN_CH * DH, lane);
-      lin_load_chunk(nxt + LIN_CH * 64, vg + size_t(c + 1) * LIN_CH * DH, lane);
-      ptx::cp_async_commit();
-      ptx::cp_async_wait<1>();
-    } else {
-      ptx::cp_async_wait<0>();
-    }
-    __syncwarp();
-    const uint32_t sk = cur, sv = cur + LIN_CH * 64;
-    uint32_t kr[2][2][4];                          // [k-step][m-tile(d)][a0..a3], raw k as A^T fragments
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-        ptx::ldmatrix_x4_trans(sk + swz(ks * 16 + (lane & 7) + 8 * (lane >> 4), 2 * mt + ((lane >> 3) & 1)),
-                               kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3]);
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float cm = -INFINITY;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const float2 x0 = bf2_to_f2(kr[ks][mt][hf]), x1 = bf2_to_f2(kr[ks][mt][hf + 2]);
-          cm = fmaxf(cm, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
-        }
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-        if (cm > mrun[mt][hf] + LIN_LAZY) {
-          const float f = __expf(mrun[mt][hf] - cm);       // 0 on the first chunk
-          mrun[mt][hf] = cm;
-          den[mt][hf] *= f;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            acc[mt][nt][2 * hf] *= f;
-            acc[mt][nt][2 * hf + 1] *= f;
-          }
-        }
-        const float ml2 = mrun[mt][hf] * LOG2E;
-        float dsum = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-          for (int q2 = 0; q2 < 2; ++q2) {
-            const float2 x = bf2_to_f2(kr[ks][mt][hf + 2 * q2]);
-            const float e0 = fast_ex2(fmaf(x.x, LOG2E, -ml2)), e1 = fast_ex2(fmaf(x.y, LOG2E, -ml2));
-            dsum += e0 + e1;
-            kr[ks][mt][hf + 2 * q2] = ptx::pack_bf16x2(e0, e1);
-          }
-        den[mt][hf] += dsum;
-      }
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-      for (int ep = 0; ep < 2; ++ep) {
-        uint32_t v0, v1, v2, v3;
-        ptx::ldmatrix_x4_trans(sv + swz(ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4)), v0, v1, v2, v3);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          ptx::mma_bf16_16816(acc[mt][2 * ep], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v0, v1);
-          ptx::mma_bf16_16816(acc[mt][2 * ep + 1], kr[ks][mt][0], kr[ks][mt][1], kr[ks][mt][2], kr[ks][mt][3], v2, v3);
-        }
-      }
-    __syncwarp();
-  }
-  // q chunk 0 can start now: it lands in stage 1 of this warp's buffer, beyond the 17 KB the warp partials alias
-  // (the partials occupy the first 17 KB of the 32 KB of stage space = warps 0, 1 and 256 bytes of warp 2: so only
-  // warp 3 may prefetch early; the others wait for the merge)
-  __syncthreads();                                 // every warp is done reading its stages before the partials overwrite them
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      float dn = den[mt][hf];
-      dn += __shfl_xor_sync(0xffffffffu, dn, 1);
-      dn += __shfl_xor_sync(0xffffffffu, dn, 2);
-      const int d = 16 * mt + 8 * hf + g;
-      if (t == 0) {
-        pmax[warp * DH + d] = mrun[mt][hf];
-        pden[warp * DH + d] = dn;
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        float* dst = pctx + (size_t(warp) * DH + d) * DH + 8 * nt + 2 * t;
-        dst[0] = acc[mt][nt][2 * hf];
-        dst[1] = acc[mt][nt][2 * hf + 1];
-      }
-    }
-  __syncthreads();
-  // ---------------------------------------------------------------- merge 1: four warps -> this CTA's set
-  for (int idx = threadIdx.x; idx < DH * DH; idx += 128) {
-    const int d = idx >> 5, e = idx & 31;
-    const float m0 = pmax[d], m1 = pmax[DH + d], m2 = pmax[2 * DH + d], m3 = pmax[3 * DH + d];
-    const float mm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    const float f0 = __expf(m0 - mm), f1 = __expf(m1 - mm), f2 = __expf(m2 - mm), f3 = __expf(m3 - mm);
-    part[idx] = pctx[(0 * DH + d) * DH + e] * f0 + pctx[(1 * DH + d) * DH + e] * f1 +
-                pctx[(2 * DH + d) * DH + e] * f2 + pctx[(3 * DH + d) * DH + e] * f3;
-    if (e == 0) {
-      part[DH * DH + d] = mm;
-      part[DH * DH + DH + d] = pden[d] * f0 + pden[DH + d] * f1 + pden[2 * DH + d] * f2 + pden[3 * DH + d] * f3;
-    }
-  }
-  // ---------------------------------------------------------------- merge 2: CL CTAs -> ctx^T (bf16), q scale folded in
-  ptx::cluster_sync_all();                         // also a CTA barrier: the stage buffers are free for q from here on
-  lin_load_chunk(stage0, qg, lane);
-  ptx::cp_async_commit();
-  const uint32_t part_addr = ptx::smem_u32(part);
-  for (int idx = threadIdx.x; idx < DH * DH; idx += 128) {
-    const int d = idx >> 5, e = idx & 31;
-    float mm = -INFINITY;
-    for (int r = 0; r < CL; ++r) mm = fmaxf(mm, ld_dsmem_f32(part_addr + (DH * DH + d) * 4, r));
-    float num = 0.f, dn = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float f = __expf(ld_dsmem_f32(part_addr + (DH * DH + d) * 4, r) - mm);
-      num = fmaf(ld_dsmem_f32(part_addr + idx * 4, r), f, num);
-      dn = fmaf(ld_dsmem_f32(part_addr + (DH * DH + DH + d) * 4, r), f, dn);
-    }
-    *reinterpret_cast<__nv_bfloat16*>(ctxT + swz(e, d >> 3) + (d & 7) * 2) = __float2bfloat16_rn(num / dn * q_scale);
-  }
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading the peers' sets; waited for at the end
-  __syncthreads();
-  // ---------------------------------------------------------------- phase B
-  uint32_t cb[4][4];                               // ctx as B fragments: [n-tile(e)][b0 ks0, b1 ks0, b0 ks1, b1 ks1]
-  const uint32_t sc = ptx::smem_u32(ctxT);
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
-    ptx::ldmatrix_x4(sc + swz(8 * nt + (lane & 7), lane >> 3), cb[nt][0], cb[nt][1], cb[nt][2], cb[nt][3]);
-  const int D = H * DH;
-  for (int c = 0; c < nchunks; ++c) {
-    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
-    if (c + 1 < nchunks) {
-      lin_load_chunk(stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES, qg + size_t(c + 1) * LIN_CH * DH, lane);
-      ptx::cp_async_commit();
-      ptx::cp_async_wait<1>();
-    } else {
-      ptx::cp_async_wait<0>();
-    }
-    __syncwarp();
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {               // 16 query rows each
-      uint32_t qa[2][4];
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        ptx::ldmatrix_x4(cur + swz(mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)), qa[ks][0],
-                         qa[ks][1], qa[ks][2], qa[ks][3]);
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float2 x[4];
-        x[0] = bf2_to_f2(qa[0][hf]); x[1] = bf2_to_f2(qa[0][hf + 2]);
-        x[2] = bf2_to_f2(qa[1][hf]); x[3] = bf2_to_f2(qa[1][hf + 2]);
-        float mx = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)),
-                         fmaxf(fmaxf(x[2].x, x[2].y), fmaxf(x[3].x, x[3].y)));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        float s = 0.f;
-        const float mxl = mx * LOG2E;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          x[i].x = fast_ex2(fmaf(x[i].x, LOG2E, -mxl));
-          x[i].y = fast_ex2(fmaf(x[i].y, LOG2E, -mxl));
-          s += x[i].x + x[i].y;
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float inv = 1.f / s;
-        qa[0][hf] = ptx::pack_bf16x2(x[0].x * inv, x[0].y * inv);
-        qa[0][hf + 2] = ptx::pack_bf16x2(x[1].x * inv, x[1].y * inv);
-        qa[1][hf] = ptx::pack_bf16x2(x[2].x * inv, x[2].y * inv);
-        qa[1][hf + 2] = ptx::pack_bf16x2(x[3].x * inv, x[3].y * inv);
-      }
-      float o[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-        ptx::mma_bf16_16816(o[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], cb[nt][0], cb[nt][1]);
-        ptx::mma_bf16_16816(o[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], cb[nt][2], cb[nt][3]);
-      }
-      const size_t row0 = size_t(b) * L + size_t(row_first) + size_t(c) * LIN_CH + mt * 16 + g;
-      __nv_bfloat16* o0 = out + row0 * D + h * DH + 2 * t;
-      __nv_bfloat16* o1 = o0 + size_t(8) * D;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<uint32_t*>(o0 + nt * 8) = ptx::pack_bf16x2(o[nt][0], o[nt][1]);
-        *reinterpret_cast<uint32_t*>(o1 + nt * 8) = ptx::pack_bf16x2(o[nt][2], o[nt][3]);
-      }
-    }
-    __syncwarp();
-  }
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // no CTA leaves while a peer may still read its set
-}
-
-
-// ================================================================================================
-// Local attention on the 5th-generation tensor cores (tcgen05), one CTA (4 warps) per (window, head, sample).
-//   TMA (64B swizzle) stages Q [128 x 32], K_w and V_w [128 x 32] of the 1-3 visible key windows.
-//   per key window j:  S_j = Q K_j^T   (tcgen05.mma 128 x 128 x 32, fp32 in TMEM, operands K-major SW64)
-//                      softmax numerators, thread = query row: two sweeps over S_j in TMEM (max, then
-//                      exp2 / row sum / bf16 pack), P_j written to smem as a K-major SW128 operand
-//                      O_j = P_j V_j   (tcgen05.mma 128 x 32 x 128; V is consumed as stored, [key][d] rows of
-//                      64 bytes = the MN-major SW64 canonical layout)
-//                      o <- o * corr + O_j in registers (online softmax across windows)
-// TMEM: 128 columns S + 32 columns O -> 256 allocated, two CTAs per SM.
-// ================================================================================================
-constexpr int TC_TILE = WIN * 64;                              // one 128 x 32 bf16 tile (64-byte rows)
-constexpr int TC_SMEM_BYTES = 7 * TC_TILE + 2 * WIN * 128 + 1024;   // Q + 3 K + 3 V + P (two 128 x 64 SW128 blocks) + align
+// one 128 x 32 bf16 tile (64-byte rows) as TMA writes it with the 64-byte swizzle
+constexpr int TC_TILE = WIN * 64;
 
 // smem matrix descriptor, 64-byte rows with the 64-byte swizzle (SBO = 8 rows x 64 B); used both for the
 // K-major Q / K tiles and for V as an MN-major B operand (SBO = stride between 8-key groups)
@@ -695,1064 +285,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(256)
-local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
-                          int L, float scale_log2e, int reverse) {
-  ptx::pdl_sync();
-  // 8 warps: two threads per query row.  Thread (row = tid & 127, half = tid >> 7) owns keys [64*half, +64) of each
-  // 128-key window (one K-major SW128 block of P) and output features [16*half, +16).
-  const int w = reverse ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x), h = blockIdx.y,
-            b = reverse ? int(gridDim.z) - 1 - int(blockIdx.z) : int(blockIdx.z);
-  const int nw = L / WIN;
-  const int w_lo = max(w - 1, 0), w_hi = min(w + 1, nw - 1);
-  const int nwin = w_hi - w_lo + 1;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & 127, half = tid >> 7;
-
-  extern __shared__ uint8_t tc_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + TC_TILE;
-  uint8_t* sV = smem + 4 * TC_TILE;
-  const uint32_t sP = ptx::smem_u32(smem + 7 * TC_TILE);
-  __shared__ uint64_t bar_load, bar_s, bar_o;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float xmax[2][2][WIN];          // [window parity][half][row]: partial row maxima
-  __shared__ float xsum[2][WIN];             // [half][row]: partial row sums (end of kernel)
-
-  if (tid == 0) {
-    ptx::tma_prefetch_desc(&tm_qkv);
-    ptx::mbar_init(&bar_load, 1);
-    ptx::mbar_init(&bar_s, 1);
-    ptx::mbar_init(&bar_o, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 0) {
-    ptx::tmem_alloc(&tmem_slot, 256);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t t_s = tmem + ((uint32_t(warp & 3) * 32u) << 16) + half * 64;   // S columns [64*half, +64)
-  const uint32_t t_o = tmem + ((uint32_t(warp & 3) * 32u) << 16) + 128 + half * 16;   // O columns [16*half, +16)
-
-  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-  auto issue_s = [&](int j) {                 // S = Q K_j^T : two k-steps of 16 features
-    const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ));
-    const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sK + j * TC_TILE));
-    ptx::umma_bf16(tmem, dq, dk, IDESC_S, 0);
-    ptx::umma_bf16(tmem, dq + 2, dk + 2, IDESC_S, 1);
-    ptx::umma_commit(&bar_s);
-  };
-  auto issue_o = [&](int j) {                 // O_j = P_j V_j : eight k-steps of 16 keys
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint64_t dp = ptx::umma_desc_sw128(sP + (ks >> 2) * (WIN * 128) + (ks & 3) * 32);
-      const uint64_t dv = umma_desc_sw64(ptx::smem_u32(sV + j * TC_TILE) + ks * 16 * 64);
-      ptx::umma_bf16(tmem + 128, dp, dv, IDESC_O, ks != 0);
-    }
-    ptx::umma_commit(&bar_o);
-  };
-
-  if (tid == 0) {
-    const int plane = B * H * L;
-    const int rq = (b * H + h) * L;
-    ptx::mbar_arrive_expect_tx(&bar_load, (1 + 2 * nwin) * TC_TILE);
-    ptx::tma_load_2d(sQ, &tm_qkv, &bar_load, 0, rq + w * WIN);
-    for (int j = 0; j < nwin; ++j) {
-      ptx::tma_load_2d(sK + j * TC_TILE, &tm_qkv, &bar_load, 0, plane + rq + (w_lo + j) * WIN);
-      ptx::tma_load_2d(sV + j * TC_TILE, &tm_qkv, &bar_load, 0, 2 * plane + rq + (w_lo + j) * WIN);
-    }
-  }
-  ptx::mbar_wait(&bar_load, 0);
-  if (tid == 0) {
-    ptx::tc_fence_after();
-    issue_s(0);
-  }
-
-  float o[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) o[i] = 0.f;
-  float m = -INFINITY, l = 0.f;
-
-  for (int j = 0; j < nwin; ++j) {
-    ptx::mbar_wait(&bar_s, j & 1);
-    ptx::tc_fence_after();
-    // sweep 1: this thread's 64 scores -> partial row maximum, exchanged with the other half through smem
-    uint32_t r0[32], r1[32];
-    ptx::tmem_ld_32x32(t_s, r0);
-    ptx::tmem_ld_32x32(t_s + 32, r1);
-    ptx::tmem_ld_wait();
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-    xmax[j & 1][half][row] = mx;
-    __syncthreads();
-    mx = fmaxf(mx, xmax[j & 1][half ^ 1][row]);
-    const float mn = fmaxf(m, mx);
-    const float corr = fast_ex2((m - mn) * scale_log2e);
-    const float ms = mn * scale_log2e;
-    m = mn;
-    // sweep 2 (from registers): numerators, partial row sum, bf16 pack -> this half's 64-key SW128 block of P
-    float rs = 0.f;
-    const uint32_t pbase = sP + half * (WIN * 128) + row * 128;
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float s0 = __uint_as_float(c2 == 0 ? r0[2 * i] : r1[2 * i]);
-        const float s1 = __uint_as_float(c2 == 0 ? r0[2 * i + 1] : r1[2 * i + 1]);
-        const float p0 = fast_ex2(fmaf(s0, scale_log2e, -ms));
-        const float p1 = fast_ex2(fmaf(s1, scale_log2e, -ms));
-        rs += p0 + p1;
-        pk[i] = ptx::pack_bf16x2(p0, p1);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = c2 * 4 + q;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbase + ((chunk ^ (row & 7)) << 4)), "r"(pk[4 * q]),
-                     "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                     : "memory");
-      }
-    }
-    l = l * corr + rs;
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      issue_o(j);
-      if (j + 1 < nwin) issue_s(j + 1);
-    }
-    ptx::mbar_wait(&bar_o, j & 1);
-    ptx::tc_fence_after();
-    {
-      uint32_t ro[16];
-      ptx::tmem_ld_32x16(t_o, ro);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(ro[i]));
-    }
-  }
-  xsum[half][row] = l;
-  ptx::tc_fence_before();
-  __syncthreads();
-  const float inv = 1.f / (l + xsum[half ^ 1][row]);
-  const int D = H * DH;
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t(b) * L + size_t(w) * WIN + row) * D + h * DH + half * 16);
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-    dst[i] = make_uint4(ptx::pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), ptx::pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                        ptx::pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv), ptx::pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
-  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
-}
-
-
-// ================================================================================================
-// Windowed softmax attention on tcgen05, second schedule (variant 2): persistent, one CTA per SM, warp-specialised.
-//   warp 0      TMA producer: Q tiles (double buffered) and K/V tiles (ring of TC2_NST stages), 64-byte swizzle
-//   warp 1      MMA issuer:  S_g = Q K_g^T into one of three 128-column TMEM slots, later O (+)= P_g V_g with P read
-//               straight from TMEM (A operand in tensor memory), V consumed as stored (MN-major SW64 B operand)
-//   warps 2-9   softmax, two threads per query row (thread = TMEM lane, warps w and w+4 split the columns): per key
-//               block row maximum, exp2 against a lazily updated reference maximum, row sum, bf16 pack, written back
-//               over the thread's own S columns with tcgen05.st
-// One "item" = (window w, sample b, head h); its key blocks are windows w-1, w, w+1 that exist (2 or 3).  Blocks are
-// numbered g = 0, 1, ... in the order a CTA meets them: TMEM slot g % 3, smem stage g % TC2_NST.  The issuer keeps S up
-// to three blocks ahead of PV, so the next item's scores are computed while this item's exponentials run and the
-// MUFU pipe (one exp per score, the floor of this kernel) is the only thing the softmax warps wait for.
-// TMEM: 3 x 128 (S / P) + 2 x 32 (O, by item parity) = 448 of 512 columns.
-// ================================================================================================
-constexpr int TC2_NST = 6;
-constexpr int TC2_THREADS = 320;
-constexpr int TC2_SMEM_BYTES = (2 + 2 * TC2_NST) * TC_TILE + 1024;
-
-struct Tc2Cursor {
-  int i, kb, nkb, w, b, h, w_lo, g, n;
-  bool valid;
-};
-
-__global__ void __launch_bounds__(TC2_THREADS, 1)
-local_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
-                           int L, int NL, float scale_log2e, int reverse) {
-  const int nw = L / WIN;
-  const int total = nw * B * NL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  extern __shared__ uint8_t tc2_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc2_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // 2 tiles
-  uint8_t* sKV = smem + 2 * TC_TILE;           // TC2_NST x (K tile, V tile)
-  __shared__ uint64_t q_full[2], q_free[2], kv_full[TC2_NST], kv_free[TC2_NST], s_full[3], p_ready[3], s_free[3],
-      o_full[2], o_free[2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ float xmax[2][2][WIN], xsum[2][2][WIN];      // [block or item parity][half][row]
-
-  if (tid == 0) {
-    ptx::tma_prefetch_desc(&tm_qkv);
-    for (int k = 0; k < 2; ++k) {
-      ptx::mbar_init(&q_full[k], 1);
-      ptx::mbar_init(&q_free[k], 1);
-      ptx::mbar_init(&o_full[k], 1);
-      ptx::mbar_init(&o_free[k], 8);
-    }
-    for (int k = 0; k < TC2_NST; ++k) {
-      ptx::mbar_init(&kv_full[k], 1);
-      ptx::mbar_init(&kv_free[k], 1);
-    }
-    for (int k = 0; k < 3; ++k) {
-      ptx::mbar_init(&s_full[k], 1);
-      ptx::mbar_init(&p_ready[k], 8);
-      ptx::mbar_init(&s_free[k], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  ptx::pdl_sync();
-
-  // the i-th item of this CTA
-  auto seek = [&](Tc2Cursor& c) {
-    const int f = int(blockIdx.x) + c.i * int(gridDim.x);
-    c.valid = f < total;
-    if (!c.valid) return;
-    const int ff = reverse ? total - 1 - f : f;
-    c.h = ff % NL;
-    c.b = (ff / NL) % B;
-    c.w = ff / (NL * B);
-    c.w_lo = max(c.w - 1, 0);
-    c.nkb = min(c.w + 1, nw - 1) - c.w_lo + 1;
-    c.kb = 0;
-  };
-  auto start = [&](Tc2Cursor& c) { c.i = 0; c.g = 0; c.n = 0; seek(c); };
-  auto advance = [&](Tc2Cursor& c) {
-    ++c.g;
-    if (++c.kb == c.nkb) { ++c.i; ++c.n; seek(c); }
-  };
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int plane = B * H * L;
-      Tc2Cursor c;
-      for (start(c); c.valid; advance(c)) {
-        const int rq = (c.b * H + c.h) * L;
-        if (c.kb == 0) {
-          const int qb = c.n & 1;
-          ptx::mbar_wait_parked(&q_free[qb], ((c.n >> 1) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&q_full[qb], TC_TILE);
-          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &q_full[qb], 0, rq + c.w * WIN);
-        }
-        const int st = c.g % TC2_NST;
-        ptx::mbar_wait_parked(&kv_free[st], ((c.g / TC2_NST) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * TC_TILE);
-        ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &kv_full[st], 0, plane + rq + (c.w_lo + c.kb) * WIN);
-        ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kb) * WIN);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      auto issue_s = [&](const Tc2Cursor& c) {
-        const int qb = c.n & 1, st = c.g % TC2_NST, slot = c.g % 3;
-        if (c.kb == 0) ptx::mbar_wait_parked(&q_full[qb], (c.n >> 1) & 1);
-        ptx::mbar_wait_parked(&kv_full[st], (c.g / TC2_NST) & 1);
-        ptx::mbar_wait_parked(&s_free[slot], ((c.g / 3) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
-        const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE));
-        ptx::umma_bf16(tmem + slot * 128, dq, dk, IDESC_S, 0);
-        ptx::umma_bf16(tmem + slot * 128, dq + 2, dk + 2, IDESC_S, 1);
-        ptx::umma_commit(&s_full[slot]);
-        if (c.kb == c.nkb - 1) ptx::umma_commit(&q_free[qb]);
-      };
-      auto issue_pv = [&](const Tc2Cursor& c) {
-        const int ob = c.n & 1, st = c.g % TC2_NST, slot = c.g % 3;
-        if (c.kb == 0) ptx::mbar_wait_parked(&o_free[ob], ((c.n >> 1) & 1) ^ 1);
-        ptx::mbar_wait_parked(&p_ready[slot], (c.g / 3) & 1);
-        ptx::tc_fence_after();
-        const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          ptx::umma_bf16_ts(tmem + 384 + ob * 32, tmem + slot * 128 + (ks >> 2) * 64 + (ks & 3) * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
-                            (c.kb | ks) != 0);
-        ptx::umma_commit(&s_free[slot]);
-        ptx::umma_commit(&kv_free[st]);
-        if (c.kb == c.nkb - 1) ptx::umma_commit(&o_full[ob]);
-      };
-      Tc2Cursor sc, pc;
-      start(sc);
-      start(pc);
-      while (pc.valid) {
-        while (sc.valid && sc.g < pc.g + 3) {
-          issue_s(sc);
-          advance(sc);
-        }
-        issue_pv(pc);
-        advance(pc);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + output (8 warps)
-    // Block-granular online softmax with a lazily updated reference maximum: the first key block of an item sets
-    // m_ref to its row maximum; a later block rescales O and the row sum only when its maximum exceeds m_ref by more
-    // than 2^8 (P stays <= 256, exact in bf16's range), which real score distributions almost never do.  So each S
-    // slot is consumed, turned into P and released as soon as it is produced, and the issuer computes the next
-    // blocks' / next item's scores under this block's exponentials.  The output of item n is read after the first
-    // block of item n+1 (O is double buffered), when its last PV has long completed.
-    // (Four threads per row / 16 softmax warps measured slower: 160.9 vs 154.5 us per layer-call with the linear heads.)
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
-    const int pair_bar = 1 + quarter;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
-    const int D = H * DH;
-    constexpr float LAZY_LOG2 = 8.0f;
-    float m_ref = 0.f, rs = 0.f;
-    bool pend = false;
-    int p_n = 0;
-    float p_rs = 0.f;
-    __nv_bfloat16* p_dst = nullptr;
-    auto epilogue = [&]() {
-      const int ob = p_n & 1;
-      xsum[ob][half][row] = p_rs;
-      pair_sync();
-      const float inv = 1.f / (p_rs + xsum[ob][half ^ 1][row]);
-      ptx::mbar_wait(&o_full[ob], (p_n >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t ro[16];
-      ptx::tmem_ld_32x16(lane_base + 384 + ob * 32 + half * 16, ro);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&o_free[ob]);
-      uint4* dst = reinterpret_cast<uint4*>(p_dst);
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * inv, __uint_as_float(ro[8 * k + 1]) * inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * inv, __uint_as_float(ro[8 * k + 3]) * inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * inv, __uint_as_float(ro[8 * k + 5]) * inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * inv, __uint_as_float(ro[8 * k + 7]) * inv));
-    };
-    Tc2Cursor c;
-    for (start(c); c.valid; advance(c)) {
-      const int g = c.g, slot = g % 3;
-      const uint32_t t_s = lane_base + slot * 128 + half * 64;       // this thread's 64 score columns of the block
-      ptx::mbar_wait(&s_full[slot], (g / 3) & 1);
-      ptx::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(t_s, r0);
-      ptx::tmem_ld_32x32(t_s + 32, r1);
-      ptx::tmem_ld_wait();
-      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        b0 = fmaxf(b0, __uint_as_float(r0[2 * k]));
-        b1 = fmaxf(b1, __uint_as_float(r0[2 * k + 1]));
-        b2 = fmaxf(b2, __uint_as_float(r1[2 * k]));
-        b3 = fmaxf(b3, __uint_as_float(r1[2 * k + 1]));
-      }
-      float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
-      xmax[g & 1][half][row] = bm;
-      pair_sync();
-      bm = fmaxf(bm, xmax[g & 1][half ^ 1][row]);
-      if (c.kb == 0) {
-        m_ref = bm;
-        rs = 0.f;
-      } else {
-        const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
-          // rare: O (+ the row sum) of the rows that need it move to the new reference.  Every PV issued so far has
-          // to have landed first: PV(g-1)'s commit completes s_free of its slot.
-          const int gp = g - 1;
-          ptx::mbar_wait(&s_free[gp % 3], (gp / 3) & 1);
-          ptx::tc_fence_after();
-          const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
-          uint32_t ro[16];
-          const uint32_t t_o = lane_base + 384 + (c.n & 1) * 32 + half * 16;
-          ptx::tmem_ld_32x16(t_o, ro);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 16; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
-          ptx::tmem_st_32x16(t_o, ro);
-          ptx::tmem_st_wait();
-          rs *= f;
-          if (need) m_ref = bm;
-        }
-      }
-      const float ms = m_ref * scale_log2e;
-      // numerators, row sum; P (bf16 pairs) goes over the first 32 of this thread's own 64 S columns, so the two halves
-      // of a row never touch each other's columns
-      uint32_t pk[32];
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
-        const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
-        const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
-        const float p3 = fast_ex2(fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms));
-        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-        pk[k] = ptx::pack_bf16x2(p0, p1);
-        pk[16 + k] = ptx::pack_bf16x2(p2, p3);
-      }
-      rs += (s0 + s1) + (s2 + s3);
-      ptx::tmem_st_32x32(t_s, pk);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_ready[slot]);
-      if (c.kb == 0 && pend) {
-        epilogue();
-        pend = false;
-      }
-      if (c.kb == c.nkb - 1) {
-        pend = true;
-        p_n = c.n;
-        p_rs = rs;
-        p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH + half * 16;
-      }
-    }
-    if (pend) epilogue();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
-}
-
-
-// ================================================================================================
-// Variant 3: the same persistent tcgen05 schedule split into TWO independent streams per CTA (ping-pong).  Each
-// stream owns a TMA producer warp, an MMA issuer warp, four softmax warps (ONE thread per query row: no cross-thread
-// exchange at all), half of the TMEM (3 S/P slots of 64 key columns + 2 O buffers = 256 columns) and its own smem
-// ring, and walks every other item of the CTA.  The two softmax warps that share an SMSP now belong to different
-// streams, so one stream's waits, maxima and TMEM traffic hide under the other's exponentials.
-// A block is 64 keys: (K/V tile of 128 keys, sub-block 0/1); blocks of a stream are numbered g, slot g % 3.
-// ================================================================================================
-constexpr int TC3_NST = 3;
-constexpr int TC3_THREADS = 384;
-constexpr int TC3_STREAM_TILES = 2 + 2 * TC3_NST;
-constexpr int TC3_SMEM_BYTES = 2 * TC3_STREAM_TILES * TC_TILE + 1024;
-
-struct Tc3Bars {
-  uint64_t q_full[2], q_free[2], kv_full[TC3_NST], kv_free[TC3_NST], s_full[3], p_ready[3], s_free[3], o_full[2], o_free[2];
-};
-struct Tc3Cursor {
-  int i, n, t, g, kt, sb, nkt, w, b, h, w_lo;
-  bool valid;
-};
-
-__global__ void __launch_bounds__(TC3_THREADS, 1)
-local_attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
-                           int L, int NL, float scale_log2e, int reverse) {
-  const int nw = L / WIN;
-  const int total = nw * B * NL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stream = warp < 4 ? (warp >> 1) : ((warp - 4) >> 2);
-  const int role = warp < 4 ? (warp & 1) : 2;            // 0 producer, 1 issuer, 2 softmax
-
-  extern __shared__ uint8_t tc3_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc3_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + stream * TC3_STREAM_TILES * TC_TILE;      // 2 tiles
-  uint8_t* sKV = sQ + 2 * TC_TILE;                               // TC3_NST x (K tile, V tile)
-  __shared__ Tc3Bars bars[2];
-  __shared__ uint32_t tmem_slot;
-  Tc3Bars& bar = bars[stream];
-
-  if (tid == 0) {
-    ptx::tma_prefetch_desc(&tm_qkv);
-    for (int s2 = 0; s2 < 2; ++s2) {
-      Tc3Bars& x = bars[s2];
-      for (int k = 0; k < 2; ++k) {
-        ptx::mbar_init(&x.q_full[k], 1);
-        ptx::mbar_init(&x.q_free[k], 1);
-        ptx::mbar_init(&x.o_full[k], 1);
-        ptx::mbar_init(&x.o_free[k], 4);
-      }
-      for (int k = 0; k < TC3_NST; ++k) {
-        ptx::mbar_init(&x.kv_full[k], 1);
-        ptx::mbar_init(&x.kv_free[k], 1);
-      }
-      for (int k = 0; k < 3; ++k) {
-        ptx::mbar_init(&x.s_full[k], 1);
-        ptx::mbar_init(&x.p_ready[k], 4);
-        ptx::mbar_init(&x.s_free[k], 1);
-      }
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = tmem_slot + stream * 256;          // this stream's half: S/P slots at 0, 64, 128; O at 192, 224
-  ptx::pdl_sync();
-
-  auto seek = [&](Tc3Cursor& c) {
-    const int f = int(blockIdx.x) + c.i * int(gridDim.x);
-    c.valid = f < total;
-    if (!c.valid) return;
-    const int ff = reverse ? total - 1 - f : f;
-    c.h = ff % NL;
-    c.b = (ff / NL) % B;
-    c.w = ff / (NL * B);
-    c.w_lo = max(c.w - 1, 0);
-    c.nkt = min(c.w + 1, nw - 1) - c.w_lo + 1;
-    c.kt = 0;
-    c.sb = 0;
-  };
-  auto start = [&](Tc3Cursor& c) { c.i = stream; c.n = 0; c.t = 0; c.g = 0; seek(c); };
-  auto advance = [&](Tc3Cursor& c) {
-    ++c.g;
-    if (++c.sb == 2) {
-      c.sb = 0;
-      ++c.t;
-      if (++c.kt == c.nkt) { c.i += 2; ++c.n; seek(c); }
-    }
-  };
-  auto first_block = [](const Tc3Cursor& c) { return c.kt == 0 && c.sb == 0; };
-  auto last_block = [](const Tc3Cursor& c) { return c.kt == c.nkt - 1 && c.sb == 1; };
-
-  if (role == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int plane = B * H * L;
-      Tc3Cursor c;
-      for (start(c); c.valid; advance(c)) {
-        if (c.sb != 0) continue;
-        const int rq = (c.b * H + c.h) * L;
-        if (c.kt == 0) {
-          const int qb = c.n & 1;
-          ptx::mbar_wait_parked(&bar.q_free[qb], ((c.n >> 1) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
-          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + c.w * WIN);
-        }
-        const int st = c.t % TC3_NST;
-        ptx::mbar_wait_parked(&bar.kv_free[st], ((c.t / TC3_NST) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
-        ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (c.w_lo + c.kt) * WIN);
-        ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kt) * WIN);
-      }
-    }
-  } else if (role == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      auto issue_s = [&](const Tc3Cursor& c) {
-        const int qb = c.n & 1, st = c.t % TC3_NST, slot = c.g % 3;
-        if (first_block(c)) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
-        if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[st], (c.t / TC3_NST) & 1);
-        ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g / 3) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
-        const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE) + c.sb * 64 * 64);
-        ptx::umma_bf16(tmem + slot * 64, dq, dk, IDESC_S, 0);
-        ptx::umma_bf16(tmem + slot * 64, dq + 2, dk + 2, IDESC_S, 1);
-        ptx::umma_commit(&bar.s_full[slot]);
-        if (last_block(c)) ptx::umma_commit(&bar.q_free[qb]);
-      };
-      auto issue_pv = [&](const Tc3Cursor& c) {
-        const int ob = c.n & 1, st = c.t % TC3_NST, slot = c.g % 3;
-        if (first_block(c)) ptx::mbar_wait_parked(&bar.o_free[ob], ((c.n >> 1) & 1) ^ 1);
-        ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g / 3) & 1);
-        ptx::tc_fence_after();
-        const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE) + c.sb * 64 * 64;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          ptx::umma_bf16_ts(tmem + 192 + ob * 32, tmem + slot * 64 + ks * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
-                            !(first_block(c) && ks == 0));
-        ptx::umma_commit(&bar.s_free[slot]);
-        if (c.sb == 1) ptx::umma_commit(&bar.kv_free[st]);
-        if (last_block(c)) ptx::umma_commit(&bar.o_full[ob]);
-      };
-      Tc3Cursor sc, pc;
-      start(sc);
-      start(pc);
-      while (pc.valid) {
-        while (sc.valid && sc.g < pc.g + 3) {
-          issue_s(sc);
-          advance(sc);
-        }
-        issue_pv(pc);
-        advance(pc);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + output (4 warps per stream)
-    // Online softmax per 64-key block against a lazily updated reference maximum (see variant 2), one thread per row.
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
-    const int D = H * DH;
-    constexpr float LAZY_LOG2 = 8.0f;
-    float m_ref = 0.f, rs = 0.f;
-    bool pend = false;
-    int p_n = 0;
-    float p_inv = 0.f;
-    __nv_bfloat16* p_dst = nullptr;
-    auto epilogue = [&]() {
-      const int ob = p_n & 1;
-      ptx::mbar_wait(&bar.o_full[ob], (p_n >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t ro[32];
-      ptx::tmem_ld_32x32(lane_base + 192 + ob * 32, ro);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar.o_free[ob]);
-      uint4* dst = reinterpret_cast<uint4*>(p_dst);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * p_inv, __uint_as_float(ro[8 * k + 1]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * p_inv, __uint_as_float(ro[8 * k + 3]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
-    };
-    Tc3Cursor c;
-    for (start(c); c.valid; advance(c)) {
-      const int g = c.g, slot = g % 3;
-      const uint32_t t_s = lane_base + slot * 64;
-      ptx::mbar_wait(&bar.s_full[slot], (g / 3) & 1);
-      ptx::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(t_s, r0);
-      ptx::tmem_ld_32x32(t_s + 32, r1);
-      ptx::tmem_ld_wait();
-      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        b0 = fmaxf(b0, __uint_as_float(r0[2 * k]));
-        b1 = fmaxf(b1, __uint_as_float(r0[2 * k + 1]));
-        b2 = fmaxf(b2, __uint_as_float(r1[2 * k]));
-        b3 = fmaxf(b3, __uint_as_float(r1[2 * k + 1]));
-      }
-      const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
-      if (first_block(c)) {
-        m_ref = bm;
-        rs = 0.f;
-      } else {
-        const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
-          const int gp = g - 1;                            // every PV issued so far must have landed in O
-          ptx::mbar_wait(&bar.s_free[gp % 3], (gp / 3) & 1);
-          ptx::tc_fence_after();
-          const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
-          uint32_t ro[32];
-          const uint32_t t_o = lane_base + 192 + (c.n & 1) * 32;
-          ptx::tmem_ld_32x32(t_o, ro);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
-          ptx::tmem_st_32x32(t_o, ro);
-          ptx::tmem_st_wait();
-          rs *= f;
-          if (need) m_ref = bm;
-        }
-      }
-      const float ms = m_ref * scale_log2e;
-      uint32_t pk[32];                                     // P (bf16 pairs) over the first 32 of the slot's 64 columns
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
-        const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
-        const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
-        const float p3 = fast_ex2(fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms));
-        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-        pk[k] = ptx::pack_bf16x2(p0, p1);
-        pk[16 + k] = ptx::pack_bf16x2(p2, p3);
-      }
-      rs += (s0 + s1) + (s2 + s3);
-      ptx::tmem_st_32x32(t_s, pk);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
-      if (first_block(c) && pend) {
-        epilogue();
-        pend = false;
-      }
-      if (last_block(c)) {
-        pend = true;
-        p_n = c.n;
-        p_inv = 1.f / rs;
-        p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH;
-      }
-    }
-    if (pend) epilogue();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
-}
-
-
-// ================================================================================================
-// Windowed softmax attention on tcgen05, NS independent streams per CTA (template; round 2).
-// The persistent schedule of variant 3 with its shape made a compile-time choice:
-//   NS   streams per CTA (2 or 4).  A stream = TMA producer warp + MMA issuer warp + four softmax warps (one thread per
-//        query row, warp w of the four owns TMEM lanes 32 w ..), 512 / NS tensor-memory columns and its own smem ring;
-//        it walks every NS-th item of the CTA.  The softmax warps of different streams that share an SMSP are what
-//        keeps the MUFU pipe (one ex2 per score: the floor of this kernel, 16 per clock per SM measured) busy while a
-//        stream waits for its MMAs, its tensor-memory loads or its barriers.
-//   BK   keys per block (64 or 32): S_g = Q K_g^T is 128 x BK, three S / P slots per stream.
-//   POLY every POLY-th exponential is evaluated on the FMA / ALU pipes (Cody-Waite + cubic), 0 = all on MUFU.
-// TMEM per stream: S / P slots at 0, BK, 2 BK; O buffers (32 columns each) from 3 BK.
-//   NS = 2, BK = 64: 192 + 2 x 32 = 256 columns;  NS = 4, BK = 32: 96 + 32 = 128 columns.
-// ================================================================================================
-template <int NS, int BK, int NSTO = 0>
-struct MsCfg {
-  static constexpr int NST = NSTO > 0 ? NSTO : (NS == 2 ? 3 : 2);   // K/V ring stages per stream (tiles of 128 keys)
-  static constexpr int NOB = NS == 2 ? 2 : 1;               // O accumulators per stream
-  static constexpr int SB = WIN / BK;                       // blocks per K/V tile
-  static constexpr int TM_STREAM = 512 / NS;
-  static constexpr int TM_O = 3 * BK;
-  static constexpr int THREADS = NS * 6 * 32;
-  static constexpr int STREAM_TILES = 2 + 2 * NST;
-  static constexpr int SMEM_BYTES = NS * STREAM_TILES * TC_TILE + 1024;
-  static_assert(TM_O + NOB * 32 <= TM_STREAM, "tensor memory budget");
-  static_assert((2 * NS) % 4 == 0, "softmax warp w must sit on TMEM lane quarter w % 4");
-};
-
-// Timeline of CTA 0 (test hook biom3_debug_trace; ABL == 30): [stream][who: 0 issuer, 1 softmax warp 0][block g < 128][event] = clock64()
-//   issuer:  0 before issue_s, 1 S issued, 2 before issue_pv, 3 p_ready seen, 4 PV issued
+// Timeline of CTA 0 of a tracing launch (test hook biom3_debug_trace(0, ...)): [stream][who: 0 issuers, 1 softmax warp 0]
+// [block g < 128][event] = clock64()
+//   issuers: 0 before the S issue (slot wait included), 1 S issued, 2 before the PV issue, 3 p_ready seen, 4 PV issued
 //   softmax: 0 loop top, 1 s_full seen, 2 scores loaded, 3 exponentials done, 4 P stored + arrived, 5 after epilogue
 __device__ long long g_ms_trace[2][2][128][6];
 
-template <int NST, int NOB>
-struct MsBars {
-  uint64_t q_full[2], q_free[2], kv_full[NST], kv_free[NST], s_full[3], p_ready[3], s_free[3], o_full[NOB], o_free[NOB];
-};
-struct MsCursor {
-  int i, n, t, g, kt, sb, nkt, w, b, h, w_lo;
-  bool valid;
-};
-
-// 2^x for x <= ~8 on the FMA / ALU pipes: round to nearest integer with the 1.5 * 2^23 trick, cubic on [-0.5, 0.5]
-// (relative error 1e-4, far inside the bf16 rounding of P), exponent added to the bit pattern.
-__device__ __forceinline__ float ex2_fma_pipe(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05550411f, 0.24022651f);
-  p = fmaf(p, f, 0.69314718f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-// ABL (timing ablations only, results are wrong): 1 = no exponentials (FMA pipe only), 2 = softmax warps only hand the
-// slots on (no tensor-memory traffic, no math): the TMA + MMA + barrier pipeline alone, 3 = no max pass
-template <int NS, int BK, int POLY, int ABL = 0, int NSTO = 0>
-__global__ void __launch_bounds__(MsCfg<NS, BK>::THREADS, 1)
-local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
-                          int L, int NL, float scale_log2e, int reverse) {
-  using Cfg = MsCfg<NS, BK, NSTO>;
-  constexpr int NST = Cfg::NST, NOB = Cfg::NOB, SB = Cfg::SB;
-  const int nw = L / WIN;
-  const int total = nw * B * NL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stream = warp < 2 * NS ? (warp >> 1) : ((warp - 2 * NS) >> 2);
-  const int role = warp < 2 * NS ? (warp & 1) : 2;       // 0 producer, 1 issuer, 2 softmax
-
-  extern __shared__ uint8_t ms_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ms_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + stream * Cfg::STREAM_TILES * TC_TILE;     // 2 tiles
-  uint8_t* sKV = sQ + 2 * TC_TILE;                               // NST x (K tile, V tile)
-  __shared__ MsBars<NST, NOB> bars[NS];
-  __shared__ uint32_t tmem_slot;
-  MsBars<NST, NOB>& bar = bars[stream];
-
-  if (tid == 0) {
-    ptx::tma_prefetch_desc(&tm_qkv);
-    for (int s2 = 0; s2 < NS; ++s2) {
-      MsBars<NST, NOB>& x = bars[s2];
-      for (int k = 0; k < 2; ++k) {
-        ptx::mbar_init(&x.q_full[k], 1);
-        ptx::mbar_init(&x.q_free[k], 1);
-      }
-      for (int k = 0; k < NOB; ++k) {
-        ptx::mbar_init(&x.o_full[k], 1);
-        ptx::mbar_init(&x.o_free[k], 4);
-      }
-      for (int k = 0; k < NST; ++k) {
-        ptx::mbar_init(&x.kv_full[k], 1);
-        ptx::mbar_init(&x.kv_free[k], 1);
-      }
-      for (int k = 0; k < 3; ++k) {
-        ptx::mbar_init(&x.s_full[k], 1);
-        ptx::mbar_init(&x.p_ready[k], 4);
-        ptx::mbar_init(&x.s_free[k], 1);
-      }
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = tmem_slot + stream * Cfg::TM_STREAM;
-  ptx::pdl_sync();
-
-  const int nlb = NL * B;
-  auto seek = [&](MsCursor& c) {
-    const int f = int(blockIdx.x) + c.i * int(gridDim.x);
-    c.valid = f < total;
-    if (!c.valid) return;
-    const int ff = reverse ? total - 1 - f : f;
-    c.w = ff / nlb;
-    const int r = ff - c.w * nlb;
-    c.b = r / NL;
-    c.h = r - c.b * NL;
-    c.w_lo = max(c.w - 1, 0);
-    c.nkt = min(c.w + 1, nw - 1) - c.w_lo + 1;
-    c.kt = 0;
-    c.sb = 0;
-  };
-  auto start = [&](MsCursor& c) { c.i = stream; c.n = 0; c.t = 0; c.g = 0; seek(c); };
-  auto advance = [&](MsCursor& c) {
-    ++c.g;
-    if (++c.sb == SB) {
-      c.sb = 0;
-      ++c.t;
-      if (++c.kt == c.nkt) { c.i += NS; ++c.n; seek(c); }
-    }
-  };
-  auto first_block = [](const MsCursor& c) { return c.kt == 0 && c.sb == 0; };
-  auto last_block = [](const MsCursor& c) { return c.kt == c.nkt - 1 && c.sb == SB - 1; };
-
-  if (role == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int plane = B * H * L;
-      MsCursor c;
-      for (start(c); c.valid; advance(c)) {
-        if (c.sb != 0) continue;
-        const int rq = (c.b * H + c.h) * L;
-        if (c.kt == 0) {
-          const int qb = c.n & 1;
-          ptx::mbar_wait_parked(&bar.q_free[qb], ((c.n >> 1) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
-          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + c.w * WIN);
-        }
-        const int st = c.t % NST;
-        ptx::mbar_wait_parked(&bar.kv_free[st], ((c.t / NST) & 1) ^ 1);
-        if constexpr (ABL == 4) {
-          ptx::mbar_arrive(&bar.kv_full[st]);
-          continue;
-        }
-        ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
-        ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (c.w_lo + c.kt) * WIN);
-        ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (c.w_lo + c.kt) * WIN);
-      }
-    }
-  } else if (role == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t(BK) >> 3) << 17) | ((128u >> 4) << 24);
-      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      const bool tr = ABL == 30 && blockIdx.x == 0 && stream < 2;
-      auto issue_s = [&](const MsCursor& c) {
-        const int qb = c.n & 1, st = c.t % NST, slot = c.g % 3;
-        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][0] = clock64();
-        if (first_block(c)) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
-        if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[st], (c.t / NST) & 1);
-        ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g / 3) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint64_t dq = umma_desc_sw64(ptx::smem_u32(sQ + qb * TC_TILE));
-        const uint64_t dk = umma_desc_sw64(ptx::smem_u32(sKV + (2 * st) * TC_TILE) + c.sb * BK * 64);
-        if constexpr (ABL != 22 && ABL != 23) {
-          ptx::umma_bf16(tmem + slot * BK, dq, dk, IDESC_S, 0);
-          ptx::umma_bf16(tmem + slot * BK, dq + 2, dk + 2, IDESC_S, 1);
-        }
-        ptx::umma_commit(&bar.s_full[slot]);
-        if (last_block(c)) ptx::umma_commit(&bar.q_free[qb]);
-        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][1] = clock64();
-      };
-      auto issue_pv = [&](const MsCursor& c) {
-        const int ob = c.n % NOB, st = c.t % NST, slot = c.g % 3;
-        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][2] = clock64();
-        if (first_block(c)) ptx::mbar_wait_parked(&bar.o_free[ob], ((c.n / NOB) & 1) ^ 1);
-        ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g / 3) & 1);
-        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][3] = clock64();
-        ptx::tc_fence_after();
-        const uint32_t sv = ptx::smem_u32(sKV + (2 * st + 1) * TC_TILE) + c.sb * BK * 64;
-#pragma unroll
-        for (int ks = 0; ks < ((ABL == 21 || ABL == 23) ? 0 : BK / 16); ++ks)
-          ptx::umma_bf16_ts(tmem + Cfg::TM_O + ob * 32, tmem + slot * BK + ks * 8, umma_desc_sw64(sv + ks * 16 * 64), IDESC_O,
-                            !(first_block(c) && ks == 0));
-        ptx::umma_commit(&bar.s_free[slot]);
-        if (c.sb == SB - 1) ptx::umma_commit(&bar.kv_free[st]);
-        if (last_block(c)) ptx::umma_commit(&bar.o_full[ob]);
-        if (tr && c.g < 128) g_ms_trace[stream][0][c.g][4] = clock64();
-      };
-      MsCursor sc, pc;
-      start(sc);
-      start(pc);
-      constexpr int AHEAD = (ABL == 7 || ABL == 8) ? 2 : 3;
-      while (pc.valid) {
-        while (sc.valid && sc.g < pc.g + AHEAD) {
-          issue_s(sc);
-          advance(sc);
-        }
-        issue_pv(pc);
-        advance(pc);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + output (4 warps per stream)
-    // Online softmax per BK-key block against a lazily updated reference maximum: the first block of an item sets m_ref
-    // to its row maximum; a later block rescales O and the row sum only when its maximum exceeds m_ref by more than 2^8
-    // (P stays <= 256, exact in bf16's range), which real score distributions almost never do.
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
-    const int D = H * DH;
-    constexpr float LAZY_LOG2 = 8.0f;
-    float m_ref = 0.f, rs = 0.f;
-    bool pend = false;
-    int p_n = 0;
-    float p_inv = 0.f;
-    __nv_bfloat16* p_dst = nullptr;
-    auto epilogue = [&]() {
-      const int ob = p_n % NOB;
-      ptx::mbar_wait(&bar.o_full[ob], (p_n / NOB) & 1);
-      ptx::tc_fence_after();
-      uint32_t ro[32];
-      ptx::tmem_ld_32x32(lane_base + Cfg::TM_O + ob * 32, ro);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar.o_free[ob]);
-      uint4* dst = reinterpret_cast<uint4*>(p_dst);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * p_inv, __uint_as_float(ro[8 * k + 1]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * p_inv, __uint_as_float(ro[8 * k + 3]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
-                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
-    };
-    MsCursor c;
-    const bool tr = ABL == 30 && blockIdx.x == 0 && stream < 2 && quarter == 0 && lane == 0;
-    for (start(c); c.valid; advance(c)) {
-      const int g = c.g, slot = g % 3;
-      const uint32_t t_s = lane_base + slot * BK;
-      if (tr && g < 128) g_ms_trace[stream][1][g][0] = clock64();
-      ptx::mbar_wait(&bar.s_full[slot], (g / 3) & 1);
-      if (tr && g < 128) g_ms_trace[stream][1][g][1] = clock64();
-      ptx::tc_fence_after();
-      if constexpr (ABL == 2 || ABL == 4 || ABL == 8 || ABL >= 20) {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
-        if (first_block(c) && pend) { epilogue(); pend = false; }
-        if (last_block(c)) { pend = true; p_n = c.n; p_inv = 1.f; p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH; }
-        continue;
-      }
-      uint32_t r[BK];
-      {
-        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
-        ptx::tmem_ld_32x32(t_s, r0);
-        if constexpr (BK == 64) {
-          uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
-          ptx::tmem_ld_32x32(t_s + 32, r1);
-        }
-      }
-      ptx::tmem_ld_wait();
-      if (tr && g < 128) g_ms_trace[stream][1][g][2] = clock64();
-      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < BK / 4; ++k) {
-        b0 = fmaxf(b0, __uint_as_float(r[4 * k]));
-        b1 = fmaxf(b1, __uint_as_float(r[4 * k + 1]));
-        b2 = fmaxf(b2, __uint_as_float(r[4 * k + 2]));
-        b3 = fmaxf(b3, __uint_as_float(r[4 * k + 3]));
-      }
-      const float bm = ABL == 3 ? __uint_as_float(r[0]) : fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
-      if (first_block(c)) {
-        m_ref = bm;
-        rs = 0.f;
-      } else {
-        const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
-        if (ABL != 3 && __any_sync(0xffffffffu, need)) {
-          const int gp = g - 1;                            // every PV issued so far must have landed in O
-          ptx::mbar_wait(&bar.s_free[gp % 3], (gp / 3) & 1);
-          ptx::tc_fence_after();
-          const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
-          uint32_t ro[32];
-          const uint32_t t_o = lane_base + Cfg::TM_O + (c.n % NOB) * 32;
-          ptx::tmem_ld_32x32(t_o, ro);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
-          ptx::tmem_st_32x32(t_o, ro);
-          ptx::tmem_st_wait();
-          rs *= f;
-          if (need) m_ref = bm;
-        }
-      }
-      const float ms = m_ref * scale_log2e;
-      uint32_t pk[BK / 2];                                 // P (bf16 pairs) over the first BK / 2 of the slot's columns
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int k = 0; k < BK / 4; ++k) {
-        const float x0 = fmaf(__uint_as_float(r[4 * k]), scale_log2e, -ms), x1 = fmaf(__uint_as_float(r[4 * k + 1]), scale_log2e, -ms);
-        const float x2 = fmaf(__uint_as_float(r[4 * k + 2]), scale_log2e, -ms), x3 = fmaf(__uint_as_float(r[4 * k + 3]), scale_log2e, -ms);
-        const float p0 = ABL == 1 ? x0 : fast_ex2(x0), p1 = ABL == 1 ? x1 : fast_ex2(x1), p2 = ABL == 1 ? x2 : fast_ex2(x2);
-        const float p3 = ABL == 1 ? x3 : (POLY > 0 && (k % (POLY / 4 > 0 ? POLY / 4 : 1)) == 0) ? ex2_fma_pipe(x3) : fast_ex2(x3);
-        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-        pk[2 * k] = ptx::pack_bf16x2(p0, p1);
-        pk[2 * k + 1] = ptx::pack_bf16x2(p2, p3);
-      }
-      rs += (s0 + s1) + (s2 + s3);
-      if (tr && g < 128) g_ms_trace[stream][1][g][3] = clock64() + (__float_as_int(rs) & 0);
-      if constexpr (BK == 64) ptx::tmem_st_32x32(t_s, pk);
-      else ptx::tmem_st_32x16(t_s, pk);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
-      if (tr && g < 128) g_ms_trace[stream][1][g][4] = clock64();
-      if (first_block(c) && pend) {
-        epilogue();
-        pend = false;
-      }
-      if (tr && g < 128) g_ms_trace[stream][1][g][5] = clock64();
-      if (last_block(c)) {
-        pend = true;
-        p_n = c.n;
-        p_inv = 1.f / rs;
-        p_dst = out + (size_t(c.b) * L + size_t(c.w) * WIN + row) * D + c.h * DH;
-      }
-    }
-    if (pend) epilogue();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
-}
-
-
 // ================================================================================================
-// Windowed softmax attention on tcgen05, round 2 schedule ("v5"): two streams per CTA as in variant 3, but every
-// stream now has TWO single-thread MMA issuers and lean, division-free control loops.
+// Windowed softmax attention on tcgen05 (heads [0, NL)): query window w attends to key windows w-1, w, w+1 (those that
+// exist), softmax over the real keys only.  Persistent, one CTA per SM, two independent streams per CTA; every stream has a
+// TMA producer warp, TWO MMA issuer warps (S and PV) with division-free control loops, and four softmax warps.
 //
 // Why (profiles/r02_attn_trace_ms_issuer_bound.log, profiles/r02_attn_ablations.log): a clock64 timeline of variant 3
 // showed the softmax warps idle ~1250 of every ~1450 cycles per 64-key block, waiting for scores; removing ALL
@@ -1773,28 +315,27 @@ local_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
 // cover exactly its own instructions.
 // TMEM per stream: S / P slots at 0, 64, 128; O buffers at 192, 224.
 // ================================================================================================
-constexpr int V5_THREADS = 14 * 32;
+constexpr int LOCAL_THREADS = 14 * 32;
+constexpr int LOCAL_NST = 5;           // K/V ring stages per stream (3: +4 %, 4: +1.5 %, 6: equal; profiles/r02_attn_variants_v5.log)
 template <int NST>
-struct V5Cfg {
+struct LocalCfg {
   static constexpr int STREAM_TILES = 2 + 2 * NST;
   static constexpr int SMEM_BYTES = 2 * STREAM_TILES * TC_TILE + 1024;
 };
 template <int NST>
-struct V5Bars {
+struct LocalBars {
   uint64_t q_full[2], q_free[2], kv_full[NST], kv_free[NST], s_full[3], p_ready[3], s_free[3], o_full[2], o_free[2];
 };
-struct V5Item {                      // one (window, sample, head)
+struct LocalItem {                      // one (window, sample, head)
   int w, b, h, w_lo, nkt;
 };
-constexpr uint32_t V5_DESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 512 B, version 1, SWIZZLE_64B
-__device__ __forceinline__ uint32_t v5_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ uint64_t v5_desc(uint32_t lo) { return (static_cast<uint64_t>(V5_DESC_HI) << 32) | lo; }
+constexpr uint32_t LOCAL_DESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint32_t local_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t local_desc(uint32_t lo) { return (static_cast<uint64_t>(LOCAL_DESC_HI) << 32) | lo; }
 
-// TURNS: the two softmax warps that share an SMSP (same row quarter, different streams) take turns on the MUFU pipe
-// (see the softmax role below); POLY: every POLY-th exponential on the FMA / ALU pipes (0 = none)
-template <int NST, int TRACE, int TURNS = 0, int POLY = 0>
-__global__ void __launch_bounds__(V5_THREADS, 1)
-local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
+template <int NST, int TRACE>
+__global__ void __launch_bounds__(LOCAL_THREADS, 1)
+local_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H,
                           int L, int NL, float scale_log2e, int reverse) {
   const int nw = L / WIN;
   const int total = nw * B * NL, nlb = NL * B;
@@ -1805,20 +346,18 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
   const int stream = warp < 6 ? warp / 3 : (warp - 6) >> 2;
   const int role = warp < 6 ? warp % 3 : 3;              // 0 producer, 1 S issuer, 2 PV issuer, 3 softmax
 
-  extern __shared__ uint8_t v5_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v5_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + stream * V5Cfg<NST>::STREAM_TILES * TC_TILE;     // 2 tiles
+  extern __shared__ uint8_t local_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(local_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + stream * LocalCfg<NST>::STREAM_TILES * TC_TILE;     // 2 tiles
   uint8_t* sKV = sQ + 2 * TC_TILE;                                      // NST x (K tile, V tile)
-  __shared__ V5Bars<NST> bars[2];
+  __shared__ LocalBars<NST> bars[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ volatile int mufu_turn[4];                  // per row quarter: 0 free, else 1 + the stream whose warp is exponentiating
-  V5Bars<NST>& bar = bars[stream];
-  if (tid < 4) mufu_turn[tid] = 0;
+  LocalBars<NST>& bar = bars[stream];
 
   if (tid == 0) {
     ptx::tma_prefetch_desc(&tm_qkv);
     for (int s2 = 0; s2 < 2; ++s2) {
-      V5Bars<NST>& x = bars[s2];
+      LocalBars<NST>& x = bars[s2];
       for (int k = 0; k < 2; ++k) {
         ptx::mbar_init(&x.q_full[k], 1);
         ptx::mbar_init(&x.q_free[k], 1);
@@ -1848,7 +387,7 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
   ptx::pdl_sync();
 
   // the n-th item of this stream: flat index blockIdx.x + (stream + 2 n) gridDim.x, walked window-major
-  auto item = [&](int n, V5Item& it) -> bool {
+  auto item = [&](int n, LocalItem& it) -> bool {
     const int f = int(blockIdx.x) + (stream + 2 * n) * int(gridDim.x);
     if (f >= total) return false;
     const int ff = reverse ? total - 1 - f : f;
@@ -1862,22 +401,28 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
   };
 
   if (role == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, one elected lane issues)
+    {
       const int plane = B * H * L;
-      V5Item it;
+      LocalItem it;
       uint32_t st = 0, st_ph = 0;
       for (int n = 0; item(n, it); ++n) {
         const int rq = (it.b * H + it.h) * L;
         const int qb = n & 1;
         ptx::mbar_wait_parked(&bar.q_free[qb], ((n >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
-        ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + it.w * WIN);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
+          ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + it.w * WIN);
+        }
+        __syncwarp();
         for (int kt = 0; kt < it.nkt; ++kt) {
           ptx::mbar_wait_parked(&bar.kv_free[st], st_ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
-          ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (it.w_lo + kt) * WIN);
-          ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (it.w_lo + kt) * WIN);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&bar.kv_full[st], 2 * TC_TILE);
+            ptx::tma_load_2d(sKV + (2 * st) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, plane + rq + (it.w_lo + kt) * WIN);
+            ptx::tma_load_2d(sKV + (2 * st + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st], 0, 2 * plane + rq + (it.w_lo + kt) * WIN);
+          }
+          __syncwarp();
           if (++st == NST) { st = 0; st_ph ^= 1; }
         }
       }
@@ -1886,8 +431,8 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
     // ------------------------------------------------------------------ S issuer (the whole warp walks the loop, one elected lane issues)
     {
       constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t q_lo0 = v5_desc_lo(ptx::smem_u32(sQ)), kv_lo0 = v5_desc_lo(ptx::smem_u32(sKV));
-      V5Item it;
+      const uint32_t q_lo0 = local_desc_lo(ptx::smem_u32(sQ)), kv_lo0 = local_desc_lo(ptx::smem_u32(sKV));
+      LocalItem it;
       uint32_t st = 0, st_ph = 0, slot = 0, slot_ph = 0;
       int g = 0;
       for (int n = 0; item(n, it); ++n) {
@@ -1903,8 +448,8 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
             ptx::mbar_wait_parked(&bar.s_free[slot], slot_ph ^ 1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              ptx::umma_bf16(tmem + slot * 64, v5_desc(q_lo), v5_desc(k_lo + sb * 256), IDESC_S, 0);
-              ptx::umma_bf16(tmem + slot * 64, v5_desc(q_lo + 2), v5_desc(k_lo + sb * 256 + 2), IDESC_S, 1);
+              ptx::umma_bf16(tmem + slot * 64, local_desc(q_lo), local_desc(k_lo + sb * 256), IDESC_S, 0);
+              ptx::umma_bf16(tmem + slot * 64, local_desc(q_lo + 2), local_desc(k_lo + sb * 256 + 2), IDESC_S, 1);
               ptx::umma_commit(&bar.s_full[slot]);
             }
             __syncwarp();
@@ -1922,8 +467,8 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
     // ------------------------------------------------------------------ PV issuer (same pattern)
     {
       constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t kv_lo0 = v5_desc_lo(ptx::smem_u32(sKV));
-      V5Item it;
+      const uint32_t kv_lo0 = local_desc_lo(ptx::smem_u32(sKV));
+      LocalItem it;
       uint32_t st = 0, st_ph = 0, slot = 0, slot_ph = 0;
       int g = 0;
       for (int n = 0; item(n, it); ++n) {
@@ -1942,7 +487,7 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                ptx::umma_bf16_ts(t_o, tmem + slot * 64 + ks * 8, v5_desc(v_lo + sb * 256 + ks * 64), IDESC_O,
+                ptx::umma_bf16_ts(t_o, tmem + slot * 64 + ks * 8, local_desc(v_lo + sb * 256 + ks * 64), IDESC_O,
                                   (kt | sb | ks) != 0);
               ptx::umma_commit(&bar.s_free[slot]);
               if (sb == 1) ptx::umma_commit(&bar.kv_free[st]);
@@ -1992,7 +537,7 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
                             ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * p_inv, __uint_as_float(ro[8 * k + 5]) * p_inv),
                             ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * p_inv, __uint_as_float(ro[8 * k + 7]) * p_inv));
     };
-    V5Item it;
+    LocalItem it;
     uint32_t slot = 0, slot_ph = 0;
     int g = 0;
     for (int n = 0; item(n, it); ++n) {
@@ -2041,19 +586,13 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
           }
         }
         const float ms = m_ref * scale_log2e;
-        // The exponentials of a block keep the MUFU pipe busy for 512 cycles (64 warp instructions at 4 lanes per clock
-        // per SMSP); everything else a softmax warp does per block (barrier, tensor-memory load and store, maximum) is
-        // ~400 cycles without MUFU work.  Two warps share the SMSP.  Left alone they fall into lockstep — both
-        // exponentiate at half rate, then both idle the pipe (measured: ~1500 cycles per block pair, MUFU 2/3 busy) —
-        // so they take turns instead: a warp that finds its neighbour exponentiating waits for it to finish (bounded:
-        // this is a scheduling hint in shared memory, not a lock) and then has the pipe to itself while the neighbour
-        // does its MUFU-free part.
-        if constexpr (TURNS) {
-          int spins = 0;
-          while (mufu_turn[quarter] == 2 - stream && ++spins < 40) {}        // ~25 cycles per poll, bounded to one block's exponentials
-          __syncwarp();
-          if (lane == 0) mufu_turn[quarter] = 1 + stream;
-        }
+        // With the issuers out of the way this loop is what bounds the kernel: the exponentials of a block keep the MUFU
+        // pipe busy for 512 cycles (64 warp instructions at 4 lanes per clock per SMSP), the rest of a block (barrier,
+        // tensor-memory load and store, maximum) is ~370 cycles, and the two warps sharing an SMSP drift into lockstep
+        // (~1500 cycles per block pair, MUFU 2/3 busy; profiles/r02_attn_trace_v5_uniform_issue.log).  Measured and not
+        // kept: taking turns on the pipe through a shared-memory hint (+5 %), a cubic exp2 on the FMA pipe for every 4th
+        // or 8th element (+4 % / +8 %: with two warps per SMSP the issue slots, not MUFU, are what the extra
+        // instructions cost), four streams of 32-key blocks (+8 %); profiles/r02_attn_variants_v5.log.
         uint32_t pk[32];                                   // P (bf16 pairs) over the first 32 of the slot's 64 columns
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -2061,16 +600,12 @@ local_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
           const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
           const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
           const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
-          const float x3 = fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms);
-          const float p3 = (POLY > 0 && (4 * k + 3) % POLY == 3 % POLY) ? ex2_fma_pipe(x3) : fast_ex2(x3);
+          const float p3 = fast_ex2(fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms));
           s0 += p0; s1 += p1; s2 += p2; s3 += p3;
           pk[k] = ptx::pack_bf16x2(p0, p1);
           pk[16 + k] = ptx::pack_bf16x2(p2, p3);
         }
         rs += (s0 + s1) + (s2 + s3);
-        if constexpr (TURNS) {
-          if (lane == 0) mufu_turn[quarter] = 0;
-        }
         if (tr && g < 128) g_ms_trace[stream][1][g][3] = clock64() + (__float_as_int(rs) & 0);
         ptx::tmem_st_32x32(t_s, pk);
         ptx::tmem_st_wait();

@@ -13,14 +13,9 @@
 //                 version is bound by the SM's L2->smem ingest (~43 B/clk measured, 48 KB per 512 MMA cycles);
 //                 the pair needs 32 KB per CTA for the same MMA work.
 //
-// ARES = true (CTA pairs, K <= 512, bf16 epilogues; optional, BIOM3_ARES=1): the A row block stays RESIDENT in shared memory.
-// A 256 x 256 tile with K = 512 pulls 256 KB of A + 256 KB of W through L2 and writes 128 KB, and under ncu the QKV GEMM
-// moves ~11.9 TB/s through L2, close to the ~6300 B/clk LTS limit — the hypothesis was that L2 bytes bound these GEMMs.
-// In this variant a worker walks a CONTIGUOUS run of tiles (consecutive column tiles of one 256-row block), loads the
-// block's A once (8 k-blocks x 16 KB per CTA, one full / empty barrier pair per k-block so the next row block's A
-// streams in behind the last column tile's MMAs) and only W goes through a 4-stage ring: A traffic / n_tiles.  It is
-// bit-identical to the streaming kernel and measured NO faster (3.92 vs 3.81 us per K = 512 tile, step unchanged), so
-// L2 traffic is not the bound; the streaming ring stays the default.
+// Round-1 experiment, removed: an A-resident variant (the 256-row A block loaded once per run of column tiles, only W
+// through the ring; halves the L2 -> SM operand traffic, bit-identical) measured no faster, before and after the
+// single-thread issue path was fixed (profiles/r01_ab_ares.jsonl, profiles/r02_gemm_trace_uniform_issue.log).
 //
 // Fusions (the reference runs each as separate library / element-wise kernels; block structure from
 // linear-attention-transformer, called at /root/reference/Stage3_source/cond_diff_transformer_layer.py:171):
@@ -46,22 +41,16 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 // warps overlap; the QKV epilogue has almost no math per element, its cost is the ~244 instructions of per-tile set-up each
 // warp executes, and it is 6 % faster with 8 warps of four chunks (A/B of compile-time variants, `tools/ab_variant.sh`:
 // QKV 1.80 -> 1.69 ms per step with 8 warps, FF1 2.56 -> 2.69 ms, hence the mixed default).
-// The A-resident variant has 16 KB of staging left: 8 warps x 2 KB.
 #ifndef BIOM3_BF16_EPI_WARPS
 #define BIOM3_BF16_EPI_WARPS 16      // GELU / plain bf16-store epilogues; compile-time A/B: python -m biom3_b200.build --variant ew8 BIOM3_BF16_EPI_WARPS=8
 #endif
 #ifndef BIOM3_QKV_EPI_WARPS
 #define BIOM3_QKV_EPI_WARPS 8
 #endif
-__host__ __device__ constexpr int epi_warps(int epi, bool ares = false) {
-  return (ares || (epi >= 3 && epi <= 7)) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
+__host__ __device__ constexpr int epi_warps(int epi) {
+  return (epi >= 3 && epi <= 5) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
 }
-// First epilogue warp.  RD = 2 (two residual chunks prefetched, 64 registers) does not fit the 168 registers a 10-warp CTA
-// gets, so that variant pads the two control warps to a full warpgroup (warps 2, 3 idle) and moves registers with
-// setmaxnreg: warpgroup 0 drops to 56 and the two epilogue warpgroups rise to 224: 128 x 56 + 256 x 224 = 64,512 = the
-// 384 x 168 the CTA was launched with (an inc beyond the pool would block forever).
-__host__ __device__ constexpr int epi_warp0(int rd) { return rd == 2 ? 4 : 2; }
-constexpr int ARES_NK = 8;         // k-blocks of the resident A row block (K <= 512)
+constexpr uint32_t EPI_WARP0 = 2;     // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
 
 enum Epi : int {
   EPI_STORE_BF16 = 0,      // C bf16 row-major [M, N]
@@ -72,12 +61,6 @@ enum Epi : int {
   EPI_BIAS_RESID_SPLIT = 5, // like 3, but R lives as two bf16 arrays, R = hi + lo (hi = bf16(R), lo = bf16(R - hi)):
                             // `out_bf16` is hi (the array the next GEMM reads as its A operand), `out` is lo.  Same
                             // bytes read, 2 instead of 6 bytes per element written; R keeps 16 significant bits.
-  EPI_BIAS_RESID_SPLIT8 = 6, // like 5 with the remainder in ONE byte (ptx::split8_*): `out` is the tiled uint8 lo plane.  3 instead
-                            // of 4 bytes per element read and written by the residual GEMMs; measured slower (optional).
-  EPI_BIAS_RESID_DIRECT = 7, // same data as 5 (bf16 hi + bf16 lo planes, row major), different access: thread = row end to end.
-                            // Each thread reads and writes its own row's 32 columns of a chunk as 64 contiguous bytes per
-                            // plane (two 256-bit accesses = full sectors), so there is no shared-memory transpose, no
-                            // __syncwarp, and the row statistics need no shuffles; measured slower (optional).
 };
 
 struct Params {
@@ -102,13 +85,10 @@ struct Params {
   float* stats_out;        // [M][(N/BN)*2][2] or nullptr
   int split3;              // fp32-class mode: A and W hold [hi | lo] bf16 halves (2K columns each); the K loop runs
                            // hi.hi, hi.lo, lo.hi (3K/BK blocks, fp32 accumulate) = the product to ~2^-16 relative
-  int tma_store;           // bf16 epilogues: 0 = smem transpose + coalesced st.global, 1 = smem block + TMA store (tmap_c, 64B
-                           // swizzle), 2 = no staging, two 256-bit stores per thread and chunk (thread = row)
   int nt_shift, l_shift, d_shift;   // log2 of N / BN, of L and of the QKV head-block width N / 3 when those are powers of two, else -1
                            // (set by fill_shifts(); the per-tile index arithmetic then costs shifts instead of ~25-instruction
                            // integer divisions, which were 17 % of the QKV GEMM's executed instructions)
-  int no_pipe;             // 1 = load the per-tile epilogue vectors / statistics at the point of use (A/B switch, BIOM3_EPI_PIPE=0)
-  int debug_skip;          // test hook: 1 = epilogue only drains the barrier (mainloop ceiling), 2 = also skips TMEM reads
+  int trace;               // test hook: CTA 0 records a clock64 timeline into g_gemm_trace
 };
 
 __host__ __device__ constexpr int log2_or_neg(int v) {
@@ -124,21 +104,20 @@ inline void fill_shifts(Params& p, int bn) {
   p.d_shift = (p.N % 3 == 0) ? log2_or_neg(p.N / 3) : -1;
 }
 
-// Shared memory of one CTA: [resident A block (ARES)] [operand ring] [epilogue staging] [per-column epilogue vectors].
+// Shared memory of one CTA: [operand ring] [epilogue staging] [per-column epilogue vectors].
 // Staging and vector space follow the epilogue (EPI), so that the kernels that need less of them can afford a deeper ring.
-__host__ __device__ constexpr bool epi_is_f32(int epi) { return epi >= 3 && epi <= 7; }
-__host__ __device__ constexpr int epi_stg_bytes(int epi, bool ares) { return epi_warps(epi, ares) * (epi_is_f32(epi) ? 4096 : 2048); }
-__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2 || epi == 7) ? CV_TOTAL : 0; }
+__host__ __device__ constexpr bool epi_is_f32(int epi) { return epi >= 3 && epi <= 5; }
+__host__ __device__ constexpr int epi_stg_bytes(int epi) { return epi_warps(epi) * (epi_is_f32(epi) ? 4096 : 2048); }
+__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2) ? CV_TOTAL : 0; }
 
-template <int BN, int STAGES, bool CG2, bool ARES, int EPI>
+template <int BN, int STAGES, bool CG2, int EPI>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;         // weight rows staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int A_RES_BYTES = ARES ? ARES_NK * A_BYTES : 0;   // resident A row block, in front of the ring
-  static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES_TOTAL = epi_stg_bytes(EPI, ARES);
-  static constexpr int STG_OFFSET = A_RES_BYTES + STAGES * STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES_TOTAL = epi_stg_bytes(EPI);
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int CV_OFFSET = STG_OFFSET + STG_BYTES_TOTAL;
   static constexpr int TOTAL = CV_OFFSET + epi_cv_bytes(EPI) + 1024;   // + alignment slack
   static_assert(TOTAL <= 232448 - 512, "more than the 227 KB a CTA can have (512 bytes left for the static barriers)");
@@ -158,21 +137,8 @@ __device__ __forceinline__ float gelu_erf_half(float h) {
   return fmaf(h, th, h);
 }
 
-// 1 / sqrt(var + eps) of the folded LayerNorm.  IEEE by default (~30 instructions per tile and thread); the compile-time
-// variant BIOM3_RSTD_RSQRT=1 uses the 2-ulp MUFU.RSQ for A/B runs.
-#ifndef BIOM3_RSTD_RSQRT
-#define BIOM3_RSTD_RSQRT 0
-#endif
-#ifndef BIOM3_MMA_PARKED
-#define BIOM3_MMA_PARKED 0       // 1: the MMA warp's per-k-block wait for the operands parks instead of polling
-#endif
-__device__ __forceinline__ float row_rstd(float v) {
-#if BIOM3_RSTD_RSQRT
-  return rsqrtf(v);
-#else
-  return 1.0f / sqrtf(v);
-#endif
-}
+// 1 / sqrt(var + eps) of the folded LayerNorm, IEEE (the 2-ulp MUFU.RSQ measured no faster)
+__device__ __forceinline__ float row_rstd(float v) { return 1.0f / sqrtf(v); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -183,17 +149,19 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-template <int BN, int STAGES, int EPI, bool CG2, bool ARES = false, int RD = 1>
-__global__ void __launch_bounds__(32 * (epi_warp0(RD) + epi_warps(EPI, ARES)), 1)
+// Timeline of CTA 0 (Params::trace != 0; test hook biom3_debug_trace(1, ...)): [who][tile < 64][event] = clock64()
+//   who 0 MMA issuer:      0 before acc_empty wait, 1 stage free, 2 last k-block issued
+//   who 1 epilogue warp 0: 0 before acc_full wait, 1 accumulator ready, 2 stage released (last TMEM load landed), 3 tile done
+//   who 2 TMA producer:    0 first k-block of the tile requested, 1 last requested
+__device__ long long g_gemm_trace[3][64][4];
+
+template <int BN, int STAGES, int EPI, bool CG2>
+__global__ void __launch_bounds__(32 * (EPI_WARP0 + epi_warps(EPI)), 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
-  static_assert(RD == 1 || RD == 2, "residual prefetch depth");
-  static_assert(!ARES || (CG2 && BN == 256 && (EPI == EPI_STORE_BF16 || EPI == EPI_QKV_HEADMAJOR || EPI == EPI_BIAS_GELU_BF16)),
-                "the A-resident variant is pair-tiled with a bf16 epilogue");
-  using SL = SmemLayout<BN, STAGES, CG2, ARES, EPI>;
-  constexpr int EPI_WARPS = epi_warps(EPI, ARES);
-  constexpr uint32_t EPI_WARP0 = epi_warp0(RD);
+  using SL = SmemLayout<BN, STAGES, CG2, EPI>;
+  constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr int STG_BYTES = SL::STG_BYTES_TOTAL / EPI_WARPS;
   constexpr int CV_BYTES = CV_TOTAL / 2 / EPI_WARPS;   // one buffer: scale vector, then shift vector
   constexpr int CV_HALF = CV_BYTES / 2;             // bytes of one per-column vector of a warp
@@ -203,7 +171,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
-  __shared__ uint64_t a_full[ARES_NK], a_empty[ARES_NK];      // ARES: one pair per resident A k-block
   __shared__ uint32_t tmem_base_slot;
 
   // The warp index goes through a shuffle so that the compiler can prove it warp-uniform: everything derived from it (roles,
@@ -229,15 +196,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   auto tile_nt = [&](int tile) { int r; if (p.nt_shift >= 0) r = tile & (n_tiles - 1); else r = tile % n_tiles; return r; };
   auto row_b = [&](int row) { int r; if (p.l_shift >= 0) r = row >> p.l_shift; else r = row / p.L; return r; };
   auto row_l = [&](int row) { int r; if (p.l_shift >= 0) r = row & (p.L - 1); else r = row % p.L; return r; };
-  // Tile walk of this worker, t = t_begin, t_begin + t_step, ... < t_end.  Round robin normally; ARES: a contiguous run,
-  // so that consecutive tiles are consecutive column tiles of the same row block (tile = row block * n_tiles + column tile).
-  int t_begin = worker, t_step = n_workers, t_end = num_tiles;
-  if constexpr (ARES) {
-    const int base = num_tiles / n_workers, rem = num_tiles % n_workers;
-    t_begin = worker * base + (worker < rem ? worker : rem);
-    t_end = t_begin + base + (worker < rem ? 1 : 0);
-    t_step = 1;
-  }
+  // Tile walk of this worker: t = t_begin, t_begin + t_step, ... < t_end (round robin over the workers)
+  const int t_begin = worker, t_step = n_workers, t_end = num_tiles;
 
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
@@ -249,12 +209,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
       ptx::mbar_init(&acc_empty[s], CG2 ? 2 * EPI_WARPS : EPI_WARPS);
-    }
-    if constexpr (ARES) {
-      for (int s = 0; s < ARES_NK; ++s) {
-        ptx::mbar_init(&a_full[s], 1);
-        ptx::mbar_init(&a_empty[s], 1);
-      }
     }
     ptx::fence_mbar_init();
   }
@@ -273,43 +227,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
   ptx::pdl_sync();          // everything above touched only this CTA's smem / TMEM
 
-  // (setmaxnreg sits at the head of each role branch so that it dominates the code whose register budget it changes)
   if (warp < EPI_WARP0) {
-  if constexpr (RD == 2) ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA; converged warp, one elected lane issues)
     {
       uint32_t stage = 0, phase = 0;
-      int cur_mb = -1;
-      uint32_t run = 0;                                    // ARES: row-block runs started so far
       for (int t = t_begin; t < t_end; t += t_step) {
         const int tile = p.reverse ? num_tiles - 1 - t : t;
         const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
         const int n0 = tile_nt(tile) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
-        if constexpr (ARES) {
-          const bool new_mb = tile_mb(tile) != cur_mb;
-          if (new_mb) { cur_mb = tile_mb(tile); ++run; }
-          for (int kb = 0; kb < nk; ++kb) {
-            if (new_mb) {
-              // slot kb of the resident block is free once the previous run's last tile has consumed it
-              ptx::mbar_wait_parked(&a_empty[kb], (run & 1) ^ 0);      // run r (1-based): parity of completion r - 1
-              if (ptx::elect_one()) {
-                if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * SL::A_BYTES);
-                ptx::tma_load_2d_cg2(smem + kb * SL::A_BYTES, &tmap_a, &a_full[kb], kb * BK, m0 + p.a_row_offset);
-              }
-              __syncwarp();
-            }
-            ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
-            if (ptx::elect_one()) {
-              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SL::B_BYTES);
-              ptx::tma_load_2d_cg2(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        } else
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
+          if (p.trace && blockIdx.x == 0 && lane == 0 && (kb == 0 || kb == k_blocks - 1)) {
+            const int ti = (t - t_begin) / t_step;
+            if (ti < 64) g_gemm_trace[2][ti][kb == 0 ? 0 : 1] = clock64();
+          }
           uint8_t* sa = smem + stage * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
           // split3: blocks [0, nk) A_hi.W_hi, [nk, 2nk) A_hi.W_lo, [2nk, 3nk) A_lo.W_hi
@@ -337,43 +269,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // one elected lane issues the MMAs and commits of a k-block)
     if (leader) {
       uint32_t stage = 0, phase = 0, it = 0;
-      int cur_mb = -1;
-      uint32_t run = 0;
       for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && it < 64;
+        if (tr) g_gemm_trace[0][it][0] = clock64();
         ptx::mbar_wait_parked(&acc_empty[as], aphase ^ 1);
+        if (tr) g_gemm_trace[0][it][1] = clock64();
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        if constexpr (ARES) {
-          const int mb = tile_mb(p.reverse ? num_tiles - 1 - t : t);
-          const bool new_mb = mb != cur_mb;
-          if (new_mb) { cur_mb = mb; ++run; }
-          // the run's last tile hands the resident A k-blocks back, one by one, behind its own MMAs
-          const bool last_of_run = t + 1 >= t_end || tile_mb(p.reverse ? num_tiles - 2 - t : t + 1) != mb;
-          for (int kb = 0; kb < nk; ++kb) {
-            if (new_mb) ptx::mbar_wait(&a_full[kb], (run & 1) ^ 1);      // run r (1-based) waits completion r
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tc_fence_after();
-            const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smem + kb * SL::A_BYTES));
-            const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem + SL::A_RES_BYTES + stage * SL::STAGE_BYTES));
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                ptx::umma_bf16_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), IDESC, (kb | k) != 0);
-              ptx::umma_commit_cg2(&empty_bar[stage], 3);
-              if (last_of_run) ptx::umma_commit_cg2(&a_empty[kb], 3);
-              if (kb == nk - 1) ptx::umma_commit_cg2(&acc_full[as], 3);
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        } else
         for (int kb = 0; kb < k_blocks; ++kb) {
-#if BIOM3_MMA_PARKED
-          ptx::mbar_wait_parked(&full_bar[stage], phase);
-#else
           ptx::mbar_wait(&full_bar[stage], phase);
-#endif
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t da = ptx::umma_desc_sw128(sa);
@@ -396,12 +301,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tr) g_gemm_trace[0][it][2] = clock64();
       }
     }
   }
   } else {
     // ------------------------------------------------------------ epilogue (8 or 16 warps, every CTA)
-    if constexpr (RD == 2) ptx::setmaxnreg_inc<224>();
     const uint32_t ew = warp - EPI_WARP0;
     const uint32_t quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
     const uint32_t col_half = ew >> 2;                 // 2 or 4 warps share a lane quarter and split the columns
@@ -410,27 +315,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t stg = ptx::smem_u32(smem + SL::STG_OFFSET + ew * STG_BYTES);
     const uint32_t cvs0 = ptx::smem_u32(smem + SL::CV_OFFSET + ew * 2 * CV_BYTES);   // two buffers: scale vector, then shift vector
     const int rr = lane >> 3, ch = lane & 7;           // fp32 read-phase mapping: row 4j + rr, 16-byte group ch
-    constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT || EPI == EPI_BIAS_RESID_SPLIT8);
-    constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT || EPI == EPI_BIAS_RESID_SPLIT8);
-    constexpr bool LO8 = (EPI == EPI_BIAS_RESID_SPLIT8);
+    constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_SPLIT);
+    constexpr bool SPLIT = (EPI == EPI_BIAS_RESID_SPLIT);
     auto tile_goff = [&](int t) -> size_t {            // element offset of this lane's first element of a tile (row rr, group ch)
       const int tile = p.reverse ? num_tiles - 1 - t : t;
       const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
       return size_t(m0 + quarter * 32 + rr) * p.N + tile_nt(tile) * BN + col_half * COLS_PER_WARP + 4 * ch;
     };
-    // byte offset of the same position in the tiled 8-bit lo plane (chunk 0, row rr): + c * 1024 per chunk, + j * 128 per 4 rows
-    auto tile_loff = [&](int t) -> size_t {
-      const int tile = p.reverse ? num_tiles - 1 - t : t;
-      const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
-      return ptx::lo8_offset(size_t(m0 + quarter * 32 + rr), tile_nt(tile) * BN + col_half * COLS_PER_WARP + 4 * ch, p.N);
-    };
-    // 4 residual values at element offset `off`, as raw bits: fp32 x 4, (hi bf16 x 4, lo bf16 x 4) or (hi bf16 x 4, lo s8 x 4)
-    auto load_res = [&](size_t off, size_t loff) -> uint4 {
-      if constexpr (LO8) {
-        const uint2 h = *reinterpret_cast<const uint2*>(p.out_bf16 + off);
-        const uint32_t l = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.out) + loff);
-        return make_uint4(h.x, h.y, l, 0u);
-      } else if constexpr (SPLIT) {
+    // 4 residual values at element offset `off`, as raw bits: fp32 x 4 or (hi bf16 x 4, lo bf16 x 4)
+    auto load_res = [&](size_t off) -> uint4 {
+      if constexpr (SPLIT) {
         const uint2 h = *reinterpret_cast<const uint2*>(p.out_bf16 + off);
         const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + off);
         return make_uint4(h.x, h.y, l.x, l.y);
@@ -449,24 +343,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     };
     // Residual rows of the chunk being processed; each slot is reloaded right after it is consumed with the value of the
-    // chunk RD positions later in the walk (the next tile's first chunks at the end of a tile), so every load has RD chunk
-    // periods to land.  RD = 1 (default): 32 registers of prefetched data; RD = 2: two buffers used alternately, 64 registers.
-    // ncu attributes 35-45 % of this epilogue's stall samples to these loads and the K sweep in DESIGN.md shows 10.8 us per
-    // tile whatever K is, which reads as latency bound — but RD = 2 measured 3 % SLOWER per tile and 7 % slower on the
-    // out-proj GEMM in the step, so the second chunk period is not what it lacks.  Kept as a switch (BIOM3_RESID_DEPTH=2).
-    // Chunk walk: RD = 1 visits the 32-column chunks 0, 2, 1, 3 so that the prefetch of the next chunk never touches the
-    // 128-byte line the current chunk is storing to (two chunks of a bf16 plane share a line); with RD = 2 the loads
-    // issued during a chunk are for the position after next, and the natural order 0, 1, 2, 3 keeps THOSE on the other line.
-    auto order = [](int i) { return (SPLIT && NCH == 4 && RD == 1) ? (((i & 1) << 1) | (i >> 1)) : i; };
-    uint4 res[RD][8];
-    uint32_t dres[4][8];                                   // EPI_BIAS_RESID_DIRECT: prefetched hi (2 x 32 B) and lo (2 x 32 B) of a chunk
+    // next chunk of the walk (the next tile's first chunk at the end of a tile): 32 registers of prefetched data.  The walk
+    // visits the 32-column chunks 0, 2, 1, 3 so that the prefetch of the next chunk never touches the 128-byte line the
+    // current chunk is storing to (two chunks of a bf16 plane share a line; walking 0, 1, 2, 3 was 2.5 x slower).  A
+    // second chunk in flight (setmaxnreg register reallocation), an 8-bit lo plane and a thread-per-row variant were
+    // built in round 1 and measured slower (profiles/r01_ab_resid_depth.jsonl, r01_ab_lo8.jsonl, r01_ab_resid_direct.jsonl).
+    auto order = [](int i) { return (SPLIT && NCH == 4) ? (((i & 1) << 1) | (i >> 1)) : i; };
+    uint4 res[8];
     if constexpr (RESID) {
       if (t_begin < t_end) {
-        const size_t g0 = tile_goff(t_begin), l0 = LO8 ? tile_loff(t_begin) : 0;
+        const size_t g0 = tile_goff(t_begin);
 #pragma unroll
-        for (int b = 0; b < RD; ++b)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[b][j] = load_res(g0 + order(b) * 32 + size_t(4 * j) * p.N, l0 + order(b) * 1024 + j * 128);
+        for (int j = 0; j < 8; ++j) res[j] = load_res(g0 + order(0) * 32 + size_t(4 * j) * p.N);
       }
     }
     // bf16 epilogues with a folded LayerNorm: the per-tile inputs (this warp's slices of ln_s / ln_t and its rows' partial
@@ -474,7 +362,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // 8 registers — so their L2 latency no longer sits at the head of every tile (it was ~30 % of the epilogue warps'
     // stall samples in ncu).  Statistics with more than 4 partial slots per row fall back to loading at the point of use.
     constexpr bool kVecEpi = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR);
-    const bool pipe = kVecEpi && p.ln_stats != nullptr && (p.ln_parts == 2 || p.ln_parts == 4) && p.debug_skip == 0 && !p.no_pipe;
+    const bool pipe = kVecEpi && p.ln_stats != nullptr && (p.ln_parts == 2 || p.ln_parts == 4);
     float4 pst[2];                                        // prefetched partial statistics of this thread's row
     auto tile_rn = [&](int t, int& rbase_o, int& nbase_o) {
       const int tile = p.reverse ? num_tiles - 1 - t : t;
@@ -507,110 +395,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int bidx = row_b(rbase);                       // 32-row blocks never straddle samples (L % 128 == 0)
       const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
 
-      if (p.debug_skip == 1 || p.debug_skip == 2) {
-        ptx::mbar_wait_parked(&acc_full[as], aphase);
-        ptx::tc_fence_after();
-        if (p.debug_skip == 1) {
-          uint32_t r[32];
-          for (int c = 0; c < NCH; ++c) {
-            ptx::tmem_ld_32x32(t_row + c * 32, r);
-            ptx::tmem_ld_wait();
-          }
-          if (r[lane] == 0x7fc12345u) reinterpret_cast<float*>(p.out)[0] = 1.f;   // keep the loads alive
-        }
-        release_acc(as);
-      } else if constexpr (EPI == EPI_BIAS_RESID_DIRECT) {
-        // thread = row.  Bias (+ the next layer's conditioning vector) of the warp's 128 columns is staged once per tile in
-        // warp-private smem and read back as broadcasts; the residual of the next chunk (or of the next tile's first
-        // chunk) is loaded into registers before the current chunk's math, as in the transposed path.
-        const int next_t = t + t_step;
-        const bool have_next = next_t < t_end;
-        auto row_ptr = [&](int tt, const __nv_bfloat16* base) {
-          int rb, nb;
-          tile_rn(tt, rb, nb);
-          return base + size_t(rb + lane) * p.N + nb;
-        };
-        __nv_bfloat16* hi_row = const_cast<__nv_bfloat16*>(row_ptr(t, p.out_bf16));
-        __nv_bfloat16* lo_row = const_cast<__nv_bfloat16*>(row_ptr(t, reinterpret_cast<const __nv_bfloat16*>(p.out)));
-        {
-          const int vl = lane < COLS_PER_WARP / 4 ? lane : 0;
-          float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + vl);
-          if (p.cond) {
-            const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase) + vl);
-            b4.x += cv.x; b4.y += cv.y; b4.z += cv.z; b4.w += cv.w;
-          }
-          __syncwarp();                                    // the previous tile's reads of the staged vector are done
-          if (lane < COLS_PER_WARP / 4)
-            st_shared_v4(cvs0 + lane * 16, __float_as_uint(b4.x), __float_as_uint(b4.y), __float_as_uint(b4.z), __float_as_uint(b4.w));
-          __syncwarp();
-        }
-        auto order = [](int i) { return NCH == 4 ? (((i & 1) << 1) | (i >> 1)) : i; };   // chunks 0, 2, 1, 3: see the transposed path
-        if (it == 0) {
-          ptx::ld_global_v8(hi_row + order(0) * 32, dres[0]);
-          ptx::ld_global_v8(hi_row + order(0) * 32 + 16, dres[1]);
-          ptx::ld_global_v8(lo_row + order(0) * 32, dres[2]);
-          ptx::ld_global_v8(lo_row + order(0) * 32 + 16, dres[3]);
-        }
-        float rsum = 0.f, rsq = 0.f;
-        ptx::mbar_wait_parked(&acc_full[as], aphase);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          const int c = order(ci);
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + c * 32, r);
-          uint32_t cur[4][8];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) cur[a][b] = dres[a][b];
-          if (ci + 1 < NCH) {
-            ptx::ld_global_v8(hi_row + order(ci + 1) * 32, dres[0]);
-            ptx::ld_global_v8(hi_row + order(ci + 1) * 32 + 16, dres[1]);
-            ptx::ld_global_v8(lo_row + order(ci + 1) * 32, dres[2]);
-            ptx::ld_global_v8(lo_row + order(ci + 1) * 32 + 16, dres[3]);
-          } else if (have_next) {
-            const __nv_bfloat16* nh = row_ptr(next_t, p.out_bf16);
-            const __nv_bfloat16* nl = row_ptr(next_t, reinterpret_cast<const __nv_bfloat16*>(p.out));
-            ptx::ld_global_v8(nh + order(0) * 32, dres[0]);
-            ptx::ld_global_v8(nh + order(0) * 32 + 16, dres[1]);
-            ptx::ld_global_v8(nl + order(0) * 32, dres[2]);
-            ptx::ld_global_v8(nl + order(0) * 32 + 16, dres[3]);
-          }
-          ptx::tmem_ld_wait();
-          if (ci + 1 == NCH) release_acc(as);
-          uint32_t oh[16], ol[16];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {                    // 4 columns: hi / lo pair words 2g, 2g + 1 of the chunk
-            const uint4 bu = ld_shared_v4(cvs0 + (c * 32 + 4 * g) * 4);
-            const uint32_t h0 = cur[g >> 2][(2 * g) & 7], h1 = cur[g >> 2][(2 * g + 1) & 7];
-            const uint32_t l0 = cur[2 + (g >> 2)][(2 * g) & 7], l1 = cur[2 + (g >> 2)][(2 * g + 1) & 7];
-            float4 o;
-            o.x = __uint_as_float(r[4 * g]) + ((__uint_as_float(h0 << 16) + __uint_as_float(l0 << 16)) + __uint_as_float(bu.x));
-            o.y = __uint_as_float(r[4 * g + 1]) + ((__uint_as_float(h0 & 0xffff0000u) + __uint_as_float(l0 & 0xffff0000u)) + __uint_as_float(bu.y));
-            o.z = __uint_as_float(r[4 * g + 2]) + ((__uint_as_float(h1 << 16) + __uint_as_float(l1 << 16)) + __uint_as_float(bu.z));
-            o.w = __uint_as_float(r[4 * g + 3]) + ((__uint_as_float(h1 & 0xffff0000u) + __uint_as_float(l1 & 0xffff0000u)) + __uint_as_float(bu.w));
-            const uint32_t n0 = ptx::pack_bf16x2(o.x, o.y), n1 = ptx::pack_bf16x2(o.z, o.w);
-            oh[2 * g] = n0;
-            oh[2 * g + 1] = n1;
-            ol[2 * g] = ptx::pack_bf16x2(o.x - __uint_as_float(n0 << 16), o.y - __uint_as_float(n0 & 0xffff0000u));
-            ol[2 * g + 1] = ptx::pack_bf16x2(o.z - __uint_as_float(n1 << 16), o.w - __uint_as_float(n1 & 0xffff0000u));
-            rsum += (o.x + o.y) + (o.z + o.w);
-            rsq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-          }
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            ptx::st_global_v8(hi_row + c * 32 + 16 * hlf, oh[8 * hlf], oh[8 * hlf + 1], oh[8 * hlf + 2], oh[8 * hlf + 3], oh[8 * hlf + 4],
-                              oh[8 * hlf + 5], oh[8 * hlf + 6], oh[8 * hlf + 7]);
-            ptx::st_global_v8(lo_row + c * 32 + 16 * hlf, ol[8 * hlf], ol[8 * hlf + 1], ol[8 * hlf + 2], ol[8 * hlf + 3], ol[8 * hlf + 4],
-                              ol[8 * hlf + 5], ol[8 * hlf + 6], ol[8 * hlf + 7]);
-          }
-        }
-        if (p.stats_out) {
-          const int parts = n_tiles * 2, part = n_tile * 2 + col_half;
-          *reinterpret_cast<float2*>(p.stats_out + (size_t(rbase + lane) * parts + part) * 2) = make_float2(rsum, rsq);
-        }
-      } else if constexpr (RESID || EPI == EPI_STORE_F32) {
+      if constexpr (RESID || EPI == EPI_STORE_F32) {
         // fp32 path.  Read phase: iteration j covers rows 4j..4j+3, lane -> (row 4j + lane/8, 16-byte column
         // group lane%8): every global access is 4 full 128-byte lines per warp instruction (4 x 64 bytes per array
         // in the split form).  The residual of the NEXT chunk (or of the next tile's first chunk) is always in flight
@@ -622,7 +407,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int next_t = t + t_step;
         const bool have_next = next_t < t_end;
         const size_t gnext = have_next ? tile_goff(next_t) : 0;
-        const size_t loff = LO8 ? tile_loff(t) : 0, lnext = (LO8 && have_next) ? tile_loff(next_t) : 0;
         float4 addv[NCH];                                  // bias (+ conditioning) of this lane's columns, per chunk
         if constexpr (RESID) {
 #pragma unroll
@@ -634,16 +418,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][0] = clock64();
         ptx::mbar_wait_parked(&acc_full[as], aphase);
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][1] = clock64();
         ptx::tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int c = order(ci);
-          // position ci + RD of the walk: a later chunk of this tile, or one of the next tile's first RD chunks
-          const bool more = (ci + RD < NCH) || have_next;
-          const size_t gn = (ci + RD < NCH) ? goff + order(ci + RD) * 32 : gnext + order(ci + RD - NCH) * 32;
-          const size_t ln = (ci + RD < NCH) ? loff + order(ci + RD) * 1024 : lnext + order(ci + RD - NCH) * 1024;
-          auto& resb = res[ci % RD];                           // buffer of this position (NCH is a multiple of RD)
+          // next position of the walk: the next chunk of this tile, or the next tile's first chunk
+          const bool more = (ci + 1 < NCH) || have_next;
+          const size_t gn = (ci + 1 < NCH) ? goff + order(ci + 1) * 32 : gnext + order(0) * 32;
+          auto& resb = res;
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + c * 32, r);
           ptx::tmem_ld_wait();
@@ -660,11 +445,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             float4 o = make_float4(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w));
             if constexpr (RESID) {
               const uint4 rb = resb[j];
-              if (more) resb[j] = load_res(gn + size_t(4 * j) * p.N, ln + j * 128);
+              if (more) resb[j] = load_res(gn + size_t(4 * j) * p.N);
               float4 rv;
-              if constexpr (LO8) {
-                rv = ptx::split8_decode(rb.x, rb.y, rb.z);
-              } else if constexpr (SPLIT) {
+              if constexpr (SPLIT) {
                 rv = make_float4(__uint_as_float(rb.x << 16) + __uint_as_float(rb.z << 16),
                                  __uint_as_float(rb.x & 0xffff0000u) + __uint_as_float(rb.z & 0xffff0000u),
                                  __uint_as_float(rb.y << 16) + __uint_as_float(rb.w << 16),
@@ -675,12 +458,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               o.x += rv.x + add.x; o.y += rv.y + add.y; o.z += rv.z + add.z; o.w += rv.w + add.w;
             }
             const size_t eoff = goff + size_t(4 * j) * p.N + c * 32;
-            if constexpr (LO8) {
-              uint32_t h0, h1, l8;
-              ptx::split8_encode(o, h0, h1, l8);
-              *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(h0, h1);
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out) + loff + c * 1024 + j * 128) = l8;
-            } else if constexpr (SPLIT) {
+            if constexpr (SPLIT) {
               const uint32_t h0 = ptx::pack_bf16x2(o.x, o.y), h1 = ptx::pack_bf16x2(o.z, o.w);
               *reinterpret_cast<uint2*>(p.out_bf16 + eoff) = make_uint2(h0, h1);
               *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + eoff) =
@@ -717,6 +495,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
         release_acc(as);           // (an earlier release costs registers this 168-register path does not have)
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][2] = clock64();
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][3] = clock64();
       } else {
         // bf16 path: thread = row while the fused math runs, then a 32 x 64-byte block is transposed
         // through smem so each warp store instruction writes 8 rows x 64 contiguous bytes.
@@ -770,23 +550,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         if constexpr (EPI == EPI_BIAS_GELU_BF16) rstd *= 0.5f;   // x / 2 = acc * (rstd / 2) + (-mean * rstd / 2) * s[n] + t[n] / 2
         const float nm = -mean * rstd;
-        // output addressing, hoisted out of the chunk loop (a warp's 128 columns never straddle q/k/v or a sample)
-        __nv_bfloat16* dst0;
-        size_t row_stride, chunk_stride;                   // elements between rows of a block / between chunks
-        if constexpr (EPI == EPI_QKV_HEADMAJOR) {
-          const int D = p.N / 3;
-          int which, hrem;
-          if (p.d_shift >= 0) { which = nbase >> p.d_shift; hrem = nbase & (D - 1); }
-          else { which = nbase / D; hrem = nbase % D; }
-          const int h0 = hrem >> 5, l0 = row_l(rbase);
-          dst0 = reinterpret_cast<__nv_bfloat16*>(p.out) + ((((size_t(which) * p.Bsz + bidx) * p.H + h0) * p.L + l0) << 5);
-          row_stride = 32;
-          chunk_stride = size_t(p.L) << 5;
-        } else {
-          dst0 = reinterpret_cast<__nv_bfloat16*>(p.out) + size_t(p.debug_skip == 6 ? (rbase & 1023) : rbase) * p.N + nbase;
-          row_stride = p.N;
-          chunk_stride = 32;
-        }
         int tma_c0 = nbase, tma_c1 = rbase;                // TMA-store coordinates (column, row) of chunk 0
         if constexpr (EPI == EPI_QKV_HEADMAJOR) {
           const int D = p.N / 3;
@@ -796,7 +559,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           else { which = nbase / D; hrem = nbase % D; }
           tma_c1 = ((which * p.Bsz + bidx) * p.H + (hrem >> 5)) * p.L + row_l(rbase);
         }
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][0] = clock64();
         ptx::mbar_wait_parked(&acc_full[as], aphase);
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][1] = clock64();
         ptx::tc_fence_after();
         uint32_t r[2][32];                                 // TMEM loads run one chunk ahead of the math
         ptx::tmem_ld_32x32(t_row, r[0]);
@@ -804,7 +569,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int c = 0; c < NCH; ++c) {
           ptx::tmem_ld_wait();
           if (c + 1 < NCH) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
-          else release_acc(as);
+          else { release_acc(as); if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][2] = clock64(); }
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
@@ -820,60 +585,34 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
           if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-            if (p.debug_skip != 5) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
-            }
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
           }
-          if (p.tma_store == 2) {
-            // Direct stores: thread = row, its 32 columns of the chunk are 64 contiguous bytes in both output layouts ->
-            // two 256-bit stores of full 32-byte sectors, no shared-memory staging at all.  The mainloop keeps the SM's
-            // shared-memory port busy (TMA writes + MMA operand reads), so every staged byte costs mainloop time.
-            __nv_bfloat16* dst = dst0 + size_t(lane) * row_stride + size_t(c) * chunk_stride;
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-              ptx::st_global_v8(dst + 16 * i, ptx::pack_bf16x2(v[16 * i], v[16 * i + 1]), ptx::pack_bf16x2(v[16 * i + 2], v[16 * i + 3]),
-                                ptx::pack_bf16x2(v[16 * i + 4], v[16 * i + 5]), ptx::pack_bf16x2(v[16 * i + 6], v[16 * i + 7]),
-                                ptx::pack_bf16x2(v[16 * i + 8], v[16 * i + 9]), ptx::pack_bf16x2(v[16 * i + 10], v[16 * i + 11]),
-                                ptx::pack_bf16x2(v[16 * i + 12], v[16 * i + 13]), ptx::pack_bf16x2(v[16 * i + 14], v[16 * i + 15]));
-            continue;
-          }
-          if (p.tma_store == 1) {
-            // the previous chunk's TMA store must have finished READING the staging block before it is rewritten
-            if (lane == 0) ptx::tma_store_wait_read();
-            __syncwarp();
-          }
+          // the previous chunk's TMA store must have finished READING the staging block before it is rewritten
+          if (lane == 0) ptx::tma_store_wait_read();
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             st_shared_v4(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]),
                          ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
                          ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          if (p.tma_store == 1) {
-            // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one lane stores
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (ptx::elect_one()) {
-              ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
-                                tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
-              ptx::tma_store_commit();
-            }
-          } else {
-            __syncwarp();
-            __nv_bfloat16* dst = dst0 + size_t(c) * chunk_stride;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int piece = j * 32 + lane, row = piece >> 2, pc = piece & 3;
-              const uint4 val = ld_shared_v4(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
-              if (p.debug_skip != 3 || val.x == 0x7fc12345u) *reinterpret_cast<uint4*>(dst + size_t(row) * row_stride + pc * 8) = val;
-            }
+          // the 64B-swizzled staging block IS the TMA box layout: publish it to the async proxy, one elected lane stores
+          // (a coalesced st.global path and direct 256-bit stores were measured 5-7 % slower, profiles/r01_ab_store_mode.jsonl)
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (ptx::elect_one()) {
+            ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
+                              tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
+            ptx::tma_store_commit();
           }
           __syncwarp();
         }
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][3] = clock64();
       }
     }
   }
 
-  if (p.tma_store == 1 && warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
+  if (warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads
   ptx::tc_fence_before();
   __syncwarp();
   if constexpr (CG2) ptx::cluster_sync_all(); else __syncthreads();

@@ -85,7 +85,7 @@ __global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* _
 __global__ void __launch_bounds__(256)
 embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, const float* __restrict__ ax0,
              const float* __restrict__ ax1, const float* __restrict__ cvec, int cond_stride, float* __restrict__ u,
-             __nv_bfloat16* __restrict__ ub, __nv_bfloat16* __restrict__ ulo, int lo8, float* __restrict__ stats, int parts,
+             __nv_bfloat16* __restrict__ ub, __nv_bfloat16* __restrict__ ulo, float* __restrict__ stats, int parts,
              int rows, int L, int W, int D) {
   ptx::pdl_sync();
   const int lane = threadIdx.x & 31;
@@ -110,11 +110,7 @@ embed_kernel(const uint8_t* __restrict__ state, const float* __restrict__ emb, c
                                      (x0.z + (x1.z + x2.z)) + x3.z, (x0.w + (x1.w + x2.w)) + x3.w);
         const uint32_t h0 = ptx::pack_bf16x2(v.x, v.y), h1 = ptx::pack_bf16x2(v.z, v.w);
         *reinterpret_cast<uint2*>(ub + size_t(row) * D + col) = make_uint2(h0, h1);
-        if (ulo && lo8) {       // split residual stream with the 8-bit remainder in the tiled lo plane (ptx::split8_*)
-          uint32_t e0, e1, l8;
-          ptx::split8_encode(v, e0, e1, l8);
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ulo) + ptx::lo8_offset(size_t(row), col, D)) = l8;
-        } else if (ulo)       // split residual stream: u = hi + lo, both bf16 (see gemm::EPI_BIAS_RESID_SPLIT)
+        if (ulo)              // split residual stream: u = hi + lo, both bf16 (see gemm::EPI_BIAS_RESID_SPLIT)
           *reinterpret_cast<uint2*>(ulo + size_t(row) * D + col) =
               make_uint2(ptx::pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u)),
                          ptx::pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u)));
@@ -253,7 +249,7 @@ __global__ void __launch_bounds__(256)
 gather_rows_kernel(const __nv_bfloat16* __restrict__ att, const __nv_bfloat16* __restrict__ u_hi,
                    const __nv_bfloat16* __restrict__ u_lo, __nv_bfloat16* __restrict__ att_c,
                    __nv_bfloat16* __restrict__ hi_c, __nv_bfloat16* __restrict__ lo_c, const int* __restrict__ inv_path,
-                   const DecodeCtl* __restrict__ ctl, int L, int D, int group, int ntok, int rows_c, int lo8) {
+                   const DecodeCtl* __restrict__ ctl, int L, int D, int group, int ntok, int rows_c) {
   ptx::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int step = ctl->step;
@@ -262,8 +258,6 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ att, const __nv_bfloat16* _
     uint4* da = reinterpret_cast<uint4*>(att_c + size_t(ti) * D);
     uint4* dh = reinterpret_cast<uint4*>(hi_c + size_t(ti) * D);
     uint4* dl = reinterpret_cast<uint4*>(lo_c + size_t(ti) * D);
-    // 8-bit tiled lo plane: a row is D / 32 pieces of 32 bytes, one per 32-column chunk block (ptx::lo8_offset)
-    uint8_t* dl8 = reinterpret_cast<uint8_t*>(lo_c) + ptx::lo8_offset(size_t(ti), 0, D);
     if (ti < ntok) {
       const int b = ti / group;
       const int src = (b / group) * group + (ti % group);          // sample whose location is written (head_kernel)
@@ -274,23 +268,15 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ att, const __nv_bfloat16* _
       for (int i = lane; i < n16; i += 32) {
         da[i] = sa[i];
         dh[i] = sh[i];
-        if (!lo8) dl[i] = sl[i];
-      }
-      if (lo8) {
-        const uint8_t* sl8 = reinterpret_cast<const uint8_t*>(u_lo) + ptx::lo8_offset(row, 0, D);
-        for (int i = lane; i < D / 16; i += 32)        // 16-byte halves of the 32-byte pieces, 1 KB apart
-          *reinterpret_cast<uint4*>(dl8 + size_t(i >> 1) * 1024 + (i & 1) * 16) =
-              *reinterpret_cast<const uint4*>(sl8 + size_t(i >> 1) * 1024 + (i & 1) * 16);
+        dl[i] = sl[i];
       }
     } else {
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       for (int i = lane; i < n16; i += 32) {
         da[i] = z;
         dh[i] = z;
-        if (!lo8) dl[i] = z;
+        dl[i] = z;
       }
-      if (lo8)
-        for (int i = lane; i < D / 16; i += 32) *reinterpret_cast<uint4*>(dl8 + size_t(i >> 1) * 1024 + (i & 1) * 16) = z;
     }
   }
 }
@@ -310,7 +296,6 @@ struct HeadArgs {
   const int* inv_path;       // [B][L] (SELECTED mode)
   const DecodeCtl* ctl;      // step / noise / seed (sampling)
   int B, L, D, C, group;     // group = samples per reference batch (SELECTED mode); 0 -> ALL mode
-  int lo8;                   // u_lo is the tiled 8-bit remainder plane (ptx::split8_*)
   int compact;               // SELECTED mode: the hidden rows are compacted, entry ti lives in row ti (gather_rows_kernel)
 };
 
@@ -346,12 +331,6 @@ head_kernel(const HeadArgs a) {
           v[i] = *reinterpret_cast<const float4*>(a.u + hrow * a.D + (i * 32 + lane) * 4);
         } else {
           const uint2 h = *reinterpret_cast<const uint2*>(a.u_hi + hrow * a.D + (i * 32 + lane) * 4);
-          if (a.lo8) {
-            v[i] = ptx::split8_decode(h.x, h.y, *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.u_lo) +
-                                                                                 ptx::lo8_offset(hrow, (i * 32 + lane) * 4, a.D)));
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            continue;
-          }
           const uint2 l = *reinterpret_cast<const uint2*>(a.u_lo + hrow * a.D + (i * 32 + lane) * 4);
           v[i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
                              __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),

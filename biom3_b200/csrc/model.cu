@@ -118,67 +118,30 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-// Operand-ring depth.  Pair tiling, 256-wide tiles: 5 stages of 32 KB; the QKV epilogue (8 warps, 16 KB of staging) and the residual
-// epilogues (no per-column vectors) leave room for a sixth (compile-time A/B: BIOM3_QKV_STAGES / BIOM3_RESID_STAGES).
-#ifndef BIOM3_QKV_STAGES
-#define BIOM3_QKV_STAGES 5
-#endif
-#ifndef BIOM3_RESID_STAGES
-#define BIOM3_RESID_STAGES 5
-#endif
+// Operand-ring depth.  Pair tiling, 256-wide tiles: 5 stages of 32 KB (3, 4 and 6 were measured: profiles/r01_ab_resid_ring_depth.jsonl;
+// a 6-stage QKV ring again in round 2: no change)
 template <int BN, bool CG2, int EPI>
 constexpr int gemm_stages() {
-  if (CG2 && BN == 256) {
-    if (EPI == gemm::EPI_QKV_HEADMAJOR && gemm::epi_warps(EPI) == 8) return BIOM3_QKV_STAGES;
-    if (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT || EPI == gemm::EPI_BIAS_RESID_SPLIT8) return BIOM3_RESID_STAGES;
-    return 5;
-  }
+  if (CG2 && BN == 256) return 5;
   return CG2 ? 7 : (BN == 256 ? 3 : 5);
-}
-constexpr int ARES_STAGES = 4;     // weight-ring stages of the A-resident variant (gemm_tcgen05.cuh)
-
-// A-resident pair-tiled launch (bf16 epilogues, K <= 512): contiguous tile runs per CTA pair
-template <int EPI>
-void launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p_in,
-                      int num_sms, cudaStream_t st) {
-  gemm::Params p = p_in;
-  gemm::fill_shifts(p, 256);
-  const int smem = gemm::SmemLayout<256, ARES_STAGES, true, true, EPI>::TOTAL;
-  const int tiles = (p.M / 256) * (p.N / 256);
-  const int workers = num_sms / 2;
-  const int grid = (tiles < workers ? tiles : workers) * 2;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(64 + 32 * gemm::epi_warps(EPI, true));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>, ta, tb, tc, p);
 }
 
 // launch only; the caller checks cudaGetLastError()
-template <int BN, int EPI, bool CG2, int RD = 1>
+template <int BN, int EPI, bool CG2>
 void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p_in,
                    int num_sms, cudaStream_t st) {
   gemm::Params p = p_in;
   gemm::fill_shifts(p, BN);
   constexpr int STAGES = gemm_stages<BN, CG2, EPI>();
-  const int smem = gemm::SmemLayout<BN, STAGES, CG2, false, EPI>::TOTAL;
+  const int smem = gemm::SmemLayout<BN, STAGES, CG2, EPI>::TOTAL;
   const int tiles = (p.M / (CG2 ? 256 : 128)) * (p.N / BN);
   const int workers = CG2 ? num_sms / 2 : num_sms;
   const int grid = (tiles < workers ? tiles : workers) * (CG2 ? 2 : 1);
+  const int threads = 32 * (int(gemm::EPI_WARP0) + gemm::epi_warps(EPI));
   if constexpr (CG2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(32 * (gemm::epi_warp0(RD) + gemm::epi_warps(EPI)));
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -190,27 +153,20 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true, false, RD>, ta, tb, tc, p);
+    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, p);
   } else {
-    launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(64 + 32 * gemm::epi_warps(EPI)), size_t(smem), st,
-             ta, tb, tc, p);
+    launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(threads), size_t(smem), st, ta, tb, tc, p);
   }
 }
 
 // bn: 128 or 256 columns per tile.  pair: CTA-pair (cta_group::2) tiling, needs bn == 256 and M % 256 == 0;
 // `tb` must then be the 128-row-box weight map (each CTA stages half of the 256 weight rows).
-// rd: residual prefetch depth of the pair-tiled residual epilogues (1 or 2, see gemm_tcgen05.cuh); ignored elsewhere
 template <int EPI>
 void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                 const gemm::Params& p, int num_sms, cudaStream_t st, int rd = 1) {
-  constexpr bool kResid = (EPI == gemm::EPI_BIAS_RESID_F32 || EPI == gemm::EPI_BIAS_RESID_SPLIT || EPI == gemm::EPI_BIAS_RESID_SPLIT8);
-  if (bn == 128) launch_gemm_t<128, EPI, false>(ta, tb, tc, p, num_sms, st);
-  else if (pair) {
-    if constexpr (kResid) {
-      if (rd == 2) { launch_gemm_t<256, EPI, true, 2>(ta, tb, tc, p, num_sms, st); return; }
-    }
-    launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
-  } else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
+                 const gemm::Params& p, int num_sms, cudaStream_t st) {
+  (void)bn;                                     // tiles are 256 columns wide (128-wide tiles were measured slower in round 1)
+  if (pair) launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
+  else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -221,81 +177,25 @@ cudaError_t init_kernel_attributes_impl() {
 #define SET_GEMM1(BN, EPI, CG2)                                                                                  \
   e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<BN, gemm_stages<BN, CG2, EPI>(), EPI, CG2>,                   \
                            cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<BN, gemm_stages<BN, CG2, EPI>(), CG2, false, EPI>::TOTAL);           \
+                           gemm::SmemLayout<BN, gemm_stages<BN, CG2, EPI>(), CG2, EPI>::TOTAL);                  \
   if (e != cudaSuccess) return e;
-#define SET_GEMM(EPI) SET_GEMM1(256, EPI, false) SET_GEMM1(128, EPI, false) SET_GEMM1(256, EPI, true)
+#define SET_GEMM(EPI) SET_GEMM1(256, EPI, false) SET_GEMM1(256, EPI, true)
   SET_GEMM(gemm::EPI_QKV_HEADMAJOR)
   SET_GEMM(gemm::EPI_BIAS_RESID_F32)
   SET_GEMM(gemm::EPI_BIAS_RESID_SPLIT)
-  SET_GEMM(gemm::EPI_BIAS_RESID_SPLIT8)
-  SET_GEMM(gemm::EPI_BIAS_RESID_DIRECT)
   SET_GEMM(gemm::EPI_BIAS_GELU_BF16)
   SET_GEMM(gemm::EPI_STORE_BF16)
   SET_GEMM(gemm::EPI_STORE_F32)
 #undef SET_GEMM1
 #undef SET_GEMM
-#define SET_RD2(EPI)                                                                                             \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, gemm_stages<256, true, EPI>(), EPI, true, false, 2>,     \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<256, gemm_stages<256, true, EPI>(), true, false, EPI>::TOTAL);       \
+  e = cudaFuncSetAttribute(attn::local_attention_kernel<attn::LOCAL_NST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::LocalCfg<attn::LOCAL_NST>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  SET_RD2(gemm::EPI_BIAS_RESID_F32)
-  SET_RD2(gemm::EPI_BIAS_RESID_SPLIT)
-  SET_RD2(gemm::EPI_BIAS_RESID_SPLIT8)
-#undef SET_RD2
-#define SET_ARES(EPI)                                                                                            \
-  e = cudaFuncSetAttribute(gemm::gemm_bf16_tcgen05<256, ARES_STAGES, EPI, true, true>,                           \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize,                                          \
-                           gemm::SmemLayout<256, ARES_STAGES, true, true, EPI>::TOTAL);                          \
-  if (e != cudaSuccess) return e;
-  SET_ARES(gemm::EPI_STORE_BF16)
-  SET_ARES(gemm::EPI_QKV_HEADMAJOR)
-  SET_ARES(gemm::EPI_BIAS_GELU_BF16)
-#undef SET_ARES
-  e = cudaFuncSetAttribute(attn::local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           attn::LOCAL_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn::local_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           attn::TC_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn::local_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           attn::TC2_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn::local_attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           attn::TC3_SMEM_BYTES);
+  e = cudaFuncSetAttribute(attn::local_attention_kernel<attn::LOCAL_NST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           attn::LocalCfg<attn::LOCAL_NST>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-#define SET_MS(NS, BK, POLY)                                                                                     \
-  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<NS, BK, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           attn::MsCfg<NS, BK>::SMEM_BYTES);                                                     \
-  if (e != cudaSuccess) return e;
-  SET_MS(2, 64, 0) SET_MS(4, 32, 0) SET_MS(4, 32, 4) SET_MS(4, 32, 8) SET_MS(2, 64, 8)
-#undef SET_MS
-#define SET_ABL(A)                                                                                               \
-  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           attn::MsCfg<2, 64>::SMEM_BYTES);                                                      \
-  if (e != cudaSuccess) return e;
-  SET_ABL(1) SET_ABL(2) SET_ABL(3) SET_ABL(4) SET_ABL(7) SET_ABL(8) SET_ABL(21) SET_ABL(22) SET_ABL(23) SET_ABL(30)
-#undef SET_ABL
-  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, 0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::MsCfg<2, 64, 6>::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn::local_attention_ms_kernel<2, 64, 0, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::MsCfg<2, 64, 6>::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-#define SET_V5(NST, TR)                                                                                         \
-  e = cudaFuncSetAttribute(attn::local_attention_v5_kernel<NST, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           attn::V5Cfg<NST>::SMEM_BYTES);                                                        \
-  if (e != cudaSuccess) return e;
-  SET_V5(3, 0) SET_V5(4, 0) SET_V5(5, 0) SET_V5(6, 0) SET_V5(3, 1)
-#undef SET_V5
-#define SET_V5T(NST, TR, TU, PO)                                                                                \
-  e = cudaFuncSetAttribute(attn::local_attention_v5_kernel<NST, TR, TU, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           attn::V5Cfg<NST>::SMEM_BYTES);                                                        \
-  if (e != cudaSuccess) return e;
-  SET_V5T(5, 0, 1, 0) SET_V5T(5, 1, 1, 0) SET_V5T(5, 0, 1, 4) SET_V5T(5, 0, 1, 8) SET_V5T(5, 0, 0, 4) SET_V5T(5, 1, 1, 4)
-#undef SET_V5T
-  e = cudaFuncSetAttribute(attn::linear_attention_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::LINC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
   if (e != cudaSuccess) return e;
@@ -321,68 +221,17 @@ cudaError_t init_kernel_attributes() {
   return e;
 }
 
-// windowed attention, multi-stream template (attention.cuh): variant 4 = <2, 64, 0> (the round-1 schedule), 5 = <4, 32, 0>,
-// 6 = <4, 32, 4>, 7 = <4, 32, 8>, 8 = <2, 64, 8>
-void launch_local_ms(int variant, const CUtensorMap& tm, bf16* out, int B, int H, int L, int NL, float scale_log2e, int reverse,
-                     int num_sms, cudaStream_t st) {
+// windowed attention (attention.cuh): persistent, one CTA per SM; trace = 1 records CTA 0's clock64 timeline
+void launch_local(const CUtensorMap& tm, bf16* out, int B, int H, int L, int NL, float scale_log2e, int reverse, int num_sms,
+                  int trace, cudaStream_t st) {
   const int grid = std::min(num_sms, (L / attn::WIN) * NL * B);
-#define MS_CASE(V, NS, BK, POLY)                                                                                  \
-  case V:                                                                                                         \
-    launch_k(attn::local_attention_ms_kernel<NS, BK, POLY>, dim3(grid), dim3(attn::MsCfg<NS, BK>::THREADS),       \
-             size_t(attn::MsCfg<NS, BK>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse);           \
-    break;
-#define V5_CASE(V, NST, TR)                                                                                      \
-  case V:                                                                                                         \
-    launch_k(attn::local_attention_v5_kernel<NST, TR>, dim3(grid), dim3(attn::V5_THREADS), size_t(attn::V5Cfg<NST>::SMEM_BYTES), st, \
-             tm, out, B, H, L, NL, scale_log2e, reverse);                                                        \
-    break;
-  switch (variant) {
-    V5_CASE(50, 3, 0) V5_CASE(51, 4, 0) V5_CASE(52, 5, 0) V5_CASE(53, 6, 0) V5_CASE(59, 3, 1)
-#define V5T_CASE(V, NST, TR, TU, PO)                                                                             \
-  case V:                                                                                                         \
-    launch_k(attn::local_attention_v5_kernel<NST, TR, TU, PO>, dim3(grid), dim3(attn::V5_THREADS), size_t(attn::V5Cfg<NST>::SMEM_BYTES), st, \
-             tm, out, B, H, L, NL, scale_log2e, reverse);                                                        \
-    break;
-    V5T_CASE(60, 5, 0, 1, 0) V5T_CASE(69, 5, 1, 1, 0) V5T_CASE(61, 5, 0, 1, 4) V5T_CASE(62, 5, 0, 1, 8) V5T_CASE(63, 5, 0, 0, 4) V5T_CASE(68, 5, 1, 1, 4)
-    case 11: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 1>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 12: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 2>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 14: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 4>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 15: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 0, 6>, dim3(grid), dim3(attn::MsCfg<2, 64, 6>::THREADS), size_t(attn::MsCfg<2, 64, 6>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 16: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 2, 6>, dim3(grid), dim3(attn::MsCfg<2, 64, 6>::THREADS), size_t(attn::MsCfg<2, 64, 6>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 17: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 7>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 18: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 8>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 21: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 21>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 22: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 22>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 23: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 23>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 30: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 30>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    case 13: launch_k(attn::local_attention_ms_kernel<2, 64, 0, 3>, dim3(grid), dim3(attn::MsCfg<2, 64>::THREADS), size_t(attn::MsCfg<2, 64>::SMEM_BYTES), st, tm, out, B, H, L, NL, scale_log2e, reverse); break;
-    MS_CASE(4, 2, 64, 0)
-    MS_CASE(5, 4, 32, 0)
-    MS_CASE(6, 4, 32, 4)
-    MS_CASE(7, 4, 32, 8)
-    default:
-    MS_CASE(8, 2, 64, 8)
-  }
-#undef MS_CASE
-}
-
-// linear attention, one cluster of `cl` CTAs per (global head, sample)
-void launch_linear_cl(int cl, const bf16* qkv, bf16* out, int B, int H, int L, int NL, float q_scale, int reverse, cudaStream_t st) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((H - NL) * cl, B);
-  cfg.blockDim = dim3(128);
-  cfg.dynamicSmemBytes = attn::LINC_SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cl;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, attn::linear_attention_cl_kernel, qkv, out, B, H, L, NL, q_scale, reverse);
+  constexpr size_t smem = attn::LocalCfg<attn::LOCAL_NST>::SMEM_BYTES;
+  if (trace)
+    launch_k(attn::local_attention_kernel<attn::LOCAL_NST, 1>, dim3(grid), dim3(attn::LOCAL_THREADS), smem, st, tm, out, B, H, L, NL,
+             scale_log2e, reverse);
+  else
+    launch_k(attn::local_attention_kernel<attn::LOCAL_NST, 0>, dim3(grid), dim3(attn::LOCAL_THREADS), smem, st, tm, out, B, H, L, NL,
+             scale_log2e, reverse);
 }
 
 enum Cat { C_QKV, C_OUT, C_FF1, C_FF2, C_LOCAL, C_LINEAR, C_LN, C_EMBED, C_HEAD, C_OTHER, C_COUNT };
@@ -427,13 +276,6 @@ struct biom3_model {
   float* u = nullptr;                           // fp32 residual stream (fp32-class mode, or BIOM3_SPLIT_RESID=0)
   bf16* u_lo = nullptr;                         // split residual stream: u = a (hi, bf16) + u_lo (bf16)
   bool split_resid = true;
-  bool lo8 = false;                             // split stream: remainder as a signed byte of hi's ulp in a tiled plane (BIOM3_LO8=1).
-                                                // 20 % fewer HBM bytes in out-proj, 12 % in FF2, all tests green — and SLOWER
-                                                // (out-proj 1.37 -> 1.63 ms/step, step 9.89 -> 10.30 ms): the residual epilogue is
-                                                // bound by its own instruction stream, not by HBM
-  bool resid_direct = false;                    // residual epilogues: thread = row with 256-bit accesses, no smem transpose
-                                                // (BIOM3_RESID_DIRECT=1).  Fewer instructions, no __syncwarp, no shuffles — and
-                                                // SLOWER: out-proj 1.34 -> 1.63 ms/step (32 distinct lines per warp access)
   bf16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
   float *Yh = nullptr, *Ytmp = nullptr, *Y = nullptr, *cvec = nullptr;
   uint8_t* state = nullptr;
@@ -441,25 +283,13 @@ struct biom3_model {
   k::DecodeCtl* ctl = nullptr;
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
-  int attn_tc = 52;                             // local attention: 0 mma.sync, 1 tcgen05 (one item per CTA), 2 tcgen05 persistent (P in TMEM),
-                                                // 3 = 2 split into two ping-pong streams per CTA (default; BIOM3_ATTN_TC)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
-  int tma_store = 1;                            // bf16 epilogue store path, see gemm::Params::tma_store (BIOM3_TMA_STORE)
   bool use_pdl = true;                          // programmatic dependent launch between the kernels of a step
   bool serpentine = true;                       // alternate the row walking direction kernel to kernel (L2 reuse)
-  int mlp_slabs = 1;                            // FF1/FF2 row slabs per layer (hid slab reused, L2 resident)
   // Last-layer row compaction (decode, split residual): after the last block's attention only the B * group token
   // rows the sampler consumes are carried through out-proj / MLP / head (k::gather_rows_kernel).  BIOM3_COMPACT=0
   // computes every row like the reference does.
   bool compact_last = true;
-  bool a_res = false;                           // QKV / FF1: A-resident pair-tiled GEMM (K <= 512), see gemm_tcgen05.cuh (BIOM3_ARES=1).
-                                                // Bit-identical and halves the L2->SM operand traffic, but measured no faster
-                                                // (step 9.99 vs 9.97 ms): these GEMMs are not L2-bound, so the default stays
-                                                // the streaming ring for both operands
-  int resid_depth = 1;                          // residual prefetch depth of the out-proj / FF2 epilogues (BIOM3_RESID_DEPTH=1|2).
-                                                // 2 (two chunks in flight, setmaxnreg register reallocation) measured SLOWER:
-                                                // out-proj 1.34 -> 1.44 ms/step, 11.5 -> 11.8 us per tile in the K sweep
-  bool epi_pipe = true;                         // bf16 GEMM epilogues fetch their per-tile vectors / statistics one tile ahead
   int compact_rows_max = 0;                     // rows allocated for the compact buffers (multiple of 256), 0 = none
   int last_compact_rows = 0;                    // rows the last run_step() carried through the last layer's MLP (0 = all)
   bf16 *att_c = nullptr, *a_c = nullptr, *ulo_c = nullptr, *hid_c = nullptr;
@@ -468,9 +298,6 @@ struct biom3_model {
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
   // step graph cache
   cudaStream_t cap_stream = nullptr;
-  cudaStream_t side_stream = nullptr;           // linear attention runs here, concurrently with local attention
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool attn_overlap = false;                    // measured: no gain (the two kernels do not co-reside), kept as a switch
   cudaGraphExec_t graph_exec = nullptr;
   int graph_B = -1, graph_group = -1;
   // forward API: the ~100 launches of one forward replayed as a graph too (B = 1 is launch bound: 1.64 ms un-graphed); the graph
@@ -604,14 +431,9 @@ void run_y_mlp(biom3_model* m, const float* y_c, int B, cudaStream_t st) {
   k::cond_transpose_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->Ytmp, m->Y, B, D, depth);
 }
 
-// Residual update of the split (hi, lo) stream: the epilogue variant is a model-level choice (gemm_tcgen05.cuh, Epi 5 / 6 / 7)
+// Residual update of the split (hi, lo) stream (gemm::EPI_BIAS_RESID_SPLIT)
 void launch_resid_split(biom3_model* m, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& r, cudaStream_t st) {
-  if (m->lo8)
-    launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
-  else if (m->resid_direct)
-    launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
-  else
-    launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st, m->resid_depth);
+  launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st);
 }
 
 // One per-step forward over the resident state.  sample: draw + unmask (decode); else write logits.
@@ -639,7 +461,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const bool split = m->precision == 0 && m->split_resid;      // residual stream stored as bf16 hi + lo
   LAUNCH(C_OTHER, launch_k(k::cond_build_kernel, dim3(std::max(1, JD / 4 / 256), B), dim3(256), 0, st,
                       m->Ttab, m->Y, t_per_sample, m->ctl, m->cvec, B, JD));
-  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a, split ? m->u_lo : nullptr, int(m->lo8),
+  LAUNCH(C_EMBED, launch_k(k::embed_kernel, dim3(row_blocks), dim3(256), 0, st, m->state, m->emb, m->ax0, m->ax1, m->cvec, JD, m->u, m->a, split ? m->u_lo : nullptr,
                                                               m->stats, m->ln_parts, M, L, c.local_window, D));
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
@@ -647,12 +469,11 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
   const int iw = (m->bn_wide == 256 && !pw) ? 1 : 0, in = (m->bn_narrow == 256 && !pn) ? 1 : 0;   // weight map: 256- or 128-row box
   // last-layer row compaction: rows of the compact buffers, 0 = every row goes through the last layer's MLP
   int Mc = 0;
-  if (sample && split && group > 0 && m->compact_rows_max > 0 && m->mlp_slabs == 1) {
+  if (sample && split && group > 0 && m->compact_rows_max > 0) {
     const int want = (B * group + 255) / 256 * 256;
     if (want <= m->compact_rows_max && want * 2 <= M) Mc = want;
   }
   m->last_compact_rows = Mc;
-  const bool ares = m->a_res && m->precision == 0 && M % 256 == 0 && D <= gemm::ARES_NK * gemm::BK && (3 * D) % 256 == 0;
   int dir = 0;                                  // row walking direction of the next launch (see Params::reverse)
   auto next_dir = [&]() { const int d = dir; if (m->serpentine) dir ^= 1; return d; };
   next_dir();                                   // the embed kernel walked forward
@@ -673,7 +494,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       gemm::Params r{};
       r.L = L; r.H = H; r.Bsz = B; r.M = M; r.split3 = 1;
       r.N = D; r.K = D; r.b_row_offset = j * D; r.out = m->u; r.bias = m->bo + size_t(j) * D;
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_a2, m->tm_wo2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_a2, m->tm_wo2[in], m->tm_st_hid, r, m->num_sms, st));
       LAUNCH(C_LN, f32p::ln_split_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D, m->ln2_b + size_t(j) * D,
                                                                     m->a2, M, D));
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid32;
@@ -682,56 +503,25 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
       r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid2, m->tm_w2s[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid2, m->tm_w2s[in], m->tm_st_hid, r, m->num_sms, st));
     }
   } else
   for (int j = 0; j < depth; ++j) {
     gemm::Params p{};
-    p.L = L; p.H = H; p.Bsz = B; p.M = M; p.no_pipe = m->epi_pipe ? 0 : 1;
+    p.L = L; p.H = H; p.Bsz = B; p.M = M;
     // q, k, v = LN1(u) Wqkv^T (no bias; LayerNorm folded) -> head-major bf16
     p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv;
-    p.ln_stats = m->stats; p.ln_parts = m->ln_parts; p.tma_store = m->tma_store;
+    p.ln_stats = m->stats; p.ln_parts = m->ln_parts;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
     p.reverse = next_dir();
-    if (ares)
-      LAUNCH(C_QKV, launch_gemm_ares<gemm::EPI_QKV_HEADMAJOR>(m->tm_a, m->tm_wqkv[0], m->tm_st_qkv, p, m->num_sms, st));
-    else
-      LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
+    LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
     const int adir = next_dir();                // both attention kernels read the same QKV output
-    // The two attention kernels read the same QKV output and write disjoint column ranges of `att`.  Outside the
-    // profiler they are forked onto two streams (two branches of the step graph): the linear heads are latency /
-    // HBM bound, the local heads MMA / MUFU bound, so the SMs can interleave their CTAs.
-    const bool fork = m->attn_overlap && !prof && NL > 0 && H - NL > 0;
-    if (fork) {
-      cudaEventRecord(m->ev_fork, st);
-      cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0);
-    }
-    cudaStream_t lst = fork ? m->side_stream : st;
+    // the two attention kernels read the same QKV output and write disjoint column ranges of `att`
     if (H - NL > 0)
-      LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), lst, m->qkv, m->att, B, H, L, NL,
+      LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), st, m->qkv, m->att, B, H, L, NL,
                                                                                        q_scale, adir));
-    if (NL > 0) {
-      if (m->attn_tc >= 4)
-        LAUNCH(C_LOCAL, launch_local_ms(m->attn_tc, m->tm_qkv_attn, m->att, B, H, L, NL, scale_log2e, adir, m->num_sms, st));
-      else if (m->attn_tc == 3)
-        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc3_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
-                                 dim3(attn::TC3_THREADS), size_t(attn::TC3_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
-                                 scale_log2e, adir));
-      else if (m->attn_tc == 2)
-        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc2_kernel, dim3(std::min(m->num_sms, (L / attn::WIN) * NL * B)),
-                                 dim3(attn::TC2_THREADS), size_t(attn::TC2_SMEM_BYTES), st, m->tm_qkv_attn, m->att, B, H, L, NL,
-                                 scale_log2e, adir));
-      else if (m->attn_tc == 1)
-        LAUNCH(C_LOCAL, launch_k(attn::local_attention_tc_kernel, dim3(L / attn::WIN, NL, B), dim3(256), size_t(attn::TC_SMEM_BYTES), st,
-                            m->tm_qkv_attn, m->att, B, H, L, scale_log2e, adir));
-      else
-        LAUNCH(C_LOCAL, launch_k(attn::local_attention_kernel, dim3(L / attn::WIN, NL, B), dim3(256), size_t(attn::LOCAL_SMEM_BYTES), st,
-                            m->qkv, m->att, B, H, L, scale_log2e, adir));
-    }
-    if (fork) {
-      cudaEventRecord(m->ev_join, m->side_stream);
-      cudaStreamWaitEvent(st, m->ev_join, 0);
-    }
+    if (NL > 0)
+      LAUNCH(C_LOCAL, launch_local(m->tm_qkv_attn, m->att, B, H, L, NL, scale_log2e, adir, m->num_sms, 0, st));
     // u += att . Wo^T + bo ; also emits bf16(u) and its row statistics for the next folded LayerNorm
     gemm::Params r{};
     r.L = L; r.H = H; r.Bsz = B; r.M = M;
@@ -740,17 +530,14 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     const bool cl = Mc > 0 && j == depth - 1;   // compact last layer: the rest of the step runs on the selected rows only
     if (cl) {
       LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
-                               m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc, int(m->lo8)));
+                               m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc));
       r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
       LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att_c, m->tm_wo[in], r, st));
       p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
       p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-      if (ares)
-        LAUNCH(C_FF1, launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(m->tm_a_c, m->tm_w1[0], m->tm_st_hid_c, p, m->num_sms, st));
-      else
-        LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
+      LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
       LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid_c, m->tm_w2[in], r, st));
@@ -760,38 +547,29 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       r.out = m->u_lo;
       LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att, m->tm_wo[in], r, st));
     } else {
-      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
+      LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
     }
     // hid = gelu(LN2(u) W1^T + b1)   (LayerNorm and bias folded into ln_s / ln_t), then
-    // u += hid . W2^T + b2 (+ next layer's conditioning vector).  Optionally in row slabs that reuse one hid
-    // slab buffer, so the 4D-wide hidden activation lives in L2 between the two GEMMs instead of HBM.
-    const int slabs = (m->mlp_slabs > 1 && B % m->mlp_slabs == 0 && (M / m->mlp_slabs) % 256 == 0) ? m->mlp_slabs : 1;
-    const int Ms = M / slabs, Bs = B / slabs;
-    for (int sl = 0; sl < slabs; ++sl) {
-      const size_t row0 = size_t(sl) * Ms;
-      p.M = Ms; p.a_row_offset = int(row0); p.reverse = next_dir();
-      p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
-      p.ln_stats = m->stats + row0 * m->ln_parts * 2;
-      p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
-      if (ares)
-        LAUNCH(C_FF1, launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(m->tm_a, m->tm_w1[0], m->tm_st_hid, p, m->num_sms, st));
-      else
-        LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
-      r.M = Ms; r.a_row_offset = 0; r.reverse = next_dir();
-      r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
-      r.out = m->u + row0 * D; r.out_bf16 = m->a + row0 * D; r.stats_out = m->stats + row0 * m->ln_parts * 2;
-      r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D + size_t(sl) * Bs * JD : nullptr;
-      r.cond_stride = JD;
-      if (split) {
-        r.out = m->u_lo + row0 * D;
-        LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid, m->tm_w2[in], r, st));
-      } else {
-        LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st, m->resid_depth));
-      }
+    // u += hid . W2^T + b2 (+ next layer's conditioning vector)
+    p.M = M; p.a_row_offset = 0; p.reverse = next_dir();
+    p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid;
+    p.ln_stats = m->stats;
+    p.ln_s = m->ln_s_ff + size_t(j) * 4 * D; p.ln_t = m->ln_t_ff + size_t(j) * 4 * D;
+    LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a, m->tm_w1[iw], m->tm_st_hid, p, m->num_sms, st));
+    r.M = M; r.a_row_offset = 0; r.reverse = next_dir();
+    r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
+    r.out = m->u; r.out_bf16 = m->a; r.stats_out = m->stats;
+    r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
+    r.cond_stride = JD;
+    if (split) {
+      r.out = m->u_lo;
+      LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid, m->tm_w2[in], r, st));
+    } else {
+      LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
     }
   }
   k::HeadArgs ha{};
-  ha.u = split ? nullptr : m->u; ha.u_hi = Mc ? m->a_c : m->a; ha.u_lo = Mc ? m->ulo_c : m->u_lo; ha.compact = Mc ? 1 : 0; ha.lo8 = (split && m->lo8) ? 1 : 0; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
+  ha.u = split ? nullptr : m->u; ha.u_hi = Mc ? m->a_c : m->a; ha.u_lo = Mc ? m->ulo_c : m->u_lo; ha.compact = Mc ? 1 : 0; ha.gamma = m->norm_g; ha.beta = m->norm_b; ha.w_out = m->w_out; ha.b_out = m->b_out;
   ha.logits_out = logits_out; ha.state = sample ? m->state : nullptr; ha.inv_path = m->inv_path; ha.ctl = m->ctl;
   ha.B = B; ha.L = L; ha.D = D; ha.C = C; ha.group = sample ? group : 0;
   const int ntok = sample ? B * group : M;
@@ -862,28 +640,14 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   m->device = device;
   m->max_batch = max_batch;
   m->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("BIOM3_BN_WIDE")) m->bn_wide = atoi(e) == 128 ? 128 : 256;
-  if (const char* e = getenv("BIOM3_BN_NARROW")) m->bn_narrow = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("BIOM3_PAIR")) m->use_pair = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_TMA_STORE")) m->tma_store = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_LO8")) m->lo8 = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_RESID_DIRECT")) m->resid_direct = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_MLP_SLABS")) m->mlp_slabs = atoi(e) > 0 ? atoi(e) : 1;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_EPI_PIPE")) m->epi_pipe = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_ARES")) m->a_res = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;
-  if (const char* e = getenv("BIOM3_RESID_DEPTH")) m->resid_depth = atoi(e) == 2 ? 2 : 1;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
-  CU_OK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
-  CU_OK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-  CU_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-  if (const char* e = getenv("BIOM3_ATTN_OVERLAP")) m->attn_overlap = atoi(e) != 0;
   *out = m;
   return BIOM3_OK;
 }
@@ -895,9 +659,6 @@ void biom3_destroy(biom3_model* m) {
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->fwd_exec) cudaGraphExecDestroy(m->fwd_exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
-  if (m->side_stream) cudaStreamDestroy(m->side_stream);
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-  if (m->ev_join) cudaEventDestroy(m->ev_join);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
 }
@@ -1382,10 +1143,11 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
   return r;
 }
 
-int biom3_debug_trace(void* host_dst, int64_t nbytes) {
-  if (!host_dst || nbytes <= 0) return fail(BIOM3_ERR_INVALID, "bad debug_trace argument");
+int biom3_debug_trace(int which, void* host_dst, int64_t nbytes) {
+  if (!host_dst || nbytes <= 0 || which < 0 || which > 1) return fail(BIOM3_ERR_INVALID, "bad debug_trace argument");
   CU_OK(cudaDeviceSynchronize());
-  CU_OK(cudaMemcpyFromSymbol(host_dst, attn::g_ms_trace, std::min(size_t(nbytes), sizeof(attn::g_ms_trace))));
+  if (which == 0) CU_OK(cudaMemcpyFromSymbol(host_dst, attn::g_ms_trace, std::min(size_t(nbytes), sizeof(attn::g_ms_trace))));
+  else CU_OK(cudaMemcpyFromSymbol(host_dst, gemm::g_gemm_trace, std::min(size_t(nbytes), sizeof(gemm::g_gemm_trace))));
   return BIOM3_OK;
 }
 
@@ -1448,46 +1210,21 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
     return fail(BIOM3_ERR_INVALID, "bad attention_test argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CU_OK(init_kernel_attributes());
-  int lin_cl = variant / 100;                      // test hook: hundreds digit = cluster size of the linear-attention kernel (0: one CTA)
-  variant %= 100;
-  while (lin_cl > 1 && L % (128 * lin_cl)) lin_cl >>= 1;
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   if (NL > 0) {
-    if (variant >= 1) {
-      CUtensorMap tm;
-      int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
-      if (r) return r;
-      if (variant >= 4) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        launch_local_ms(variant, tm, o, B, H, L, NL, scale_log2e, 0, sms, st);
-      } else if (variant == 3) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attn::local_attention_tc3_kernel<<<std::min(sms, (L / attn::WIN) * NL * B), attn::TC3_THREADS, attn::TC3_SMEM_BYTES, st>>>(
-            tm, o, B, H, L, NL, scale_log2e, 0);
-      } else if (variant == 2) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attn::local_attention_tc2_kernel<<<std::min(sms, (L / attn::WIN) * NL * B), attn::TC2_THREADS, attn::TC2_SMEM_BYTES, st>>>(
-            tm, o, B, H, L, NL, scale_log2e, 0);
-      } else {
-        attn::local_attention_tc_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::TC_SMEM_BYTES, st>>>(tm, o, B, H, L, scale_log2e, 0);
-      }
-    } else {
-      attn::local_attention_kernel<<<dim3(L / attn::WIN, NL, B), 256, attn::LOCAL_SMEM_BYTES, st>>>(q, o, B, H, L, scale_log2e, 0);
-    }
+    CUtensorMap tm;
+    int r = make_tmap_sw64(&tm, qkv, uint64_t(3) * B * H * L);
+    if (r) return r;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    launch_local(tm, o, B, H, L, NL, scale_log2e, 0, sms, variant == 1, st);
   }
-  if (H - NL > 0) {
-    if (lin_cl > 0) launch_linear_cl(lin_cl, q, o, B, H, L, NL, q_scale, 0, st);
-    else attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
-  }
+  if (H - NL > 0)
+    attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }
@@ -1495,13 +1232,10 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
                     int block_n, int pair, void* stream) {
   if (!A || !W || !out) return fail(BIOM3_ERR_INVALID, "null argument");
-  if (block_n != 128 && block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 128 or 256");
+  if (block_n != 256) return fail(BIOM3_ERR_INVALID, "block_n must be 256");
   if (M % 128 || N % block_n || K % 64) return fail(BIOM3_ERR_INVALID, "M%128, N%block_n, K%64 must be 0");
   const int split3 = (pair >> 1) & 1;          // bit 1: A and W are [hi | lo] halves of width 2K (fp32-class schedule)
-  const int ares = (pair >> 2) & 1;            // bit 2: A-resident pair tiling (bf16 epilogues 0 / 2, K <= 512)
   pair &= 1;
-  if (ares && (!pair || split3 || K > gemm::ARES_NK * gemm::BK || (epi != gemm::EPI_STORE_BF16 && epi != gemm::EPI_BIAS_GELU_BF16)))
-    return fail(BIOM3_ERR_INVALID, "A-resident tiling needs pair tiling, K <= 512 and a bf16 epilogue");
   if (pair && (block_n != 256 || M % 256)) return fail(BIOM3_ERR_INVALID, "pair tiling needs block_n == 256 and M % 256 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int gemm_dev = 0, sms = 0;
@@ -1515,45 +1249,30 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
   p.split3 = split3;
   p.M = M; p.N = N; p.K = K; p.b_row_offset = 0; p.out = out; p.bias = bias; p.cond = nullptr; p.cond_stride = 0;
   p.L = M; p.H = 1; p.Bsz = 1;
-  if (const char* e = getenv("BIOM3_EPI_SKIP")) p.debug_skip = atoi(e);
+  if (const char* e = getenv("BIOM3_GEMM_TRACE")) p.trace = atoi(e);
   CUtensorMap tc;
   memset(&tc, 0, sizeof(tc));
   if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_BIAS_GELU_BF16) {
     if ((r = make_store_tmap(&tc, out, M, N))) return r;
-    p.tma_store = 1;
-    if (const char* e = getenv("BIOM3_TMA_STORE")) p.tma_store = std::max(0, std::min(2, atoi(e)));
   }
   CU_OK(init_kernel_attributes());
-  int rd = 1;
-  if (const char* e = getenv("BIOM3_RESID_DEPTH")) rd = atoi(e) == 2 ? 2 : 1;
   switch (epi) {
     case gemm::EPI_STORE_BF16:
-      if (ares) launch_gemm_ares<gemm::EPI_STORE_BF16>(ta, tb, tc, p, sms, st);
-      else launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
+      launch_gemm<gemm::EPI_STORE_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
       break;
     case gemm::EPI_BIAS_GELU_BF16:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      if (ares) launch_gemm_ares<gemm::EPI_BIAS_GELU_BF16>(ta, tb, tc, p, sms, st);
-      else launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
+      launch_gemm<gemm::EPI_BIAS_GELU_BF16>(block_n, pair != 0, ta, tb, tc, p, sms, st);
       break;
     case gemm::EPI_BIAS_RESID_F32:
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_STORE_F32: launch_gemm<gemm::EPI_STORE_F32>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     case gemm::EPI_BIAS_RESID_SPLIT:      // out = bf16 [2][M][N]: hi plane then lo plane, updated in place
-      p.out_bf16 = reinterpret_cast<bf16*>(out);
-      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
-      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
-    case gemm::EPI_BIAS_RESID_DIRECT:     // same planes as 5
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
       p.out_bf16 = reinterpret_cast<bf16*>(out);
       p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
-      launch_gemm<gemm::EPI_BIAS_RESID_DIRECT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
-    case gemm::EPI_BIAS_RESID_SPLIT8:     // out = bf16 hi plane [M][N] followed by the tiled uint8 lo plane (M * N bytes)
-      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
-      p.out_bf16 = reinterpret_cast<bf16*>(out);
-      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
-      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT8>(block_n, pair != 0, ta, tb, tc, p, sms, st, rd); break;
+      launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

@@ -38,13 +38,6 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-// Warp-specialised register reallocation (whole warpgroups, sm_90+): the control warpgroup gives registers away, the
-// epilogue warpgroups take them.
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -343,55 +336,9 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// 256-bit global load (sm_100: LDG.E.256): one full 32-byte sector per thread
-__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
-  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(p)
-               : "memory");
-}
-// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per thread
-__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
-                                             uint32_t g, uint32_t h) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
-               "r"(g), "r"(h)
-               : "memory");
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// ---------------------------------------------------------------- split residual stream, 8-bit remainder
-// u = hi + lo with hi = bf16(u).  The remainder |u - hi| <= ulp(hi) / 2 is stored as a signed 8-bit multiple of ulp(hi) / 256
-// = 2^(E - 142), E the biased exponent of hi: 16 significant bits in 3 bytes.  The lo plane is private to this library and
-// TILED, [rows / 32][cols / 32][32 rows][32 bytes], so that the residual epilogue (a warp = 32 rows x 32 columns per chunk)
-// reads and writes 1 KB contiguous blocks and no two chunks ever share a 128-byte line.
-__device__ __forceinline__ float lo8_dec_scale(uint32_t E) { return __uint_as_float(E >= 16u ? (E - 15u) << 23 : 0u); }
-__device__ __forceinline__ float lo8_enc_scale(uint32_t E) { return __uint_as_float(E >= 16u ? (269u - E) << 23 : 0u); }
-__device__ __forceinline__ uint32_t lo8_quant(float r, float enc) {
-  const int q = __float2int_rn(r * enc);
-  return uint32_t(max(-127, min(127, q))) & 0xffu;
-}
-__device__ __forceinline__ size_t lo8_offset(size_t row, int col, int ncols) {
-  return ((row >> 5) * size_t(ncols >> 5) + size_t(col >> 5)) * 1024 + (row & 31) * 32 + (col & 31);
-}
-// 4 consecutive elements: hi pair words h0 (elements 0, 1), h1 (2, 3), remainder bytes l
-__device__ __forceinline__ float4 split8_decode(uint32_t h0, uint32_t h1, uint32_t l) {
-  const int q0 = int(l << 24) >> 24, q1 = int(l << 16) >> 24, q2 = int(l << 8) >> 24, q3 = int(l) >> 24;
-  return make_float4(fmaf(float(q0), lo8_dec_scale((h0 >> 7) & 0xffu), __uint_as_float(h0 << 16)),
-                     fmaf(float(q1), lo8_dec_scale((h0 >> 23) & 0xffu), __uint_as_float(h0 & 0xffff0000u)),
-                     fmaf(float(q2), lo8_dec_scale((h1 >> 7) & 0xffu), __uint_as_float(h1 << 16)),
-                     fmaf(float(q3), lo8_dec_scale((h1 >> 23) & 0xffu), __uint_as_float(h1 & 0xffff0000u)));
-}
-__device__ __forceinline__ void split8_encode(float4 o, uint32_t& h0, uint32_t& h1, uint32_t& l) {
-  h0 = pack_bf16x2(o.x, o.y);
-  h1 = pack_bf16x2(o.z, o.w);
-  l = lo8_quant(o.x - __uint_as_float(h0 << 16), lo8_enc_scale((h0 >> 7) & 0xffu)) |
-      (lo8_quant(o.y - __uint_as_float(h0 & 0xffff0000u), lo8_enc_scale((h0 >> 23) & 0xffu)) << 8) |
-      (lo8_quant(o.z - __uint_as_float(h1 << 16), lo8_enc_scale((h1 >> 7) & 0xffu)) << 16) |
-      (lo8_quant(o.w - __uint_as_float(h1 & 0xffff0000u), lo8_enc_scale((h1 >> 23) & 0xffu)) << 24);
 }
 
 }  // namespace ptx

@@ -197,29 +197,28 @@ def unmask_(state: torch.Tensor, tok: torch.Tensor, path: torch.Tensor, step: in
                                     C.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)))
 
 
-def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int,
-              out: Optional[torch.Tensor] = None, pair: bool = False, split3: bool = False, ares: bool = False) -> torch.Tensor:
+def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], epi: int, block_n: int = 256,
+              out: Optional[torch.Tensor] = None, pair: bool = False, split3: bool = False) -> torch.Tensor:
     """Unit-test hook: A bf16 [M, K], W bf16 [N, K] -> out per `epi` (see include/biom3_b200.h).
-    split3: A and W are [hi | lo] bf16 halves, [M, 2K] and [N, 2K] (the fp32-class K schedule).
-    ares: the A-resident pair tiling (pair=True, K <= 512, epi 0 or 2)."""
+    split3: A and W are [hi | lo] bf16 halves, [M, 2K] and [N, 2K] (the fp32-class K schedule)."""
     lib = _lib.load()
     M, K = A.shape
     N = W.shape[0]
     if split3:
         K //= 2
     if out is None:
-        if epi in (5, 6, 7):
-            raise ValueError('epilogues 5 / 6 update `out` in place: bf16 [2, M, N] (hi plane, lo plane), or for 6 the bf16 '
-                             'hi plane followed by the tiled uint8 lo plane (3 * M * N bytes)')
+        if epi == 5:
+            raise ValueError('epilogue 5 updates `out` in place: bf16 [2, M, N] (hi plane, lo plane)')
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
     with torch.cuda.device(A.device):
-        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0) | (4 if ares else 0),
+        _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
     return out
 
 
 def attention_test(qkv: torch.Tensor, NL: int, variant: int = 0) -> torch.Tensor:
-    """Unit-test hook: qkv bf16 [3, B, H, L, 32] (cuda) -> attention output bf16 [B*L, H*32]."""
+    """Unit-test hook: qkv bf16 [3, B, H, L, 32] (cuda) -> attention output bf16 [B*L, H*32]; variant 1 also records
+    the local-attention kernel's clock64 timeline (biom3_debug_trace)."""
     lib = _lib.load()
     _, B, H, L, dh = qkv.shape
     assert dh == 32 and qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous()

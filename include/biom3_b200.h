@@ -108,15 +108,16 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
 /* Unit-test hook for the tcgen05 GEMM: C = A . W^T with one of the fused epilogues.
  * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
  * 3 fp32 in-place residual (+bias), 4 fp32 out, 5 in-place residual stored split (out = bf16 [2][M][N]: hi plane
- * bf16(R), lo plane bf16(R - hi)).  block_n: 128 or 256.  pair bit 0: CTA-pair (cta_group::2)
- * tiling, 256 x 256 tiles (needs block_n == 256, M % 256 == 0); pair bit 1: fp32-class K schedule, A and W are
- * [hi | lo] bf16 halves of width 2K and the result is hi.hi + hi.lo + lo.hi. */
+ * bf16(R), lo plane bf16(R - hi)).  block_n: 256.  pair bit 0: CTA-pair (cta_group::2) tiling, 256 x 256 tiles
+ * (needs M % 256 == 0; otherwise 128 x 256 tiles, one CTA each); pair bit 1: fp32-class K schedule, A and W are
+ * [hi | lo] bf16 halves of width 2K and the result is hi.hi + hi.lo + lo.hi.  With BIOM3_GEMM_TRACE=1 in the
+ * environment CTA 0 records its clock64 timeline (biom3_debug_trace(1, ...)). */
 int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epi,
                     int block_n, int pair, void* stream);
 
 /* Unit-test hook for the attention kernels: qkv device bf16 [3][B][H][L][32] -> out device bf16 [B*L][H*32].
- * Heads [0, NL) windowed softmax (variant 0: mma.sync kernel, 1: tcgen05 kernel, one item per CTA, 2: tcgen05 persistent
- * kernel with P kept in tensor memory), heads [NL, H) linear attention. */
+ * Heads [0, NL) windowed softmax (tcgen05 kernel; variant 1 = the same kernel recording CTA 0's clock64 timeline,
+ * biom3_debug_trace(0, ...)), heads [NL, H) linear attention. */
 int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL, int variant, void* stream);
 
 /* Per-kernel device timings (ms) of the last biom3_profile_step() call; for bench.py's roofline. */
@@ -157,9 +158,11 @@ int biom3_facilitator(const float* z_t, int P, int in_dim, int hid_dim, int out_
  * (tests/test_gpu_parity.py); oracle/philox.py restates the stream independently. */
 int biom3_debug_noise(uint64_t seed, int step, int B, int L, int C, float* out, void* stream);
 
-/* Test hook: clock64() timeline of CTA 0 of the last traced local-attention launch (biom3_attention_test variant 30):
- * int64 [2 streams][2: issuer, softmax warp 0][128 blocks][6 events] (csrc/attention.cuh, g_ms_trace).  Synchronous. */
-int biom3_debug_trace(void* host_dst, int64_t nbytes);
+/* Test hook: clock64() timelines of CTA 0.  which = 0: the last traced local-attention launch (biom3_attention_test with a
+ * tracing variant): int64 [2 streams][2: issuers, softmax warp 0][128 blocks][6 events] (csrc/attention.cuh, g_ms_trace);
+ * which = 1: the last biom3_gemm_test launch with BIOM3_GEMM_TRACE=1: int64 [3: MMA issuer, epilogue warp 0, TMA
+ * producer][64 tiles][4 events] (csrc/gemm_tcgen05.cuh, g_gemm_trace).  Synchronous. */
+int biom3_debug_trace(int which, void* host_dst, int64_t nbytes);
 
 /* Number of kernel launches one decode step issues (for bench.py's gpu_launches): the count of the most recently
  * captured step graph, or the full-row estimate before the first decode. */

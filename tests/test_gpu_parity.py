@@ -36,8 +36,8 @@ def make(over, B, seed=11, perturb=True):
 
 
 # ---------------------------------------------------------------- GEMM (tcgen05) vs torch fp32
-@pytest.mark.parametrize('M,N,K,bn,pair', [(128, 256, 64, 256, False), (128, 128, 64, 128, False), (384, 768, 256, 256, False),
-                                           (1024, 1536, 512, 256, False), (2048, 512, 2048, 128, False),
+@pytest.mark.parametrize('M,N,K,bn,pair', [(128, 256, 64, 256, False), (384, 768, 256, 256, False),
+                                           (1024, 1536, 512, 256, False), (2048, 512, 2048, 256, False),
                                            (20096, 512, 512, 256, False), (256, 256, 64, 256, True), (512, 768, 256, 256, True),
                                            (1024, 1536, 512, 256, True), (37888, 512, 2048, 256, True)])
 def test_gemm_plain(M, N, K, bn, pair):
@@ -50,7 +50,7 @@ def test_gemm_plain(M, N, K, bn, pair):
     assert rel_err(out, ref) < 1e-5          # same bf16 inputs, fp32 accumulation on both sides
 
 
-@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
+@pytest.mark.parametrize('bn,pair', [(256, False), (256, True)])
 def test_gemm_epilogues(bn, pair):
     from biom3_b200 import engine
     g = torch.Generator().manual_seed(7)
@@ -65,25 +65,6 @@ def test_gemm_epilogues(bn, pair):
     assert rel_err(engine.gemm_test(A, W, bias, 2, bn, pair=pair).float(), gelu) < 4e-3          # bias + erf-GELU
     out = engine.gemm_test(A, W, bias, 3, bn, out=resid.clone(), pair=pair)
     assert rel_err(out, resid + ref + bias) < 1e-5                                     # in-place residual
-
-
-@pytest.mark.parametrize('M,N,K', [(256, 256, 64), (1024, 1536, 512), (20224, 2048, 512), (37888, 1536, 256), (4096, 2048, 512),
-                                   (65536, 1536, 512)])
-def test_gemm_a_resident_matches_streaming_pair_kernel(M, N, K):
-    """A-resident pair tiling (contiguous tile runs, the A row block loaded once per run) against torch fp32 and, bit for bit,
-    against the streaming pair kernel (same per-element accumulation order); uneven runs, runs that start mid row block,
-    K < 512, and both bf16 epilogues."""
-    from biom3_b200 import engine
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
-    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
-    bias = torch.randn(N, generator=g).cuda()
-    ref = A.float() @ W.float().t()
-    for epi, want in ((0, ref), (2, torch.nn.functional.gelu(ref + bias))):
-        got = engine.gemm_test(A, W, bias, epi, 256, pair=True, ares=True)
-        base = engine.gemm_test(A, W, bias, epi, 256, pair=True)
-        assert rel_err(got.float(), want) < 4e-3
-        assert torch.equal(got, base)
 
 
 # ---------------------------------------------------------------- sampler kernels, bit exact
@@ -475,12 +456,12 @@ def test_batch_of_one_decode_matches_oracle():
 # ---------------------------------------------------------------- attention kernels in isolation
 @pytest.mark.parametrize('B,H,L,NL,amp', [(1, 2, 128, 1, 1.5), (2, 4, 256, 2, 1.5), (2, 16, 1024, 8, 1.5),
                                           (2, 4, 512, 2, 4.0), (3, 4, 1024, 3, 6.0), (5, 8, 384, 8, 1.0)])
-@pytest.mark.parametrize('variant', [0, 1, 2, 3])
+@pytest.mark.parametrize('variant', [0, 1])
 def test_attention_kernels_vs_fp32_reference(B, H, L, NL, amp, variant):
-    """Local attention variants: 0 mma.sync; 1 tcgen05, one item per CTA (TMEM S/O, MN-major V operand); 2 tcgen05
-    persistent with P kept in TMEM and a lazily rescaled online softmax; 3 = 2 as two ping-pong streams per CTA (the
-    default in the decode step).  Heads >= NL: linear attention.  amp >= 4 gives peaked rows whose block maxima jump
-    by more than 2^8, which exercises the rescale path of variants 2 / 3.  Same bf16 inputs, fp32 reference."""
+    """Heads < NL: the tcgen05 windowed-softmax kernel (two streams per CTA, split S / PV issuers, P kept in TMEM, lazily
+    rescaled online softmax; variant 1 = the same kernel with its clock64 timeline recording on); heads >= NL: linear
+    attention.  amp >= 4 gives peaked rows whose block maxima jump by more than 2^8, which exercises the rescale path.
+    Same bf16 inputs, fp32 reference."""
     from biom3_b200 import engine
     from oracle.upstream_blocks import LocalAttention, linear_attention
     g = torch.Generator().manual_seed(B * 100 + L)
@@ -512,7 +493,7 @@ def test_gemm_split3_matches_fp32_product():
         return torch.cat([hi, (x - hi.float()).bfloat16()], 1).contiguous()
 
     ref = A.double() @ W.double().t()
-    for bn, pair in ((128, False), (256, False), (256, True)):
+    for bn, pair in ((256, False), (256, True)):
         out = engine.gemm_test(split(A).cuda(), split(W).cuda(), None, 4, bn, pair=pair, split3=True).cpu()
         assert rel_err(out, ref) < 2e-5, (bn, pair)
 
@@ -619,11 +600,11 @@ def test_generate_denoised_sampled_single_sequence_vs_reference_fixture():
                                        sampling_path=path)
 
 
-@pytest.mark.parametrize('epi', [5, 7])
-@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
+@pytest.mark.parametrize('epi', [5])
+@pytest.mark.parametrize('bn,pair', [(256, False), (256, True)])
 def test_gemm_split_residual_epilogue(bn, pair, epi):
-    """Epilogues 5 / 7: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place (5: accumulator
-    transposed through shared memory, coalesced accesses; 7: thread = row, 256-bit accesses)."""
+    """Epilogue 5: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place (accumulator transposed
+    through shared memory, coalesced accesses)."""
     from biom3_b200 import engine
     g = torch.Generator().manual_seed(9)
     M, N, K = 1024, 512, 512
@@ -642,48 +623,6 @@ def test_gemm_split_residual_epilogue(bn, pair, epi):
     assert torch.equal(planes[0], got.bfloat16()) or rel_err(planes[0].float(), ref) < 4e-3   # hi plane = bf16(R)
 
 
-def _lo8_encode(R):
-    """torch restatement of ptx::split8_encode + the tiled lo plane [M/32][N/32][32][32] (ptx.cuh)."""
-    M, N = R.shape
-    hi = R.bfloat16()
-    E = (hi.view(torch.int16).to(torch.int32) >> 7) & 0xff
-    q = torch.round(torch.ldexp(R - hi.float(), 142 - E)).clamp(-127, 127)
-    q = torch.where(E >= 16, q, torch.zeros_like(q)).to(torch.int8)
-    return hi, q.view(M // 32, 32, N // 32, 32).permute(0, 2, 1, 3).contiguous().view(-1)
-
-
-def _lo8_decode(hi, lo_tiled):
-    M, N = hi.shape
-    E = (hi.view(torch.int16).to(torch.int32) >> 7) & 0xff
-    q = lo_tiled.view(M // 32, N // 32, 32, 32).permute(0, 2, 1, 3).reshape(M, N).float()
-    return hi.float() + torch.where(E >= 16, torch.ldexp(q, E - 142), torch.zeros_like(q))
-
-
-@pytest.mark.parametrize('bn,pair', [(128, False), (256, False), (256, True)])
-def test_gemm_split8_residual_epilogue(bn, pair):
-    """Epilogue 6: residual stream as a bf16 hi plane + a tiled plane of signed 8-bit remainders (units of ulp(hi) / 256)."""
-    from biom3_b200 import engine
-    g = torch.Generator().manual_seed(10)
-    M, N, K = 1024, 512, 512
-    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
-    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
-    bias = torch.randn(N, generator=g).cuda()
-    R = (torch.randn(M, N, generator=g) * 3.0).cuda()
-    hi, lo = _lo8_encode(R)
-    r0 = _lo8_decode(hi, lo)
-    assert rel_err(r0, R) < 2e-5                                  # 16 significant bits in 3 bytes (2^-16 = 1.5e-5)
-    buf = torch.empty(3 * M * N, dtype=torch.uint8, device='cuda')
-    buf[:2 * M * N].view(torch.bfloat16).view(M, N).copy_(hi)
-    buf[2 * M * N:].view(torch.int8).copy_(lo)
-    ref = r0 + A.float() @ W.float().t() + bias
-    engine.gemm_test(A, W, bias, 6, bn, out=buf, pair=pair)
-    hi2 = buf[:2 * M * N].view(torch.bfloat16).view(M, N)
-    got = _lo8_decode(hi2, buf[2 * M * N:].view(torch.int8))
-    assert rel_err(got, ref) < 4e-5
-    assert torch.equal(hi2, got.bfloat16()) or rel_err(hi2.float(), ref) < 4e-3   # hi plane = bf16(R)
-    # the kernel's encoding of its own result is the canonical one
-    hi3, lo3 = _lo8_encode(got)
-    assert torch.equal(hi3, hi2)
 
 
 # ---------------------------------------------------------------- the on-device noise (the path bench.py times) under the oracle

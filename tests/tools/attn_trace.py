@@ -11,11 +11,11 @@ B, H, L = int(os.environ.get('TRACE_B', '64')), 8, 1024
 G0, G1 = (0, 6) if B <= 2 else (8, 44)
 qkv = torch.randn(3, B, H, L, 32, device='cuda').bfloat16()
 for _ in range(2):
-    engine.attention_test(qkv, H, int(os.environ.get("TRACE_VARIANT", "59")))
+    engine.attention_test(qkv, H, int(os.environ.get("TRACE_VARIANT", "1")))
     torch.cuda.synchronize()
 torch.cuda.synchronize()
 tr = np.zeros((2, 2, 128, 6), dtype=np.int64)
-_lib.check(_lib.load().biom3_debug_trace(C.c_void_p(tr.ctypes.data), tr.nbytes))
+_lib.check(_lib.load().biom3_debug_trace(0, C.c_void_p(tr.ctypes.data), tr.nbytes))
 t0 = tr[tr > 0].min()
 for s in range(2):
     print(f'---- stream {s}: block, issuer [before S, S issued, before PV, p_ready seen, PV issued], softmax [top, s_full, loaded, exp done, P stored, after epilogue]')
