@@ -184,6 +184,7 @@ def run_cuda_arm(a):
 
     args = synthetic.stage3_args(batch_size_sample=BATCH, num_replicas=BATCH * world)
     args.device = str(dev)
+    args.b200_precision = a.precision
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):       # the reference-compatible get_model prints; keep stdout = one JSON line
         model = mod.get_model(args, (32, 32), C)
@@ -328,8 +329,9 @@ def run_cuda_arm(a):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'ProteoScribe full-length decode, batch 64 sequences per GPU, bf16 (BASELINE.json configs[1]; '
+            'dtype': 'bf16' if a.precision == 'bf16' else 'f32 (bf16 x 3 split products on the tensor cores, fp32 accumulate / softmax / LayerNorm / GELU)',
+            'data': 'synthetic',
+            'config': {'workload': f'ProteoScribe full-length decode, batch 64 sequences per GPU, {a.precision} (BASELINE.json configs[1]; '
                                    'N>1: configs[2] sharding, 64 per GPU + NCCL all-gather of token ids)',
                        'global_batch': BATCH * world, 'seq_len': L, 'denoising_steps': L, 'parallelism': f'units{world}',
                        'l2': 'per-step working set (737 MB of activations at B=64) is larger than the 126 MB L2; no flush needed',
@@ -345,6 +347,171 @@ def run_cuda_arm(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def run_c4(a):
+    """BASELINE.json configs[3]: Facilitator z_t -> z_c + ProteoScribe sampling for 16 prompts x 32 replicas (units of 32),
+    units round-robin over the ranks, two units fused per launch (B = 64, group = 32), token ids all-gathered.  `value`:
+    inputs resident, engine calls; `e2e`: the reference-facing path (Facilitator module + batch_stage3_generate_sequences,
+    host z_t in, strings out)."""
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    from biom3_b200 import distributed as bdist
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    from biom3_b200 import synthetic
+    from biom3_b200.Stage1_source.model import Facilitator
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+
+    rank, world, local = bdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    P, R, BS = 16, 32, 32
+    args = synthetic.stage3_args(batch_size_sample=BS, num_replicas=R)
+    args.device = str(dev)
+    args.b200_precision = a.precision
+    with contextlib.redirect_stdout(sys.stderr):
+        model = mod.get_model(args, (32, 32), C)
+    model.load_state_dict(synthetic.random_state_dict(args, seed=0))
+    model.eval().to(dev)
+    fac = Facilitator(512, 1024, 512, dropout=0.0)
+    fac.load_state_dict(synthetic.facilitator_state_dict(512, 1024, seed=31))
+    z_t_host = torch.randn(P, 512, generator=torch.Generator().manual_seed(32)) * 1.45
+    z_t_dev = z_t_host.to(dev)
+    units = bdist.plan_units(P, R, BS)
+    mine = bdist.units_for_rank(len(units), rank, world)
+    eng = model.engine(2 * BS)
+    paths = [synthetic.synthetic_paths(BS, L, seed=100 + u).to(dev) for u in range(len(units))]
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def one_job(seed0):
+        z_c = fac(z_t_dev)                                           # [16, 512] on the device
+        local_tok = torch.zeros(len(mine), BS, L, dtype=torch.uint8, device=dev)
+        for i in range(0, len(mine), 2):
+            batch = mine[i:i + 2]
+            z = torch.cat([z_c[units[u][0]].unsqueeze(0).repeat(BS, 1) for u in batch])
+            pth = torch.cat([paths[u] for u in batch])
+            gs = torch.tensor([seed0 * 1000 + u for u in batch], dtype=torch.int64, device=dev)
+            tok, _ = eng.decode(z, pth, group=BS, group_seeds=gs)
+            local_tok[i:i + len(batch)] = tok.to(torch.uint8).view(len(batch), BS, L)
+        return bdist.gather_unit_tokens(local_tok, mine, len(units), BS)
+
+    with torch.cuda.stream(stream):
+        for i in range(a.warmup):
+            one_job(i)
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(a.steps):
+            allt = one_job(10 + i)
+        e1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = P * R * a.steps / (ms_total / 1e3)
+    # e2e: host z_t -> Facilitator -> CLI entry point -> strings (every rank runs the CLI; rank 0 keeps the dictionary)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        torch.manual_seed(77)
+        z_c_host = fac(z_t_host)                                     # host in -> host out (H2D + D2H inside)
+        seqs = cli.batch_stage3_generate_sequences(args, model, z_c_host)
+    torch.cuda.synchronize(dev)
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    assert len(seqs) == R and all(len(v) == P for v in seqs.values())
+    if rank == 0:
+        per_launch = L * eng.launches_per_step + 9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': a.precision, 'data': 'synthetic',
+            'config': {'workload': 'Facilitator z_t->z_c + ProteoScribe end-to-end sampling, 16 prompts x 32 replicas '
+                                   '(BASELINE.json configs[3]): 16 units of 32, round-robin over the ranks, two units fused per '
+                                   'launch (B = 64, group = 32), NCCL all-gather of token ids',
+                       'global_batch': P * R, 'seq_len': L, 'denoising_steps': L, 'parallelism': f'units{world}',
+                       'l2': 'per-step working set (737 MB of activations at B=64) is larger than the 126 MB L2; no flush needed',
+                       'noise': 'Exp(1) race noise drawn on the device (Philox), one seed per unit'},
+            'e2e': {'value': P * R / float(t_e2e.item()), 'unit': UNIT, 'h2d_bytes_per_step': P * 512 * 4 + P * 512 * 4 + P * R * L * 8,
+                    'd2h_bytes_per_step': P * 512 * 4 + P * R * L, 'steps': 1,
+                    'api': 'biom3_b200.Stage1_source.model.Facilitator + biom3_b200.run_ProteoScribe_sample.batch_stage3_generate_sequences'},
+            'roofline': None, 'cpu_baseline': None, 'clocks': clk,
+            'gpu_launches': a.steps * ((len(mine) + 1) // 2) * per_launch,
+            'checksum': int(allt.sum().item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c5(a):
+    """BASELINE.json configs[4]: per-step forward microbench, L = 1024, batch sweep 1..1024, fp32-class vs bf16.  One JSON
+    line: `value` = sequence-steps per second of the bf16 forward at B = 64; the whole sweep under `sweep`."""
+    import torch
+    from biom3_b200 import synthetic
+    from biom3_b200.engine import Engine
+    dev = torch.device('cuda:0')
+    torch.cuda.set_device(dev)
+    args = synthetic.stage3_args()
+    sd = synthetic.random_state_dict(args, seed=0)
+    peaks = load_peaks()
+    sweep = []
+    clocks = ClockSampler(0)
+    clocks.start()
+    for prec in ('bf16', 'fp32'):
+        for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+            eng = Engine(args, sd, dev, B, precision=prec)
+            g = torch.Generator().manual_seed(B)
+            x = torch.randint(0, C, (B, L), generator=g).to(dev)
+            t = torch.randint(0, L, (B,), generator=g).to(dev)
+            zc = synthetic.synthetic_z_c(B, 512, seed=1).to(dev)
+            for _ in range(max(3, a.warmup)):
+                eng.forward(x, t, zc)
+            torch.cuda.synchronize(dev)
+            n = max(a.steps, 3) * (8 if B <= 64 else 2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                eng.forward(x, t, zc)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            sweep.append({'precision': prec, 'B': B, 'ms': round(ms, 4), 'seq_steps_per_s': round(B / ms * 1e3, 1),
+                          'tflops': round(FLOP_PER_SEQ_STEP * B / (ms * 1e-3) / 1e12, 1)})
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+    clk = clocks.stop()
+    ref = next(r for r in sweep if r['precision'] == 'bf16' and r['B'] == 64)
+    line = {
+        'metric': 'per-step forward throughput (sequence-steps/s, sequence length 1024)', 'value': ref['seq_steps_per_s'],
+        'unit': 'sequence-steps/s', 'n_gpus': 1, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ref['ms'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 (headline) and f32-class (sweep)',
+        'data': 'synthetic',
+        'config': {'workload': 'ProteoScribe per-step forward microbench: sequence length 1024, batch sweep 1-1024, fp32 vs bf16 '
+                               '(BASELINE.json configs[4]); forward API biom3_forward (logits for every position), CUDA-graph replay',
+                   'seq_len': L, 'l2': 'B >= 16: activations exceed the 126 MB L2; B < 16 is launch / weight-bandwidth bound'},
+        'sweep': sweep, 'peak_tflops_sustained': peaks['tf_sustained'], 'clocks': clk, 'e2e': None, 'roofline': None,
+        'cpu_baseline': None, 'gpu_launches': None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -352,6 +519,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', type=str, default='c2', choices=['c2', 'c4', 'c5'],
+                    help='c2: BASELINE configs[1] / [2] (default, the driver contract); c4: configs[3] Facilitator + 16 x 32; '
+                         'c5: configs[4] forward microbench sweep')
+    ap.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'],
+                    help='fp32 = the fp32-class mode (the arithmetic the reference itself runs at inference)')
     a = ap.parse_args()
     # stdout must carry exactly one JSON line: libraries that write to file descriptor 1 behind Python's back (NCCL prints
     # its version banner there) are sent to stderr, and print() is pointed at the saved descriptor.
@@ -364,7 +536,12 @@ def main():
     else:
         import __graft_entry__
         __graft_entry__.build()
-        run_cuda_arm(a)
+        if a.config == 'c4':
+            run_c4(a)
+        elif a.config == 'c5':
+            run_c5(a)
+        else:
+            run_cuda_arm(a)
     real_stdout.flush()
 
 

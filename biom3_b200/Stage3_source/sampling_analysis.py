@@ -138,13 +138,17 @@ def default_noise_seed(device) -> int:
 @torch.no_grad()
 def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_time, extract_digit_label,
                                     sampling_path, noise: Optional[torch.Tensor] = None,
-                                    seed: Optional[int] = None, final_only: bool = False):
-    """Reference signature (:204-211) plus three optional keywords:
+                                    seed: Optional[int] = None, final_only: bool = False,
+                                    group: Optional[int] = None, group_seeds=None):
+    """Reference signature (:204-211) plus optional keywords:
 
     noise       explicit Exp(1) draws [T, B*L, C] (parity runs); default: drawn on the device.
     seed        Philox seed for the on-device draws; default: ``default_noise_seed`` (CUDA generator).
     final_only  bring back only the final state (64 KB instead of the 64 MB trajectory at B = 64): the returned
                 list has the reference's length but only ``[-1]`` can be read.
+    group, group_seeds  several independent reference batches of ``group`` samples fused into one launch (the
+                cross-sample unmask write, :254-256, stays inside each batch); ``group_seeds[g]`` is batch g's Philox
+                seed, and its tokens are exactly those of a separate call with ``seed=group_seeds[g]``.
     """
     assert extract_digit_samples.size(0) == extract_digit_label.size(0) == sampling_path.size(0) == \
         extract_time.size(0), "Mismatched batch dimensions"
@@ -157,7 +161,12 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
     L = eng.L
     start = int(extract_time.reshape(-1)[0].item())          # the reference assumes one shared start step
     steps = max(0, int(args.diffusion_steps) - start)
-    if seed is None and noise is None:
+    if group is None:
+        group = B
+    gs = None
+    if group_seeds is not None:
+        gs = torch.as_tensor([int(v) & (2 ** 63 - 1) for v in group_seeds], dtype=torch.int64).to(dev)
+    elif seed is None and noise is None:
         seed = default_noise_seed(dev)
     y_c = _pinned(extract_digit_label.float()).to(dev, non_blocking=True)
     path = _pinned(sampling_path.long()).to(dev, non_blocking=True)
@@ -167,8 +176,8 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
         state0 = _pinned(x0.long()).to(dev, non_blocking=True)
     if noise is not None:
         noise = _pinned(noise.float()).to(dev, non_blocking=True)
-    tokens, traj = eng.decode(y_c, path, state0=state0, start_step=start, num_steps=steps, group=B,
-                              noise=noise, seed=seed or 0, want_traj=not final_only)
+    tokens, traj = eng.decode(y_c, path, state0=state0, start_step=start, num_steps=steps, group=group,
+                              noise=noise, seed=seed or 0, want_traj=not final_only, group_seeds=gs)
     if final_only:
         host = torch.empty((B, L), dtype=torch.uint8, pin_memory=True)
         host.copy_(tokens.to(torch.uint8), non_blocking=True)

@@ -60,7 +60,7 @@ def load() -> C.CDLL:
     lib.biom3_finalize_weights.restype = i32
     lib.biom3_forward.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     lib.biom3_forward.restype = i32
-    lib.biom3_decode.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, u64, vp, vp, i32, vp]
+    lib.biom3_decode.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, u64, vp, vp, vp, i32, vp]
     lib.biom3_decode.restype = i32
     lib.biom3_sample_all.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.biom3_sample_all.restype = i32

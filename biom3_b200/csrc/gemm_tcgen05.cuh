@@ -236,6 +236,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int tile = p.reverse ? num_tiles - 1 - t : t;
         const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
         const int n0 = tile_nt(tile) * BN + int(cta_rank) * SL::B_ROWS * (CG2 ? 1 : 0) + p.b_row_offset;
+        // (Round 2: an L2 prefetch of the NEXT tile's A boxes from here, cp.async.bulk.prefetch.tensor, made the step 6 %
+        // slower, FF2 +24 %: the operand feed of these GEMMs is not bound by first-touch HBM latency.)
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait_parked(&empty_bar[stage], phase ^ 1);
           if (p.trace && blockIdx.x == 0 && lane == 0 && (kb == 0 || kb == k_blocks - 1)) {

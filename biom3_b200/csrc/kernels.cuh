@@ -22,6 +22,9 @@ struct DecodeCtl {
   const float* noise;          // external Exp(1) noise [T][B*L][C] or nullptr -> Philox
   uint8_t* traj;               // trajectory [T][B][L] or nullptr
   unsigned long long seed;     // Philox seed when noise == nullptr
+  const unsigned long long* group_seeds;   // or one seed per reference batch (group) of a fused launch: the draw for (sample b,
+                               // position l) then uses seed group_seeds[b / group] at position (b % group) * L + l, i.e. exactly
+                               // what a separate launch of that group with that seed would draw
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -381,7 +384,10 @@ head_kernel(const HeadArgs a) {
           const size_t BLC = size_t(a.B) * a.L * a.C;
           qn = __ldg(a.ctl->noise + size_t(step - a.ctl->start) * BLC + size_t(pos) * a.C + lane);
         } else {
-          qn = philox_exp1(a.ctl->seed, step, pos, lane);
+          if (a.ctl->group_seeds)
+            qn = philox_exp1(a.ctl->group_seeds[b / a.group], step, (b % a.group) * a.L + l, lane);
+          else
+            qn = philox_exp1(a.ctl->seed, step, pos, lane);
         }
       }
       const int tok = categorical_draw(my_logit, qn, lane, a.C);

@@ -587,7 +587,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
 }
 
 __global__ void set_ctl_kernel(k::DecodeCtl* ctl, int step, int start, const float* noise, uint8_t* traj,
-                               unsigned long long seed) {
+                               unsigned long long seed, const unsigned long long* group_seeds) {
   ctl->step = step;
   ctl->start = start;
   ctl->done = 0;
@@ -595,6 +595,7 @@ __global__ void set_ctl_kernel(k::DecodeCtl* ctl, int step, int start, const flo
   ctl->noise = noise;
   ctl->traj = traj;
   ctl->seed = seed;
+  ctl->group_seeds = group_seeds;
 }
 
 int check_ready(biom3_model* m, int B) {
@@ -951,8 +952,8 @@ int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const floa
 }
 
 int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const int64_t* state0, int start_step,
-                 int num_steps, int group, const float* noise, uint64_t seed, int64_t* tokens, uint8_t* traj, int B,
-                 void* stream) {
+                 int num_steps, int group, const float* noise, uint64_t seed, const uint64_t* group_seeds, int64_t* tokens,
+                 uint8_t* traj, int B, void* stream) {
   int r = check_ready(m, B);
   if (r) return r;
   if (!y_c || !path || !tokens) return fail(BIOM3_ERR_INVALID, "null argument");
@@ -970,7 +971,8 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
   CU_OK(cudaMemsetAsync(m->inv_path, 0, size_t(n) * sizeof(int), st));   // a non-permutation row falls back to location 0, like argmax of an all-false mask
   k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L);
   run_y_mlp(m, y_c, B, st);
-  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed);
+  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed,
+                                  reinterpret_cast<const unsigned long long*>(group_seeds));
   CU_OK(cudaGetLastError());
 
   if (num_steps > 0) {
@@ -1008,7 +1010,7 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
   CU_OK(cudaDeviceSynchronize());             // a decode still running on the caller's stream owns the resident state
   cudaStream_t st = m->cap_stream;
   // a valid resident state is assumed (call after a decode); run one warm step then a timed one
-  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull);
+  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull, nullptr);
   CU_OK(run_step(m, B, group, nullptr, nullptr, true, true, st, nullptr, nullptr));
   Profiler prof;
   prof.st = st;

@@ -106,8 +106,10 @@ class Engine:
 
     def decode(self, y_c: torch.Tensor, path: torch.Tensor, state0: Optional[torch.Tensor] = None,
                start_step: int = 0, num_steps: Optional[int] = None, group: Optional[int] = None,
-               noise: Optional[torch.Tensor] = None, seed: int = 0, want_traj: bool = False):
-        """All tensors already on the device.  Returns (tokens int64 [B, L], traj uint8 [T, B, L] | None)."""
+               noise: Optional[torch.Tensor] = None, seed: int = 0, want_traj: bool = False,
+               group_seeds: Optional[torch.Tensor] = None):
+        """All tensors already on the device.  Returns (tokens int64 [B, L], traj uint8 [T, B, L] | None).
+        group_seeds: int64 [B / group] (cuda), one Philox seed per reference batch of a fused launch."""
         B = path.shape[0]
         L = self.L
         if num_steps is None:
@@ -121,12 +123,16 @@ class Engine:
         if noise is not None:
             assert noise.dtype == torch.float32 and noise.is_cuda and noise.is_contiguous()
             assert noise.shape == (num_steps, B * L, self.C), (noise.shape, (num_steps, B * L, self.C))
+        if group_seeds is not None:
+            assert group_seeds.shape == (B // group,) and group_seeds.dtype == torch.int64 and group_seeds.is_cuda
+            group_seeds = group_seeds.contiguous()
         tokens = torch.empty(B, L, device=self.device, dtype=torch.int64)
         traj = torch.empty(num_steps, B, L, device=self.device, dtype=torch.uint8) if want_traj else None
         with torch.cuda.device(self.device):
             _lib.check(self.lib.biom3_decode(
                 self.handle, _ptr(y_c), _ptr(path), _ptr(state0), int(start_step), int(num_steps), int(group),
-                _ptr(noise), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(tokens), _ptr(traj), B, self._stream()))
+                _ptr(noise), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(group_seeds), _ptr(tokens), _ptr(traj), B,
+                self._stream()))
         return tokens, traj
 
     def debug_buffer(self, name: str, shape, dtype: torch.dtype) -> torch.Tensor:

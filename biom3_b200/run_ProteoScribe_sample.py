@@ -85,18 +85,33 @@ def batch_stage3_generate_sequences(args, model, z_t, unit_paths=None, unit_nois
         paths = [torch.stack([torch.randperm(L) for _ in range(bs)]) for (_, _, bs) in units]
     if unit_seeds is None and unit_noise is None:
         unit_seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in units]
-    for slot, uid in enumerate(mine):
-        p, _, bs = units[uid]
-        z = z_t[p].unsqueeze(0).repeat(bs, 1)
+    # Units are independent, so consecutive units of equal size are fused into one launch of up to
+    # ``args.b200_rows_per_launch`` (default 64) rows with ``group = unit size``: the unmask write stays inside each unit and
+    # every unit keeps its own noise seed, so its tokens do not depend on what it was fused with.
+    max_rows = int(getattr(args, 'b200_rows_per_launch', 64) or 64)
+    slot = 0
+    while slot < len(mine):
+        bs = units[mine[slot]][2]
+        n = 1
+        while slot + n < len(mine) and units[mine[slot + n]][2] == bs and (n + 1) * bs <= max_rows:
+            n += 1
+        batch = mine[slot:slot + n]
         if device_paths:
             from . import engine as _engine
-            paths[uid] = _engine.random_paths(bs, L, path_seeds[uid], args.device)
+            for uid in batch:
+                paths[uid] = _engine.random_paths(bs, L, path_seeds[uid], args.device)
+        z = torch.cat([z_t[units[uid][0]].unsqueeze(0).repeat(bs, 1) for uid in batch]).to(args.device)
+        pth = torch.cat([paths[uid].to(args.device) for uid in batch])
+        noise = None if unit_noise is None else torch.cat([unit_noise[uid] for uid in batch], dim=1)
         states, _ = Stage3_sample_tools.batch_generate_denoised_sampled(
-            args=args, model=model, extract_digit_samples=torch.zeros(bs, L),
-            extract_time=torch.zeros(bs).long(), extract_digit_label=z, sampling_path=paths[uid],
-            noise=None if unit_noise is None else unit_noise[uid],
-            seed=None if unit_seeds is None else unit_seeds[uid], final_only=True)
-        local[slot, :bs] = torch.from_numpy(states[-1][:, 0, :].astype(np.uint8)).to(args.device)
+            args=args, model=model, extract_digit_samples=torch.zeros(n * bs, L),
+            extract_time=torch.zeros(n * bs).long(), extract_digit_label=z, sampling_path=pth,
+            noise=noise, group=bs, group_seeds=None if unit_seeds is None else [unit_seeds[uid] for uid in batch],
+            final_only=True)
+        last = torch.from_numpy(states[-1][:, 0, :].astype(np.uint8)).to(args.device)
+        for k in range(n):
+            local[slot + k, :bs] = last[k * bs:(k + 1) * bs]
+        slot += n
     allt = bdist.gather_unit_tokens(local, mine, len(units), rows).cpu().numpy()
     design_sequence_dict = {f'replica_{ii}': [] for ii in range(args.num_replicas)}
     for uid, (p, start, bs) in enumerate(units):

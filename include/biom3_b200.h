@@ -84,11 +84,14 @@ int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const floa
  *            (sampling_analysis.py:254-256) couples the samples of one call; B % group == 0
  *   noise    device fp32 [num_steps][B*L][num_classes] Exp(1) draws (what OneHotCategorical.sample()
  *            consumes, sampling_analysis.py:251), or NULL to draw on the device (Philox, `seed`)
+ *   group_seeds  device uint64 [B / group] or NULL: one Philox seed per reference batch of a fused launch; batch g
+ *            then draws exactly what a separate launch of its `group` samples with seed group_seeds[g] would draw
+ *            (so fusing independent (prompt, replica-batch) units into one launch does not change their tokens)
  *   tokens   device int64 [B][L] final state (out)
  *   traj     device uint8 [num_steps][B][L] state after every step (out), or NULL */
 int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const int64_t* state0, int start_step,
-                 int num_steps, int group, const float* noise, uint64_t seed, int64_t* tokens, uint8_t* traj, int B,
-                 void* stream);
+                 int num_steps, int group, const float* noise, uint64_t seed, const uint64_t* group_seeds,
+                 int64_t* tokens, uint8_t* traj, int B, void* stream);
 
 /* Replaces `argmax(OneHotCategorical(probs=softmax(logits,1).permute(0,2,1)).sample(), -1)`
  * (transformer_training_helper.py:444-449 + sampling_analysis.py:251) at every position.

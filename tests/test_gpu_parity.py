@@ -779,6 +779,24 @@ def test_cli_units_vs_reference_fixture():
     assert got == json.loads(str(z['result']))
 
 
+def test_cli_fused_units_equal_separate_launches():
+    """Independent (prompt, replica-batch) units fused into one launch (group = unit size, one Philox seed per unit) give
+    the tokens of separate launches: the result does not depend on args.b200_rows_per_launch."""
+    from biom3_b200 import run_ProteoScribe_sample as cli
+    from biom3_b200.Stage3_source import cond_diff_transformer_layer as mod
+    out = {}
+    for rows in (64, 2, 4):
+        args = synthetic.stage3_args(**dict(SMALL, text_emb_dim=64), num_replicas=4, batch_size_sample=2, b200_rows_per_launch=rows)
+        args.device = 'cuda'
+        model = mod.get_model(args, (32, 32), 29)
+        model.load_state_dict(synthetic.random_state_dict(args, seed=11, perturb_norm=True))
+        model.eval()
+        torch.manual_seed(5)
+        out[rows] = cli.batch_stage3_generate_sequences(args, model, synthetic.synthetic_z_c(3, 64, seed=4))
+    assert out[64] == out[2] == out[4]
+    assert sorted(out[64]) == [f'replica_{i}' for i in range(4)] and all(len(v) == 3 for v in out[64].values())
+
+
 def test_run_facilitator_sample_pt_round_trip(tmp_path):
     """run_Facilitator_sample.py:76-121 as a drop-in: config JSON + state-dict file + {'z_t': ...} .pt in, the same dict
     plus 'z_c' out; z_c equals the REAL Facilitator's (fixture), and the file feeds run_ProteoScribe_sample's loader."""
