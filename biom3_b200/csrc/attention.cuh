@@ -40,9 +40,15 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(ro
 constexpr int LIN_CH = 32;                         // rows per chunk
 constexpr float LIN_LAZY = 8.0f;                   // the column reference may trail the running maximum by e^8
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr int LIN_STAGE_BYTES = 2 * LIN_CH * 64;   // k + v (or q alone in phase B)
-constexpr int LIN_WARP_BYTES = 2 * LIN_STAGE_BYTES;
-constexpr int LIN_SMEM_BYTES = 4 * LIN_WARP_BYTES + 4 * DH * DH * 4 + 2 * 4 * DH * 4 + DH * 64;
+constexpr int LIN_STAGE_BYTES = 2 * LIN_CH * 64;   // one k + v chunk
+constexpr int LIN_NST = 3;                         // k/v stages per warp: two chunks in flight while one is consumed (the kernel is
+                                                   // bound by load latency, not bytes: round 1 had two stages = one chunk in flight)
+constexpr int LIN_QST = 4;                         // q stages per warp in phase B (LIN_CH x 64 bytes each, inside the same space)
+constexpr int LIN_WARP_BYTES = LIN_NST * LIN_STAGE_BYTES;
+// the four warps' partial (ctx, max, denominator) sets alias the stage space once phase A is over: 4 CTAs per SM still fit
+constexpr int LIN_SMEM_BYTES = 4 * LIN_WARP_BYTES + DH * 64;
+static_assert(4 * DH * DH * 4 + 2 * 4 * DH * 4 <= 4 * LIN_WARP_BYTES, "partials must fit in the stage space");
+static_assert(LIN_QST * LIN_CH * 64 <= LIN_WARP_BYTES, "q stages must fit in the warp's stage space");
 
 __device__ __forceinline__ void lin_load_chunk(uint32_t dst, const __nv_bfloat16* src, int lane) {
 #pragma unroll
@@ -74,10 +80,10 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 
   extern __shared__ __align__(128) uint8_t lin_smem[];
   const uint32_t stage0 = ptx::smem_u32(lin_smem) + warp * LIN_WARP_BYTES;
-  float* pctx = reinterpret_cast<float*>(lin_smem + 4 * LIN_WARP_BYTES);     // [4][32][32]
+  float* pctx = reinterpret_cast<float*>(lin_smem);                           // [4][32][32]: aliases the stages after phase A
   float* pmax = pctx + 4 * DH * DH;                                           // [4][32]
   float* pden = pmax + 4 * DH;                                                // [4][32]
-  uint8_t* ctxT = reinterpret_cast<uint8_t*>(pden + 4 * DH);                  // [32 e][32 d] bf16, swizzled rows
+  uint8_t* ctxT = lin_smem + 4 * LIN_WARP_BYTES;                              // [32 e][32 d] bf16, swizzled rows
 
   // ---------------------------------------------------------------- phase A
   float acc[2][4][4];
@@ -90,16 +96,20 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   float mrun[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
   float den[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 
-  lin_load_chunk(stage0, kg, lane);
-  lin_load_chunk(stage0 + LIN_CH * 64, vg, lane);
-  ptx::cp_async_commit();
+  auto load_kv = [&](int c) {
+    const uint32_t dst = stage0 + (c % LIN_NST) * LIN_STAGE_BYTES;
+    lin_load_chunk(dst, kg + size_t(c) * LIN_CH * DH, lane);
+    lin_load_chunk(dst + LIN_CH * 64, vg + size_t(c) * LIN_CH * DH, lane);
+    ptx::cp_async_commit();
+  };
+  for (int c = 0; c < LIN_NST - 1 && c < nchunks; ++c) load_kv(c);
   for (int c = 0; c < nchunks; ++c) {
-    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
-    if (c + 1 < nchunks) {
-      const uint32_t nxt = stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES;
-      lin_load_chunk(nxt, kg + size_t(c + 1) * LIN_CH * DH, lane);
-      lin_load_chunk(nxt + LIN_CH * 64, vg + size_t(c + 1) * LIN_CH * DH, lane);
-      ptx::cp_async_commit();
+    const uint32_t cur = stage0 + (c % LIN_NST) * LIN_STAGE_BYTES;
+    // chunk c + NST - 1 goes into the stage chunk c - 1 was consumed from (the __syncwarp at the loop's end orders it)
+    if (c + LIN_NST - 1 < nchunks) {
+      load_kv(c + LIN_NST - 1);
+      ptx::cp_async_wait<LIN_NST - 1>();
+    } else if (c + 1 < nchunks) {                  // LIN_NST == 3: exactly one younger chunk is still in flight
       ptx::cp_async_wait<1>();
     } else {
       ptx::cp_async_wait<0>();
@@ -164,7 +174,8 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       }
     __syncwarp();
   }
-  // partial results of this warp -> shared
+  // partial results of this warp -> shared (the partials alias the stages: every warp must be done reading its chunks)
+  __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -204,16 +215,18 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   for (int nt = 0; nt < 4; ++nt)
     ptx::ldmatrix_x4(sc + swz(8 * nt + (lane & 7), lane >> 3), cb[nt][0], cb[nt][1], cb[nt][2], cb[nt][3]);
   const int D = H * DH;
-  lin_load_chunk(stage0, qg, lane);
-  ptx::cp_async_commit();
+  auto load_q = [&](int c) {
+    lin_load_chunk(stage0 + (c % LIN_QST) * (LIN_CH * 64), qg + size_t(c) * LIN_CH * DH, lane);
+    ptx::cp_async_commit();
+  };
+  for (int c = 0; c < LIN_QST - 1 && c < nchunks; ++c) load_q(c);
   for (int c = 0; c < nchunks; ++c) {
-    const uint32_t cur = stage0 + (c & 1) * LIN_STAGE_BYTES;
-    if (c + 1 < nchunks) {
-      lin_load_chunk(stage0 + ((c + 1) & 1) * LIN_STAGE_BYTES, qg + size_t(c + 1) * LIN_CH * DH, lane);
-      ptx::cp_async_commit();
-      ptx::cp_async_wait<1>();
+    const uint32_t cur = stage0 + (c % LIN_QST) * (LIN_CH * 64);
+    if (c + LIN_QST - 1 < nchunks) {
+      load_q(c + LIN_QST - 1);
+      ptx::cp_async_wait<LIN_QST - 1>();
     } else {
-      ptx::cp_async_wait<0>();
+      ptx::cp_async_wait<0>();                     // tail: the last LIN_QST - 1 chunks are all in flight already
     }
     __syncwarp();
 #pragma unroll
