@@ -25,7 +25,15 @@ struct DecodeCtl {
   const unsigned long long* group_seeds;   // or one seed per reference batch (group) of a fused launch: the draw for (sample b,
                                // position l) then uses seed group_seeds[b / group] at position (b % group) * L + l, i.e. exactly
                                // what a separate launch of that group with that seed would draw
+  unsigned long long* stamps;  // [L][2] %globaltimer (ns) at the start of a step's first kernel and at the end of its last one
+                               // (biom3_debug_copy "stamps": shows that consecutive graph replays leave no host-side gap)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -73,6 +81,7 @@ __global__ void cond_build_kernel(const float* __restrict__ Ttab, const float* _
   ptx::pdl_sync();
   const int b = blockIdx.y;
   const int t = t_per_sample ? t_per_sample[b] : ctl->step;
+  if (!t_per_sample && ctl->stamps && blockIdx.x == 0 && b == 0 && threadIdx.x == 0) ctl->stamps[2 * t] = global_timer_ns();
   const float4* tt = reinterpret_cast<const float4*>(Ttab + size_t(t) * JD);
   const float4* yy = reinterpret_cast<const float4*>(Y + size_t(b) * JD);
   float4* cc = reinterpret_cast<float4*>(cvec + size_t(b) * JD);
@@ -559,6 +568,7 @@ __global__ void advance_kernel(DecodeCtl* ctl, const uint8_t* __restrict__ state
     __threadfence();
     if (atomicAdd(&ctl->done, 1u) == gridDim.x - 1) {
       ctl->done = 0;
+      if (ctl->stamps) ctl->stamps[2 * step + 1] = global_timer_ns();
       ctl->step = step + 1;
     }
   }

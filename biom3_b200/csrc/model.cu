@@ -281,6 +281,7 @@ struct biom3_model {
   uint8_t* state = nullptr;
   int *inv_path = nullptr, *t_i32 = nullptr;
   k::DecodeCtl* ctl = nullptr;
+  unsigned long long* stamps = nullptr;         // [L][2] per-step %globaltimer stamps of the last decode (debug_copy "stamps")
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
   CUtensorMap tm_qkv_attn{};                   // qkv as [3*B*H*L][32], 128-row boxes, 64B swizzle (tcgen05 attention loads)
   CUtensorMap tm_st_qkv{}, tm_st_hid{};        // TMA-store maps: qkv as [3*B*H*L][32], hid as [M][4D]
@@ -587,7 +588,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
 }
 
 __global__ void set_ctl_kernel(k::DecodeCtl* ctl, int step, int start, const float* noise, uint8_t* traj,
-                               unsigned long long seed, const unsigned long long* group_seeds) {
+                               unsigned long long seed, const unsigned long long* group_seeds, unsigned long long* stamps) {
   ctl->step = step;
   ctl->start = start;
   ctl->done = 0;
@@ -596,6 +597,7 @@ __global__ void set_ctl_kernel(k::DecodeCtl* ctl, int step, int start, const flo
   ctl->traj = traj;
   ctl->seed = seed;
   ctl->group_seeds = group_seeds;
+  ctl->stamps = stamps;
 }
 
 int check_ready(biom3_model* m, int B) {
@@ -853,6 +855,8 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(dev_alloc(m, &m->inv_path, M));
   TRY(dev_alloc(m, &m->t_i32, Bm));
   TRY(dev_alloc(m, &m->ctl, 1));
+  TRY(dev_alloc(m, &m->stamps, 2 * L));
+  CU_OK(cudaMemset(m->stamps, 0, 2 * L * sizeof(unsigned long long)));
   CU_OK(cudaMemset(m->ctl, 0, sizeof(k::DecodeCtl)));
   CU_OK(cudaMemset(m->inv_path, 0, M * sizeof(int)));
 
@@ -972,7 +976,7 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
   k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L);
   run_y_mlp(m, y_c, B, st);
   set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed,
-                                  reinterpret_cast<const unsigned long long*>(group_seeds));
+                                  reinterpret_cast<const unsigned long long*>(group_seeds), m->stamps);
   CU_OK(cudaGetLastError());
 
   if (num_steps > 0) {
@@ -1010,7 +1014,7 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
   CU_OK(cudaDeviceSynchronize());             // a decode still running on the caller's stream owns the resident state
   cudaStream_t st = m->cap_stream;
   // a valid resident state is assumed (call after a decode); run one warm step then a timed one
-  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull, nullptr);
+  set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, 0, 0, nullptr, nullptr, 1234ull, nullptr, nullptr);
   CU_OK(run_step(m, B, group, nullptr, nullptr, true, true, st, nullptr, nullptr));
   Profiler prof;
   prof.st = st;
@@ -1058,6 +1062,7 @@ int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t n
   else if (n == "Y") { src = m->Y; sz = size_t(m->max_batch) * depth * D * 4; }
   else if (n == "Ttab") { src = m->Ttab; sz = L * depth * D * 4; }
   else if (n == "state") { src = m->state; sz = M; }
+  else if (n == "stamps") { src = m->stamps; sz = 2 * L * sizeof(unsigned long long); }
   else return fail(BIOM3_ERR_INVALID, "unknown buffer " + n);
   CU_OK(cudaSetDevice(m->device));
   CU_OK(cudaDeviceSynchronize());

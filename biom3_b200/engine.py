@@ -101,7 +101,11 @@ class Engine:
         y_c = y_c.to(self.device, torch.float32).contiguous()
         out = torch.empty(B, self.C, self.L, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.biom3_forward(self.handle, _ptr(x), _ptr(t), _ptr(y_c), B, _ptr(out), self._stream()))
+            torch.cuda.nvtx.range_push(f'biom3_forward B={B}')           # NVTX: one range per C-ABI call
+            try:
+                _lib.check(self.lib.biom3_forward(self.handle, _ptr(x), _ptr(t), _ptr(y_c), B, _ptr(out), self._stream()))
+            finally:
+                torch.cuda.nvtx.range_pop()
         return out
 
     def decode(self, y_c: torch.Tensor, path: torch.Tensor, state0: Optional[torch.Tensor] = None,
@@ -129,10 +133,14 @@ class Engine:
         tokens = torch.empty(B, L, device=self.device, dtype=torch.int64)
         traj = torch.empty(num_steps, B, L, device=self.device, dtype=torch.uint8) if want_traj else None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.biom3_decode(
-                self.handle, _ptr(y_c), _ptr(path), _ptr(state0), int(start_step), int(num_steps), int(group),
-                _ptr(noise), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(group_seeds), _ptr(tokens), _ptr(traj), B,
-                self._stream()))
+            torch.cuda.nvtx.range_push(f'biom3_decode B={B} group={group} steps={num_steps}')
+            try:
+                _lib.check(self.lib.biom3_decode(
+                    self.handle, _ptr(y_c), _ptr(path), _ptr(state0), int(start_step), int(num_steps), int(group),
+                    _ptr(noise), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(group_seeds), _ptr(tokens), _ptr(traj), B,
+                    self._stream()))
+            finally:
+                torch.cuda.nvtx.range_pop()
         return tokens, traj
 
     def debug_buffer(self, name: str, shape, dtype: torch.dtype) -> torch.Tensor:

@@ -137,7 +137,9 @@ int biom3_profile_step(biom3_model* m, int B, int group, biom3_step_profile* out
 /* Test hook: synchronous device->host copy of an internal buffer after a forward/decode call.
  * name: "u" fp32 [B*L][D] | "a" bf16 [B*L][D] | "qkv" bf16 [3][B][H][L][32] | "att" bf16 [B*L][D] |
  * "hid" bf16 [B*L][4D] | "cvec" fp32 [B][depth][D] | "Y" fp32 [B][depth][D] | "Ttab" fp32 [L][depth][D] |
- * "state" u8 [B*L].  Copies min(nbytes, buffer size). */
+ * "state" u8 [B*L] | "stamps" u64 [L][2]: %globaltimer (ns) at the start of each step's first kernel and at the end of
+ * its last one, of the last biom3_decode (consecutive CUDA-graph replays: no host-side gap between steps).
+ * Copies min(nbytes, buffer size). */
 int biom3_debug_copy(biom3_model* m, const char* name, void* host_dst, int64_t nbytes);
 
 /* Replaces Facilitator.forward (Stage1_source/model.py:473-493; called at run_Facilitator_sample.py:79-83):
