@@ -48,7 +48,7 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 #define BIOM3_QKV_EPI_WARPS 8
 #endif
 __host__ __device__ constexpr int epi_warps(int epi) {
-  return (epi >= 3 && epi <= 5) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
+  return (epi >= 3 && epi <= 6) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
 }
 constexpr uint32_t EPI_WARP0 = 2;     // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
 
@@ -61,7 +61,19 @@ enum Epi : int {
   EPI_BIAS_RESID_SPLIT = 5, // like 3, but R lives as two bf16 arrays, R = hi + lo (hi = bf16(R), lo = bf16(R - hi)):
                             // `out_bf16` is hi (the array the next GEMM reads as its A operand), `out` is lo.  Same
                             // bytes read, 2 instead of 6 bytes per element written; R keeps 16 significant bits.
+  EPI_BIAS_RESID_SPLIT_TMA = 6, // same arithmetic and planes as 5, other data path (round 2): every epilogue warp owns a ring of
+                            // RESID_SLOTS shared-memory slots of one 32 x 32 chunk (hi block + lo block, 64-byte swizzle) that TMA
+                            // fills two chunks ahead; thread = row straight out of TMEM (no transposition), the slot is updated
+                            // in place and handed back to TMA as the store source.  tmap_c / tmap_d = the hi / lo plane.
+                            // Epilogue 5 keeps one chunk of residual in registers (16 x 16-byte loads per lane), which with the
+                            // ~1.7 us loaded HBM latency of this kernel pinned it at 4.4 TB/s (ncu: 45 % of the stall samples on
+                            // the first use of the prefetched registers).
 };
+#ifndef BIOM3_RESID_SLOTS
+#define BIOM3_RESID_SLOTS 3
+#endif
+constexpr int RESID_SLOTS = BIOM3_RESID_SLOTS;
+constexpr int RESID_SLOT_BYTES = 4096;   // 32 rows x 64 bytes, hi block then lo block
 
 struct Params {
   int M, N, K;
@@ -107,8 +119,11 @@ inline void fill_shifts(Params& p, int bn) {
 // Shared memory of one CTA: [operand ring] [epilogue staging] [per-column epilogue vectors].
 // Staging and vector space follow the epilogue (EPI), so that the kernels that need less of them can afford a deeper ring.
 __host__ __device__ constexpr bool epi_is_f32(int epi) { return epi >= 3 && epi <= 5; }
-__host__ __device__ constexpr int epi_stg_bytes(int epi) { return epi_warps(epi) * (epi_is_f32(epi) ? 4096 : 2048); }
-__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2) ? CV_TOTAL : 0; }
+__host__ __device__ constexpr int epi_stg_bytes(int epi) {
+  return epi == 6 ? epi_warps(epi) * RESID_SLOTS * RESID_SLOT_BYTES : epi_warps(epi) * (epi_is_f32(epi) ? 4096 : 2048);
+}
+// 1: the scale / shift vectors of the bf16 epilogues; 6: bias (+ conditioning) of the warp's 128 columns, double buffered
+__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2) ? CV_TOTAL : (epi == 6 ? 8 * 1024 : 0); }
 
 template <int BN, int STAGES, bool CG2, int EPI>
 struct SmemLayout {
@@ -158,7 +173,7 @@ __device__ long long g_gemm_trace[3][64][4];
 template <int BN, int STAGES, int EPI, bool CG2>
 __global__ void __launch_bounds__(32 * (EPI_WARP0 + epi_warps(EPI)), 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, const Params p) {
   static_assert(BN == 128 || BN == 256, "BN");
   using SL = SmemLayout<BN, STAGES, CG2, EPI>;
   constexpr int EPI_WARPS = epi_warps(EPI);
@@ -171,6 +186,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  constexpr bool TMA_RESID = (EPI == EPI_BIAS_RESID_SPLIT_TMA);
+  __shared__ uint64_t res_full[TMA_RESID ? EPI_WARPS * RESID_SLOTS : 1];   // one barrier per (epilogue warp, residual slot)
   __shared__ uint32_t tmem_base_slot;
 
   // The warp index goes through a shuffle so that the compiler can prove it warp-uniform: everything derived from it (roles,
@@ -209,6 +226,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
       ptx::mbar_init(&acc_empty[s], CG2 ? 2 * EPI_WARPS : EPI_WARPS);
+    }
+    if constexpr (TMA_RESID) {
+      ptx::tma_prefetch_desc(&tmap_c);
+      ptx::tma_prefetch_desc(&tmap_d);
+      for (int s = 0; s < EPI_WARPS * RESID_SLOTS; ++s) ptx::mbar_init(&res_full[s], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -344,6 +366,126 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         else ptx::mbar_arrive(&acc_empty[as]);
       }
     };
+    if constexpr (TMA_RESID) {
+      // ---------------------------------------------------------- epilogue 6: TMA-fed residual ring, thread = row
+      static_assert(!TMA_RESID || (BN == 256 && EPI_WARPS == 8), "epilogue 6: 128 columns per warp");
+      constexpr int RS = RESID_SLOTS;
+      uint8_t* const slot_p = smem + SL::STG_OFFSET + ew * (RS * RESID_SLOT_BYTES);
+      const uint32_t slot0 = ptx::smem_u32(slot_p);
+      const uint32_t addv0 = ptx::smem_u32(smem + SL::CV_OFFSET + ew * 1024);      // two 512-byte buffers
+      uint64_t* const rbar = &res_full[ew * RS];
+      const int my_tiles = t_begin < t_end ? (t_end - t_begin + t_step - 1) / t_step : 0;
+      const int n_chunks = my_tiles * NCH;
+      auto order4 = [](int i) { return ((i & 1) << 1) | (i >> 1); };               // 0, 2, 1, 3 (see below)
+      // TMA coordinates (column, row) of the n-th chunk of this warp's walk
+      auto chunk_coord = [&](int n, int& c0, int& c1) {
+        const int t = t_begin + (n >> 2) * t_step;
+        const int tile = p.reverse ? num_tiles - 1 - t : t;
+        c1 = tile_mb(tile) * TILE_M + int(cta_rank) * BM + quarter * 32;
+        c0 = tile_nt(tile) * BN + col_half * COLS_PER_WARP + order4(n & 3) * 32;
+      };
+      auto issue_load = [&](int n, uint32_t s) {                                   // one elected lane
+        int c0, c1;
+        chunk_coord(n, c0, c1);
+        ptx::mbar_arrive_expect_tx(&rbar[s], RESID_SLOT_BYTES);
+        ptx::tma_load_2d(slot_p + s * RESID_SLOT_BYTES, &tmap_c, &rbar[s], c0, c1);
+        ptx::tma_load_2d(slot_p + s * RESID_SLOT_BYTES + 2048, &tmap_d, &rbar[s], c0, c1);
+      };
+      if (ptx::elect_one()) {
+        for (int n = 0; n < RS && n < n_chunks; ++n) issue_load(n, uint32_t(n));
+      }
+      __syncwarp();
+      int n = 0;                         // chunks consumed so far
+      uint32_t slot = 0, sphase = 0;     // ring position of chunk n
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
+        const int tile = p.reverse ? num_tiles - 1 - t : t;
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const int m0 = tile_mb(tile) * TILE_M + int(cta_rank) * BM;
+        const int n_tile = tile_nt(tile);
+        const int rbase = m0 + quarter * 32;
+        const int nbase = n_tile * BN + col_half * COLS_PER_WARP;
+        const int bidx = row_b(rbase);
+        const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + as * BN + col_half * COLS_PER_WARP;
+        // bias (+ conditioning) of this warp's 128 columns -> warp-private smem, read back as broadcasts
+        const uint32_t av = addv0 + (it & 1) * 512;
+        {
+          float4 a4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + lane);
+          if (p.cond) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(p.cond + size_t(bidx) * p.cond_stride + nbase) + lane);
+            a4.x += cv.x; a4.y += cv.y; a4.z += cv.z; a4.w += cv.w;
+          }
+          st_shared_v4(av + lane * 16, __float_as_uint(a4.x), __float_as_uint(a4.y), __float_as_uint(a4.z), __float_as_uint(a4.w));
+        }
+        __syncwarp();
+        float rs = 0.f, rq = 0.f;
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][0] = clock64();
+        ptx::mbar_wait_parked(&acc_full[as], aphase);
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][1] = clock64();
+        ptx::tc_fence_after();
+        uint32_t r[2][32];                                   // TMEM loads run one chunk ahead
+        ptx::tmem_ld_32x32(t_row + order4(0) * 32, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci, ++n) {
+          // 32-column chunks in the order 0, 2, 1, 3: two chunks of a bf16 plane share a 128-byte line, and the chunk being
+          // fetched must not hit the line the current chunk is storing to (round 1: walking 0, 1, 2, 3 was 2.5 x slower)
+          const int c = order4(ci);
+          ptx::tmem_ld_wait();
+          if (ci + 1 < NCH) ptx::tmem_ld_32x32(t_row + order4(ci + 1) * 32, r[(ci + 1) & 1]);
+          else {
+            release_acc(as);
+            if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][2] = clock64();
+          }
+          ptx::mbar_wait(&rbar[slot], sphase);
+          const uint32_t sp = slot0 + slot * RESID_SLOT_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                      // 8 columns per step: one 16-byte piece of the hi and of the lo row
+            const uint32_t off = lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
+            const uint4 h4 = ld_shared_v4(sp + off), l4 = ld_shared_v4(sp + 2048 + off);
+            const uint4 a0 = ld_shared_v4(av + c * 128 + i * 32), a1 = ld_shared_v4(av + c * 128 + i * 32 + 16);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float ad[8] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z), __uint_as_float(a0.w),
+                                 __uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(a1.z), __uint_as_float(a1.w)};
+            uint32_t nh[4], nl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {                    // same expression order as epilogue 5: acc + ((hi + lo) + add)
+              const float r0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+              const float r1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              const float o0 = __uint_as_float(r[ci & 1][8 * i + 2 * e]) + (r0 + ad[2 * e]);
+              const float o1 = __uint_as_float(r[ci & 1][8 * i + 2 * e + 1]) + (r1 + ad[2 * e + 1]);
+              nh[e] = ptx::pack_bf16x2(o0, o1);
+              nl[e] = ptx::pack_bf16x2(o0 - __uint_as_float(nh[e] << 16), o1 - __uint_as_float(nh[e] & 0xffff0000u));
+              rs += o0 + o1;
+              rq = fmaf(o0, o0, fmaf(o1, o1, rq));
+            }
+            st_shared_v4(sp + off, nh[0], nh[1], nh[2], nh[3]);
+            st_shared_v4(sp + 2048 + off, nl[0], nl[1], nl[2], nl[3]);
+          }
+          // the updated slot IS the TMA box image of both planes: publish it to the async proxy, one elected lane stores,
+          // waits until the store has read the slot, and refills it with the chunk RS positions further on
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (ptx::elect_one()) {
+            int c0, c1;
+            chunk_coord(n, c0, c1);
+            ptx::tma_store_2d(&tmap_c, sp, c0, c1);
+            ptx::tma_store_2d(&tmap_d, sp + 2048, c0, c1);
+            ptx::tma_store_commit();
+            if (n + RS < n_chunks) {
+              ptx::tma_store_wait_read();
+              issue_load(n + RS, slot);
+            }
+          }
+          __syncwarp();
+          if (++slot == RS) { slot = 0; sphase ^= 1; }
+        }
+        if (p.stats_out) {
+          const int parts = n_tiles * 2, part = n_tile * 2 + col_half;
+          *reinterpret_cast<float2*>(p.stats_out + (size_t(rbase + lane) * parts + part) * 2) = make_float2(rs, rq);
+        }
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][3] = clock64();
+      }
+    } else {
     // Residual rows of the chunk being processed; each slot is reloaded right after it is consumed with the value of the
     // next chunk of the walk (the next tile's first chunk at the end of a tile): 32 registers of prefetched data.  The walk
     // visits the 32-column chunks 0, 2, 1, 3 so that the prefetch of the next chunk never touches the 128-byte line the
@@ -612,6 +754,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][3] = clock64();
       }
     }
+    }   // !TMA_RESID
   }
 
   if (warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();   // smem must outlive the last TMA-store reads

@@ -122,14 +122,17 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
 // a 6-stage QKV ring again in round 2: no change)
 template <int BN, bool CG2, int EPI>
 constexpr int gemm_stages() {
+  // epilogue 6 spends 96 KB on its residual slots; it serves the K = 512 out-projection, whose mainloop is far from
+  // binding (3 stages measured equal to 5 for that GEMM in round 1)
+  if (CG2 && BN == 256 && EPI == gemm::EPI_BIAS_RESID_SPLIT_TMA) return 3;
   if (CG2 && BN == 256) return 5;
   return CG2 ? 7 : (BN == 256 ? 3 : 5);
 }
 
 // launch only; the caller checks cudaGetLastError()
 template <int BN, int EPI, bool CG2>
-void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p_in,
-                   int num_sms, cudaStream_t st) {
+void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
+                   const gemm::Params& p_in, int num_sms, cudaStream_t st) {
   gemm::Params p = p_in;
   gemm::fill_shifts(p, BN);
   constexpr int STAGES = gemm_stages<BN, CG2, EPI>();
@@ -153,9 +156,9 @@ void launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, p);
+    cudaLaunchKernelEx(&cfg, gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, true>, ta, tb, tc, td, p);
   } else {
-    launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(threads), size_t(smem), st, ta, tb, tc, p);
+    launch_k(gemm::gemm_bf16_tcgen05<BN, STAGES, EPI, false>, dim3(grid), dim3(threads), size_t(smem), st, ta, tb, tc, td, p);
   }
 }
 
@@ -165,8 +168,8 @@ template <int EPI>
 void launch_gemm(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                  const gemm::Params& p, int num_sms, cudaStream_t st) {
   (void)bn;                                     // tiles are 256 columns wide (128-wide tiles were measured slower in round 1)
-  if (pair) launch_gemm_t<256, EPI, true>(ta, tb, tc, p, num_sms, st);
-  else launch_gemm_t<256, EPI, false>(ta, tb, tc, p, num_sms, st);
+  if (pair) launch_gemm_t<256, EPI, true>(ta, tb, tc, tc, p, num_sms, st);
+  else launch_gemm_t<256, EPI, false>(ta, tb, tc, tc, p, num_sms, st);
 }
 
 constexpr int HEAD_SMEM_MAX = 32 * 1024 * 4;   // num_classes <= 32, dim <= 1024, fp32
@@ -186,6 +189,7 @@ cudaError_t init_kernel_attributes_impl() {
   SET_GEMM(gemm::EPI_BIAS_GELU_BF16)
   SET_GEMM(gemm::EPI_STORE_BF16)
   SET_GEMM(gemm::EPI_STORE_F32)
+  SET_GEMM1(256, gemm::EPI_BIAS_RESID_SPLIT_TMA, true)      // pair tiling only
 #undef SET_GEMM1
 #undef SET_GEMM
   e = cudaFuncSetAttribute(attn::local_attention_kernel<attn::LOCAL_NST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -297,6 +301,11 @@ struct biom3_model {
   float* stats_c = nullptr;
   CUtensorMap tm_att_c{}, tm_a_c{}, tm_hid_c{}, tm_st_hid_c{};
   CUtensorMap tm_wqkv[2]{}, tm_wo[2]{}, tm_w1[2]{}, tm_w2[2]{};   // [0]: box 128 rows, [1]: box 256 rows
+  // Residual planes as 32 x 32 TMA boxes (epilogue 6).  resid_tma (BIOM3_RESID_TMA): 0 = epilogue 5 everywhere, 1 = the
+  // out-projection (K = 512, bound by its residual epilogue) uses epilogue 6, 2 = FF2 as well (A/B only: FF2 is bound
+  // by its K = 2048 mainloop and wants the 5-stage operand ring epilogue 6 has no room for)
+  int resid_tma = 1;
+  CUtensorMap tm_rs_hi{}, tm_rs_lo{}, tm_rs_hi_c{}, tm_rs_lo_c{};
   // step graph cache
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -432,9 +441,12 @@ void run_y_mlp(biom3_model* m, const float* y_c, int B, cudaStream_t st) {
   k::cond_transpose_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->Ytmp, m->Y, B, D, depth);
 }
 
-// Residual update of the split (hi, lo) stream (gemm::EPI_BIAS_RESID_SPLIT)
-void launch_resid_split(biom3_model* m, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& r, cudaStream_t st) {
-  launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st);
+// Residual update of the split (hi, lo) stream: gemm::EPI_BIAS_RESID_SPLIT, or, with `tma_resid` (pair tiling; the caller
+// picks it per GEMM, see biom3_model::resid_tma), gemm::EPI_BIAS_RESID_SPLIT_TMA over the (hi, lo) plane maps `th`, `tl`.
+void launch_resid_split(biom3_model* m, bool pair, bool tma_resid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& th,
+                        const CUtensorMap& tl, const gemm::Params& r, cudaStream_t st) {
+  if (tma_resid && pair) launch_gemm_t<256, gemm::EPI_BIAS_RESID_SPLIT_TMA, true>(ta, tb, th, tl, r, m->num_sms, st);
+  else launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(m->bn_narrow, pair, ta, tb, m->tm_st_hid, r, m->num_sms, st);
 }
 
 // One per-step forward over the resident state.  sample: draw + unmask (decode); else write logits.
@@ -533,7 +545,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_OTHER, launch_k(k::gather_rows_kernel, dim3(std::min(Mc / 8, m->num_sms * 8)), dim3(256), 0, st, m->att, m->a, m->u_lo,
                                m->att_c, m->a_c, m->ulo_c, m->inv_path, m->ctl, L, D, group, B * group, Mc));
       r.M = Mc; r.out = m->ulo_c; r.out_bf16 = m->a_c; r.stats_out = m->stats_c; r.reverse = 0;
-      LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att_c, m->tm_wo[in], r, st));
+      LAUNCH(C_OUT, launch_resid_split(m, pn, m->resid_tma >= 1, m->tm_att_c, m->tm_wo[in], m->tm_rs_hi_c, m->tm_rs_lo_c, r, st));
       p.M = Mc; p.a_row_offset = 0; p.reverse = 0;
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid_c;
       p.ln_stats = m->stats_c;
@@ -541,12 +553,12 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_BF16>(m->bn_wide, pw, m->tm_a_c, m->tm_w1[iw], m->tm_st_hid_c, p, m->num_sms, st));
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = nullptr; r.cond_stride = JD;
-      LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid_c, m->tm_w2[in], r, st));
+      LAUNCH(C_FF2, launch_resid_split(m, pn, m->resid_tma >= 2, m->tm_hid_c, m->tm_w2[in], m->tm_rs_hi_c, m->tm_rs_lo_c, r, st));
       continue;
     }
     if (split) {
       r.out = m->u_lo;
-      LAUNCH(C_OUT, launch_resid_split(m, pn, m->tm_att, m->tm_wo[in], r, st));
+      LAUNCH(C_OUT, launch_resid_split(m, pn, m->resid_tma >= 1, m->tm_att, m->tm_wo[in], m->tm_rs_hi, m->tm_rs_lo, r, st));
     } else {
       LAUNCH(C_OUT, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_att, m->tm_wo[in], m->tm_st_hid, r, m->num_sms, st));
     }
@@ -564,7 +576,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     r.cond_stride = JD;
     if (split) {
       r.out = m->u_lo;
-      LAUNCH(C_FF2, launch_resid_split(m, pn, m->tm_hid, m->tm_w2[in], r, st));
+      LAUNCH(C_FF2, launch_resid_split(m, pn, m->resid_tma >= 2, m->tm_hid, m->tm_w2[in], m->tm_rs_hi, m->tm_rs_lo, r, st));
     } else {
       LAUNCH(C_FF2, launch_gemm<gemm::EPI_BIAS_RESID_F32>(m->bn_narrow, pn, m->tm_hid, m->tm_w2[in], m->tm_st_hid, r, m->num_sms, st));
     }
@@ -647,6 +659,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_PDL")) m->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_RESID_TMA")) m->resid_tma = atoi(e);
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
@@ -889,7 +902,15 @@ int biom3_finalize_weights(biom3_model* m) {
       TRY(make_tmap(&m->tm_a_c, m->a_c, want, D, 128));
       TRY(make_tmap(&m->tm_hid_c, m->hid_c, want, 4 * D, 128));
       TRY(make_store_tmap(&m->tm_st_hid_c, m->hid_c, want, 4 * D));
+      TRY(make_store_tmap(&m->tm_rs_hi_c, m->a_c, want, D));
+      TRY(make_store_tmap(&m->tm_rs_lo_c, m->ulo_c, want, D));
     }
+  }
+  if (m->u_lo) {
+    TRY(make_store_tmap(&m->tm_rs_hi, m->a, M, D));
+    TRY(make_store_tmap(&m->tm_rs_lo, m->u_lo, M, D));
+  } else {
+    m->resid_tma = 0;
   }
   TRY(make_tmap(&m->tm_a, m->a, M, D, 128));
   TRY(make_tmap(&m->tm_att, m->att, M, D, 128));
@@ -1280,6 +1301,17 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
       p.out_bf16 = reinterpret_cast<bf16*>(out);
       p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
       launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_BIAS_RESID_SPLIT_TMA: {  // same planes, TMA-fed residual ring (pair tiling only)
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      if (!pair) return fail(BIOM3_ERR_INVALID, "epilogue 6 needs pair tiling");
+      CUtensorMap th, tl;
+      if ((r = make_store_tmap(&th, out, M, N))) return r;
+      if ((r = make_store_tmap(&tl, reinterpret_cast<bf16*>(out) + size_t(M) * N, M, N))) return r;
+      p.out_bf16 = reinterpret_cast<bf16*>(out);
+      p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
+      launch_gemm_t<256, gemm::EPI_BIAS_RESID_SPLIT_TMA, true>(ta, tb, th, tl, p, sms, st);
+      break;
+    }
     default: return fail(BIOM3_ERR_INVALID, "unknown epilogue");
   }
   CU_OK(cudaGetLastError());

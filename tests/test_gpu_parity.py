@@ -600,12 +600,14 @@ def test_generate_denoised_sampled_single_sequence_vs_reference_fixture():
                                        sampling_path=path)
 
 
-@pytest.mark.parametrize('epi', [5])
+@pytest.mark.parametrize('epi', [5, 6])
 @pytest.mark.parametrize('bn,pair', [(256, False), (256, True)])
 def test_gemm_split_residual_epilogue(bn, pair, epi):
-    """Epilogue 5: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place (accumulator transposed
-    through shared memory, coalesced accesses)."""
+    """Epilogues 5 / 6: the residual stream stored as bf16 hi + lo planes, R += A W^T + bias in place (5: accumulator
+    transposed through shared memory, residual prefetched in registers; 6: TMA-fed residual slots, thread = row, TMA stores)."""
     from biom3_b200 import engine
+    if epi == 6 and not pair:
+        pytest.skip('epilogue 6 exists for the pair tiling only')
     g = torch.Generator().manual_seed(9)
     M, N, K = 1024, 512, 512
     A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
@@ -623,6 +625,28 @@ def test_gemm_split_residual_epilogue(bn, pair, epi):
     assert torch.equal(planes[0], got.bfloat16()) or rel_err(planes[0].float(), ref) < 4e-3   # hi plane = bf16(R)
 
 
+@pytest.mark.parametrize('M,K', [(256 * 74 * 3 + 512, 512), (32768, 2048)])
+def test_gemm_tma_residual_epilogue_equals_register_epilogue(M, K):
+    """Epilogue 6 against epilogue 5 on problems with several tiles per CTA pair (the residual ring wraps, slots are
+    refilled across tile boundaries, the last tiles of a worker drain the ring): same per-element expression, so both
+    planes must be bit-identical; twice in a row (the planes are updated in place)."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(11)
+    N = 512
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    R = (torch.randn(M, N, generator=g) * 3.0).cuda()
+    hi = R.bfloat16()
+    p5 = torch.stack([hi, (R - hi.float()).bfloat16()]).contiguous()
+    p6 = p5.clone()
+    for _ in range(2):
+        engine.gemm_test(A, W, bias, 5, 256, out=p5, pair=True)
+        engine.gemm_test(A, W, bias, 6, 256, out=p6, pair=True)
+        torch.cuda.synchronize()
+        assert torch.equal(p5[0], p6[0]) and torch.equal(p5[1], p6[1])
+    ref = R + 2 * (A.float() @ W.float().t() + bias)
+    assert rel_err(p6[0].float() + p6[1].float(), ref) < 1e-4
 
 
 # ---------------------------------------------------------------- the on-device noise (the path bench.py times) under the oracle
