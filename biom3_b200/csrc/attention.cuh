@@ -605,7 +605,10 @@ local_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
         // (~1500 cycles per block pair, MUFU 2/3 busy; profiles/r02_attn_trace_v5_uniform_issue.log).  Measured and not
         // kept: taking turns on the pipe through a shared-memory hint (+5 %), a cubic exp2 on the FMA pipe for every 4th
         // or 8th element (+4 % / +8 %: with two warps per SMSP the issue slots, not MUFU, are what the extra
-        // instructions cost), four streams of 32-key blocks (+8 %); profiles/r02_attn_variants_v5.log.
+        // instructions cost), four streams of 32-key blocks (+8 %); profiles/r02_attn_variants_v5.log.  Strict alternation of
+        // the two warps' exponential loops through a pair of named barriers per quarter (bar.sync / bar.arrive token, the
+        // MUFU-free part of one warp under the other's loop): +5 % (88.8 -> 93.7 us isolated, 1.56 -> 1.70 ms per step;
+        // profiles/r02_attn_pingpong_rejected.log): one warp alone does not keep the pipe full.
         uint32_t pk[32];                                   // P (bf16 pairs) over the first 32 of the slot's 64 columns
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll

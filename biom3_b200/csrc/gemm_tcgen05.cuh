@@ -73,6 +73,9 @@ enum Epi : int {
 #define BIOM3_RESID_SLOTS 3
 #endif
 constexpr int RESID_SLOTS = BIOM3_RESID_SLOTS;
+#ifndef BIOM3_RESID_REFILL_LATE
+#define BIOM3_RESID_REFILL_LATE 1
+#endif
 constexpr int RESID_SLOT_BYTES = 4096;   // 32 rows x 64 bytes, hi block then lo block
 
 struct Params {
@@ -387,9 +390,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       auto issue_load = [&](int n, uint32_t s) {                                   // one elected lane
         int c0, c1;
         chunk_coord(n, c0, c1);
+#ifdef BIOM3_ABL_NO_RESID_LOAD
+        ptx::mbar_arrive(&rbar[s]);
+#else
         ptx::mbar_arrive_expect_tx(&rbar[s], RESID_SLOT_BYTES);
         ptx::tma_load_2d(slot_p + s * RESID_SLOT_BYTES, &tmap_c, &rbar[s], c0, c1);
         ptx::tma_load_2d(slot_p + s * RESID_SLOT_BYTES + 2048, &tmap_d, &rbar[s], c0, c1);
+#endif
       };
       if (ptx::elect_one()) {
         for (int n = 0; n < RS && n < n_chunks; ++n) issue_load(n, uint32_t(n));
@@ -397,6 +404,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
       int n = 0;                         // chunks consumed so far
       uint32_t slot = 0, sphase = 0;     // ring position of chunk n
+      int pend_n = -1;                   // chunk whose slot waits for its refill (BIOM3_RESID_REFILL_LATE)
+      uint32_t pend_slot = 0;
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const int tile = p.reverse ? num_tiles - 1 - t : t;
@@ -440,6 +449,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t sp = slot0 + slot * RESID_SLOT_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {                      // 8 columns per step: one 16-byte piece of the hi and of the lo row
+#if BIOM3_RESID_REFILL_LATE
+            // the previous chunk's slot is refilled half a chunk later, when its TMA store has long finished reading it
+            // (waiting right after the store stalled the warp for the store's issue-to-read latency every chunk)
+            if (i == 2 && pend_n >= 0) {
+              if (ptx::elect_one()) {
+                ptx::tma_store_wait_read();
+                issue_load(pend_n + RS, pend_slot);
+              }
+              pend_n = -1;
+            }
+#endif
             const uint32_t off = lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
             const uint4 h4 = ld_shared_v4(sp + off), l4 = ld_shared_v4(sp + 2048 + off);
             const uint4 a0 = ld_shared_v4(av + c * 128 + i * 32), a1 = ld_shared_v4(av + c * 128 + i * 32 + 16);
@@ -468,15 +488,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (ptx::elect_one()) {
             int c0, c1;
             chunk_coord(n, c0, c1);
+#ifndef BIOM3_ABL_NO_RESID_STORE
             ptx::tma_store_2d(&tmap_c, sp, c0, c1);
             ptx::tma_store_2d(&tmap_d, sp + 2048, c0, c1);
+#endif
             ptx::tma_store_commit();
+#if !BIOM3_RESID_REFILL_LATE
             if (n + RS < n_chunks) {
               ptx::tma_store_wait_read();
               issue_load(n + RS, slot);
             }
+#endif
           }
+#if BIOM3_RESID_REFILL_LATE
+          if (n + RS < n_chunks) { pend_n = n; pend_slot = slot; }
+#else
           __syncwarp();
+#endif
           if (++slot == RS) { slot = 0; sphase ^= 1; }
         }
         if (p.stats_out) {

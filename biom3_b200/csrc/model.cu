@@ -120,11 +120,14 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
 
 // Operand-ring depth.  Pair tiling, 256-wide tiles: 5 stages of 32 KB (3, 4 and 6 were measured: profiles/r01_ab_resid_ring_depth.jsonl;
 // a 6-stage QKV ring again in round 2: no change)
+#ifndef BIOM3_RESID_STAGES
+#define BIOM3_RESID_STAGES 3
+#endif
 template <int BN, bool CG2, int EPI>
 constexpr int gemm_stages() {
   // epilogue 6 spends 96 KB on its residual slots; it serves the K = 512 out-projection, whose mainloop is far from
   // binding (3 stages measured equal to 5 for that GEMM in round 1)
-  if (CG2 && BN == 256 && EPI == gemm::EPI_BIAS_RESID_SPLIT_TMA) return 3;
+  if (CG2 && BN == 256 && EPI == gemm::EPI_BIAS_RESID_SPLIT_TMA) return BIOM3_RESID_STAGES;
   if (CG2 && BN == 256) return 5;
   return CG2 ? 7 : (BN == 256 ? 3 : 5);
 }
