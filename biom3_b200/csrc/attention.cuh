@@ -608,7 +608,11 @@ local_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
         // instructions cost), four streams of 32-key blocks (+8 %); profiles/r02_attn_variants_v5.log.  Strict alternation of
         // the two warps' exponential loops through a pair of named barriers per quarter (bar.sync / bar.arrive token, the
         // MUFU-free part of one warp under the other's loop): +5 % (88.8 -> 93.7 us isolated, 1.56 -> 1.70 ms per step;
-        // profiles/r02_attn_pingpong_rejected.log): one warp alone does not keep the pipe full.
+        // profiles/r02_attn_pingpong_rejected.log): one warp alone does not keep the pipe full.  Dropping the block maximum
+        // after an item's first block (exponentials against the first block's reference, floating point keeps the rest):
+        // 77 us instead of 85 with no overflow check at all, but every correct form of the check (a vote on the block's row
+        // sum after this loop; a score bound from q / k row norms written by the QKV epilogue) gave the gain back in the
+        // step (profiles/r02_attn_nomax_variants.log).
         uint32_t pk[32];                                   // P (bf16 pairs) over the first 32 of the slot's 64 columns
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
