@@ -36,6 +36,10 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(ro
 //            context out of the loop (the kernel is issue bound)
 //   merge    the four partial (max, denominator, ctx) sets are combined in shared memory -> ctx^T bf16
 //   phase B  each warp softmaxes its q rows in registers (quad shuffles) and multiplies by ctx
+// Round 2 built the two phases as two kernels, twice, and kept this one (profiles/r02_linear_two_kernel.log): TMA-fed
+// context CTAs per 512 rows with global partials merged by the last CTA to arrive plus an output kernel per 128 rows
+// (37 + 19 us under ncu against 35 us for this kernel; step +0.25 ms); this kernel stopping after its merge plus an
+// output kernel per 512 rows with the row sums taken from the tensor cores (19.7 + 21.5 us; step +0.02 ms).
 // ------------------------------------------------------------------------------------------------
 constexpr int LIN_CH = 32;                         // rows per chunk
 constexpr float LIN_LAZY = 8.0f;                   // the column reference may trail the running maximum by e^8
