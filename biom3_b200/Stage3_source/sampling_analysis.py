@@ -182,10 +182,12 @@ def batch_generate_denoised_sampled(args, model, extract_digit_samples, extract_
         host = torch.empty((B, L), dtype=torch.uint8, pin_memory=True)
         host.copy_(tokens.to(torch.uint8), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        eng.check_inputs()
         return _FinalState(host.numpy(), steps), _LazyTimes(start, steps, B)
     host = torch.empty(traj.shape, dtype=torch.uint8, pin_memory=True)
     host.copy_(traj, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
+    eng.check_inputs()
     return _LazyStates(host.numpy()), _LazyTimes(start, steps, B)
 
 

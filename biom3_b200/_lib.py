@@ -15,7 +15,7 @@ SYMBOLS = [
     'biom3_forward', 'biom3_decode', 'biom3_sample_all', 'biom3_unmask', 'biom3_gemm_test',
     'biom3_profile_step', 'biom3_launches_per_step', 'biom3_debug_copy', 'biom3_facilitator', 'biom3_attention_test',
     'biom3_set_precision', 'biom3_random_paths', 'biom3_debug_noise', 'biom3_debug_trace',
-    'biom3_facilitator_create', 'biom3_facilitator_forward', 'biom3_facilitator_destroy',
+    'biom3_facilitator_create', 'biom3_facilitator_forward', 'biom3_facilitator_destroy', 'biom3_input_errors',
 ]
 
 # BIOM3_DTYPE_* of include/biom3_b200.h
@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     lib.biom3_facilitator_forward.restype = i32
     lib.biom3_facilitator_destroy.argtypes = [vp]
     lib.biom3_facilitator_destroy.restype = None
+    lib.biom3_input_errors.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.biom3_input_errors.restype = i32
     lib.biom3_launches_per_step.argtypes = [vp]
     lib.biom3_launches_per_step.restype = i32
     _lib = lib

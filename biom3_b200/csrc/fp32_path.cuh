@@ -175,6 +175,164 @@ local_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restr
     store_split4(dst + 4 * i, D, make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
 }
 
+// Windowed softmax attention of the fp32-class mode on the tensor cores (round 2; the CUDA-core kernel above is kept as the
+// unit-test reference).  Same input and output as local_attention_f32_kernel.  Every contraction is a three-product bf16
+// split on mma.sync m16n8k16 with fp32 accumulators: x = hi + lo, hi = bf16(x), lo = bf16(x - hi), and
+// a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (what the tcgen05 GEMMs of this mode do, Params::split3); the softmax itself
+// (scores, maxima, exponentials, sums, the output accumulator) stays fp32.
+//   grid (L/128, NL, B), 256 threads: one query window; warp w owns query rows 16 w .. 16 w + 15 (Q fragments in registers)
+//   per key window (w - 1, w, w + 1 where they exist): K and V converted to (hi, lo) bf16 tiles in shared memory (64-byte
+//   rows, 16-byte pieces XOR-swizzled for ldmatrix), S = Q K^T for the 128 keys (96 MMAs per warp), online softmax over the
+//   window, P split in registers (the accumulator fragments of two key tiles are the A fragment of one k-step), O += P V.
+__device__ __forceinline__ uint32_t f32_swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = ptx::pack_bf16x2(x, y);
+  lo = ptx::pack_bf16x2(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(256)
+local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
+                               float scale) {
+  __shared__ __align__(128) uint8_t sKh[WIN * 64], sKl[WIN * 64], sVh[WIN * 64], sVl[WIN * 64];
+  const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * DH;
+  const int nw = L / WIN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr float LOG2E = 1.4426950408889634f;
+  // Q fragments (A operand, rows g and g + 8 of this warp's 16 rows), scaled like the reference scales q before the dot
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const float* q0 = qkv + (size_t(b) * L + size_t(w) * WIN + warp * 16 + g) * 3 * D + h * DH + 2 * t;
+    const float* q1 = q0 + size_t(8) * 3 * D;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const float2 a0 = *reinterpret_cast<const float2*>(q0 + 16 * ks), a1 = *reinterpret_cast<const float2*>(q1 + 16 * ks);
+      const float2 a2 = *reinterpret_cast<const float2*>(q0 + 16 * ks + 8), a3 = *reinterpret_cast<const float2*>(q1 + 16 * ks + 8);
+      split_pack2(a0.x * scale, a0.y * scale, qh[ks][0], ql[ks][0]);
+      split_pack2(a1.x * scale, a1.y * scale, qh[ks][1], ql[ks][1]);
+      split_pack2(a2.x * scale, a2.y * scale, qh[ks][2], ql[ks][2]);
+      split_pack2(a3.x * scale, a3.y * scale, qh[ks][3], ql[ks][3]);
+    }
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mx[2] = {-INFINITY, -INFINITY}, den[2] = {0.f, 0.f};      // rows g, g + 8
+  const uint32_t kh0 = ptx::smem_u32(sKh), kl0 = ptx::smem_u32(sKl), vh0 = ptx::smem_u32(sVh), vl0 = ptx::smem_u32(sVl);
+  for (int kw = w - 1; kw <= w + 1; ++kw) {
+    if (kw < 0 || kw >= nw) continue;
+    __syncthreads();
+    // K, V of the key window: fp32 -> (hi, lo) bf16 tiles
+    for (int i = tid; i < WIN * DH / 4; i += 256) {
+      const int r = i >> 3, c4 = i & 7;                             // row, float4 index within the 32 features
+      const float* src = qkv + (size_t(b) * L + size_t(kw) * WIN + r) * 3 * D + h * DH + 4 * c4;
+      const float4 kk = *reinterpret_cast<const float4*>(src + D), vv = *reinterpret_cast<const float4*>(src + 2 * D);
+      const uint32_t off = f32_swz(r, c4 >> 1) + (c4 & 1) * 8;
+      uint32_t h0, l0, h1, l1;
+      split_pack2(kk.x, kk.y, h0, l0);
+      split_pack2(kk.z, kk.w, h1, l1);
+      *reinterpret_cast<uint2*>(sKh + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(sKl + off) = make_uint2(l0, l1);
+      split_pack2(vv.x, vv.y, h0, l0);
+      split_pack2(vv.z, vv.w, h1, l1);
+      *reinterpret_cast<uint2*>(sVh + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(sVl + off) = make_uint2(l0, l1);
+    }
+    __syncthreads();
+    // S = Q K^T: 16 key tiles of 8
+    float s[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      uint32_t bh[4], bl[4];                                         // b0, b1 of k-step 0, then of k-step 1
+      const uint32_t off = f32_swz(8 * j + (lane & 7), lane >> 3);
+      ptx::ldmatrix_x4(kh0 + off, bh[0], bh[1], bh[2], bh[3]);
+      ptx::ldmatrix_x4(kl0 + off, bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        ptx::mma_bf16_16816(s[j], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh[2 * ks], bh[2 * ks + 1]);
+        ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl[2 * ks], bl[2 * ks + 1]);
+        ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh[2 * ks], bh[2 * ks + 1]);
+      }
+    }
+    // online softmax over the window's 128 keys; rows g (c0, c1) and g + 8 (c2, c3)
+    float corr[2], ml2[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cm = fmaxf(cm, fmaxf(s[j][2 * hf], s[j][2 * hf + 1]));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+      const float nm = fmaxf(mx[hf], cm);
+      corr[hf] = exp2f((mx[hf] - nm) * LOG2E);                       // first window: exp(-inf) = 0
+      mx[hf] = nm;
+      ml2[hf] = nm * LOG2E;
+      den[hf] *= corr[hf];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    float ps[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      s[j][0] = exp2f(fmaf(s[j][0], LOG2E, -ml2[0]));
+      s[j][1] = exp2f(fmaf(s[j][1], LOG2E, -ml2[0]));
+      s[j][2] = exp2f(fmaf(s[j][2], LOG2E, -ml2[1]));
+      s[j][3] = exp2f(fmaf(s[j][3], LOG2E, -ml2[1]));
+      ps[0] += s[j][0] + s[j][1];
+      ps[1] += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float v = ps[hf];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      den[hf] += v;
+    }
+    // O += P V: key k-steps of 16 = two key tiles; V fragments through ldmatrix.trans (V is stored key-major)
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      uint32_t ph[4], pl[4];
+      split_pack2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split_pack2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int ep = 0; ep < 2; ++ep) {
+        uint32_t vh[4], vl[4];
+        const uint32_t off = f32_swz(kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4));
+        ptx::ldmatrix_x4_trans(vh0 + off, vh[0], vh[1], vh[2], vh[3]);
+        ptx::ldmatrix_x4_trans(vl0 + off, vl[0], vl[1], vl[2], vl[3]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          ptx::mma_bf16_16816(o[2 * ep + q], pl[0], pl[1], pl[2], pl[3], vh[2 * q], vh[2 * q + 1]);
+          ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vl[2 * q], vl[2 * q + 1]);
+          ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vh[2 * q], vh[2 * q + 1]);
+        }
+      }
+    }
+  }
+  const float inv0 = 1.0f / den[0], inv1 = 1.0f / den[1];
+  const size_t row0 = size_t(b) * L + size_t(w) * WIN + warp * 16 + g;
+  __nv_bfloat16* d0 = att2 + row0 * 2 * D + h * DH + 2 * t;
+  __nv_bfloat16* d1 = d0 + size_t(8) * 2 * D;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    uint32_t hi, lo;
+    split_pack2(o[nt][0] * inv0, o[nt][1] * inv0, hi, lo);
+    *reinterpret_cast<uint32_t*>(d0 + 8 * nt) = hi;
+    *reinterpret_cast<uint32_t*>(d0 + 8 * nt + D) = lo;
+    split_pack2(o[nt][2] * inv1, o[nt][3] * inv1, hi, lo);
+    *reinterpret_cast<uint32_t*>(d1 + 8 * nt) = hi;
+    *reinterpret_cast<uint32_t*>(d1 + 8 * nt + D) = lo;
+  }
+}
+
 // Linear attention, fp32, heads [NL, H): q = softmax_d(q) * dh^-0.5, k = softmax_n(k), ctx = k^T v, out = q ctx.
 // grid (H - NL, B), 256 threads.  Three passes over the head's [L][32] k / v / q columns (L2 resident).
 __global__ void __launch_bounds__(256)

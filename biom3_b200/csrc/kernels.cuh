@@ -532,25 +532,41 @@ unmask_scan_kernel(const long long* __restrict__ tok, const long long* __restric
   }
 }
 
-__global__ void inverse_path_kernel(const long long* __restrict__ path, int* __restrict__ inv, int B, int L) {
+__global__ void inverse_path_kernel(const long long* __restrict__ path, int* __restrict__ inv, int B, int L, int* err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * L) return;
   const int b = i / L;
   const long long t = path[i];
   if (t >= 0 && t < L) inv[size_t(b) * L + t] = i % L;
+  else atomicOr(err, 4);
 }
 
-__global__ void i64_to_u8_kernel(const long long* __restrict__ src, uint8_t* __restrict__ dst, int n) {
+// Inputs are range-checked where they enter the resident state, once per call: an out-of-range value sets a sticky bit in
+// `err` (1: token id outside [0, limit), 2: time index outside [0, limit), 4: path entry outside [0, limit)) and is
+// clamped so that nothing downstream indexes out of bounds; biom3_input_errors() reports and clears the bits.
+__global__ void i64_to_u8_kernel(const long long* __restrict__ src, uint8_t* __restrict__ dst, int n, int limit, int* err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = uint8_t(src[i]);
+  if (i >= n) return;
+  long long v = src[i];
+  if (v < 0 || v >= limit) {
+    atomicOr(err, 1);
+    v = v < 0 ? 0 : limit - 1;
+  }
+  dst[i] = uint8_t(v);
 }
 __global__ void u8_to_i64_kernel(const uint8_t* __restrict__ src, long long* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
-__global__ void i64_to_i32_kernel(const long long* __restrict__ src, int* __restrict__ dst, int n) {
+__global__ void i64_to_i32_kernel(const long long* __restrict__ src, int* __restrict__ dst, int n, int limit, int* err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = int(src[i]);
+  if (i >= n) return;
+  long long v = src[i];
+  if (v < 0 || v >= limit) {
+    atomicOr(err, 2);
+    v = v < 0 ? 0 : limit - 1;
+  }
+  dst[i] = int(v);
 }
 
 // Last kernel of a step: snapshot the state into the trajectory, then advance `step` exactly once

@@ -287,6 +287,7 @@ struct biom3_model {
   float *Yh = nullptr, *Ytmp = nullptr, *Y = nullptr, *cvec = nullptr;
   uint8_t* state = nullptr;
   int *inv_path = nullptr, *t_i32 = nullptr;
+  int* err_flags = nullptr;                     // sticky input-range bits set by the load kernels (biom3_input_errors)
   k::DecodeCtl* ctl = nullptr;
   unsigned long long* stamps = nullptr;         // [L][2] per-step %globaltimer stamps of the last decode (debug_copy "stamps")
   CUtensorMap tm_a{}, tm_att{}, tm_hid{};
@@ -870,6 +871,8 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(dev_alloc(m, &m->state, M));
   TRY(dev_alloc(m, &m->inv_path, M));
   TRY(dev_alloc(m, &m->t_i32, Bm));
+  TRY(dev_alloc(m, &m->err_flags, 1));
+  CU_OK(cudaMemset(m->err_flags, 0, sizeof(int)));
   TRY(dev_alloc(m, &m->ctl, 1));
   TRY(dev_alloc(m, &m->stamps, 2 * L));
   CU_OK(cudaMemset(m->stamps, 0, 2 * L * sizeof(unsigned long long)));
@@ -937,6 +940,15 @@ int biom3_finalize_weights(biom3_model* m) {
 
 int biom3_launches_per_step(const biom3_model* m) { return m ? m->launches_per_step : 0; }
 
+int biom3_input_errors(biom3_model* m, int* flags) {
+  if (!m || !flags || !m->finalized) return fail(BIOM3_ERR_INVALID, "bad input_errors argument");
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(flags, m->err_flags, sizeof(int), cudaMemcpyDeviceToHost));
+  if (*flags) CU_OK(cudaMemset(m->err_flags, 0, sizeof(int)));
+  return BIOM3_OK;
+}
+
 int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const float* y_c, int B, float* logits,
                   void* stream) {
   int r = check_ready(m, B);
@@ -945,8 +957,8 @@ int biom3_forward(biom3_model* m, const int64_t* x, const int64_t* t, const floa
   CU_OK(cudaSetDevice(m->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int L = m->cfg.seq_len, n = B * L;
-  k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(x), m->state, n);
-  k::i64_to_i32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), m->t_i32, B);
+  k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(x), m->state, n, m->cfg.num_classes, m->err_flags);
+  k::i64_to_i32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), m->t_i32, B, L, m->err_flags);
   run_y_mlp(m, y_c, B, st);
   if (!m->fwd_graph) {
     CU_OK(run_step(m, B, 0, m->t_i32, logits, false, false, st, nullptr, nullptr));
@@ -993,11 +1005,11 @@ int biom3_decode(biom3_model* m, const float* y_c, const int64_t* path, const in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n = B * L;
   if (state0)
-    k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(state0), m->state, n);
+    k::i64_to_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(state0), m->state, n, m->cfg.num_classes, m->err_flags);
   else
     CU_OK(cudaMemsetAsync(m->state, 0, n, st));
   CU_OK(cudaMemsetAsync(m->inv_path, 0, size_t(n) * sizeof(int), st));   // a non-permutation row falls back to location 0, like argmax of an all-false mask
-  k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L);
+  k::inverse_path_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(path), m->inv_path, B, L, m->err_flags);
   run_y_mlp(m, y_c, B, st);
   set_ctl_kernel<<<1, 1, 0, st>>>(m->ctl, start_step, start_step, noise, traj, seed,
                                   reinterpret_cast<const unsigned long long*>(group_seeds), m->stamps);

@@ -92,6 +92,17 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def check_inputs(self) -> None:
+        """Raises IndexError if a forward / decode since the last check was given a token id >= num_classes (what the
+        reference's nn.Embedding raises for), a time index outside [0, L) or a path entry outside [0, L).  The kernels
+        clamp such values instead of indexing out of bounds and record them; this call synchronises the device."""
+        flags = C.c_int32(0)
+        _lib.check(self.lib.biom3_input_errors(self.handle, C.byref(flags)))
+        if flags.value:
+            what = [msg for bit, msg in ((1, f'token id outside [0, {self.C})'), (2, f'time index outside [0, {self.L})'),
+                                         (4, f'sampling path entry outside [0, {self.L})')) if flags.value & bit]
+            raise IndexError('biom3_b200: ' + ', '.join(what))
+
     def forward(self, x: torch.Tensor, t: torch.Tensor, y_c: torch.Tensor) -> torch.Tensor:
         """x int [B, L], t int [B], y_c [B, E] -> logits fp32 [B, C, L] (reference layout)."""
         B = x.shape[0]

@@ -174,6 +174,14 @@ int biom3_debug_trace(int which, void* host_dst, int64_t nbytes);
  * captured step graph, or the full-row estimate before the first decode. */
 int biom3_launches_per_step(const biom3_model* m);
 
+/* Range check of the device inputs of biom3_forward / biom3_decode, done where they enter the resident state.  The
+ * reference raises for a token id >= num_classes (nn.Embedding, Stage3_source/cond_diff_transformer_layer.py:213) and
+ * indexes with whatever time / path values it is given; here an out-of-range value is clamped (no out-of-bounds access)
+ * and recorded.  Synchronises the device, writes the sticky bits to *flags and clears them:
+ * 1 = token id outside [0, num_classes), 2 = time index outside [0, diffusion_steps), 4 = path entry outside
+ * [0, diffusion_steps) (such an entry is skipped: a row that is not a permutation unmasks location 0 at the missing steps). */
+int biom3_input_errors(biom3_model* m, int* flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,37 @@ def test_forward_small_vs_oracle():
     assert rel_err(got, orc(x, t, z)) < LOGIT_TOL
 
 
+def test_out_of_range_inputs_are_flagged_not_dereferenced():
+    """The reference raises for a token id >= num_classes (nn.Embedding); here the load kernels clamp and record such a
+    value, and a time index / path entry outside [0, L) likewise; Engine.check_inputs() raises, once, and clean calls stay
+    clean and unchanged."""
+    B = 2
+    args, sd, eng, orc = make(SMALL, B)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 29, (B, 256), generator=g)
+    t = torch.tensor([3, 200])
+    z = synthetic.synthetic_z_c(B, 64, seed=6)
+    good = eng.forward(x.cuda(), t.cuda(), z.cuda()).cpu()
+    eng.check_inputs()
+    bad_x = x.clone()
+    bad_x[1, 17] = 29
+    eng.forward(bad_x.cuda(), t.cuda(), z.cuda())
+    with pytest.raises(IndexError, match='token id'):
+        eng.check_inputs()
+    eng.check_inputs()                                     # the bits are cleared by the report
+    eng.forward(x.cuda(), torch.tensor([3, 256]).cuda(), z.cuda())
+    with pytest.raises(IndexError, match='time index'):
+        eng.check_inputs()
+    path = synthetic.synthetic_paths(B, 256, seed=7)
+    bad_path = path.clone()
+    bad_path[0, 5] = 256
+    eng.decode(z.cuda(), bad_path.cuda(), num_steps=2, seed=1)
+    with pytest.raises(IndexError, match='path entry'):
+        eng.check_inputs()
+    assert torch.equal(eng.forward(x.cuda(), t.cuda(), z.cuda()).cpu(), good)
+    eng.check_inputs()
+
+
 @pytest.mark.parametrize('name', ['gpu_small_b3', 'gpu_resume_b2'])
 def test_forward_vs_reference_fixture(name):
     """Fixture logits come from the real reference forward (tests/golden/make_golden.py)."""
