@@ -182,8 +182,8 @@ local_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restr
 // (scores, maxima, exponentials, sums, the output accumulator) stays fp32.
 //   grid (L/128, NL, B), 256 threads: one query window; warp w owns query rows 16 w .. 16 w + 15 (Q fragments in registers)
 //   per key window (w - 1, w, w + 1 where they exist): K and V converted to (hi, lo) bf16 tiles in shared memory (64-byte
-//   rows, 16-byte pieces XOR-swizzled for ldmatrix), S = Q K^T for the 128 keys (96 MMAs per warp), online softmax over the
-//   window, P split in registers (the accumulator fragments of two key tiles are the A fragment of one k-step), O += P V.
+//   rows, 16-byte pieces XOR-swizzled for ldmatrix); per block of 64 keys S = Q K^T (48 MMAs per warp), online softmax,
+//   P split in registers (the accumulator fragments of two key tiles are the A fragment of one k-step), O += P V.
 __device__ __forceinline__ uint32_t f32_swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint
   lo = ptx::pack_bf16x2(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
                                float scale) {
   __shared__ __align__(128) uint8_t sKh[WIN * 64], sKl[WIN * 64], sVh[WIN * 64], sVl[WIN * 64];
@@ -241,78 +241,81 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
       *reinterpret_cast<uint2*>(sVl + off) = make_uint2(l0, l1);
     }
     __syncthreads();
-    // S = Q K^T: 16 key tiles of 8
-    float s[16][4];
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {                                  // two blocks of 64 keys (half the score registers of 128)
+      // S = Q K^T: 8 key tiles of 8
+      float s[8][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      uint32_t bh[4], bl[4];                                         // b0, b1 of k-step 0, then of k-step 1
-      const uint32_t off = f32_swz(8 * j + (lane & 7), lane >> 3);
-      ptx::ldmatrix_x4(kh0 + off, bh[0], bh[1], bh[2], bh[3]);
-      ptx::ldmatrix_x4(kl0 + off, bl[0], bl[1], bl[2], bl[3]);
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        uint32_t bh[4], bl[4];                                       // b0, b1 of k-step 0, then of k-step 1
+        const uint32_t off = f32_swz(64 * hb + 8 * j + (lane & 7), lane >> 3);
+        ptx::ldmatrix_x4(kh0 + off, bh[0], bh[1], bh[2], bh[3]);
+        ptx::ldmatrix_x4(kl0 + off, bl[0], bl[1], bl[2], bl[3]);
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        ptx::mma_bf16_16816(s[j], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh[2 * ks], bh[2 * ks + 1]);
-        ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl[2 * ks], bl[2 * ks + 1]);
-        ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh[2 * ks], bh[2 * ks + 1]);
+        for (int ks = 0; ks < 2; ++ks) {
+          ptx::mma_bf16_16816(s[j], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh[2 * ks], bh[2 * ks + 1]);
+          ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl[2 * ks], bl[2 * ks + 1]);
+          ptx::mma_bf16_16816(s[j], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh[2 * ks], bh[2 * ks + 1]);
+        }
       }
-    }
-    // online softmax over the window's 128 keys; rows g (c0, c1) and g + 8 (c2, c3)
-    float corr[2], ml2[2];
+      // online softmax over the block's 64 keys; rows g (c0, c1) and g + 8 (c2, c3)
+      float corr[2], ml2[2];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      float cm = -INFINITY;
+      for (int hf = 0; hf < 2; ++hf) {
+        float cm = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) cm = fmaxf(cm, fmaxf(s[j][2 * hf], s[j][2 * hf + 1]));
-      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-      const float nm = fmaxf(mx[hf], cm);
-      corr[hf] = exp2f((mx[hf] - nm) * LOG2E);                       // first window: exp(-inf) = 0
-      mx[hf] = nm;
-      ml2[hf] = nm * LOG2E;
-      den[hf] *= corr[hf];
-    }
+        for (int j = 0; j < 8; ++j) cm = fmaxf(cm, fmaxf(s[j][2 * hf], s[j][2 * hf + 1]));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        const float nm = fmaxf(mx[hf], cm);
+        corr[hf] = exp2f((mx[hf] - nm) * LOG2E);                     // first block: exp(-inf) = 0
+        mx[hf] = nm;
+        ml2[hf] = nm * LOG2E;
+        den[hf] *= corr[hf];
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[i][0] *= corr[0]; o[i][1] *= corr[0];
-      o[i][2] *= corr[1]; o[i][3] *= corr[1];
-    }
-    float ps[2] = {0.f, 0.f};
+      for (int i = 0; i < 4; ++i) {
+        o[i][0] *= corr[0]; o[i][1] *= corr[0];
+        o[i][2] *= corr[1]; o[i][3] *= corr[1];
+      }
+      float ps[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      s[j][0] = exp2f(fmaf(s[j][0], LOG2E, -ml2[0]));
-      s[j][1] = exp2f(fmaf(s[j][1], LOG2E, -ml2[0]));
-      s[j][2] = exp2f(fmaf(s[j][2], LOG2E, -ml2[1]));
-      s[j][3] = exp2f(fmaf(s[j][3], LOG2E, -ml2[1]));
-      ps[0] += s[j][0] + s[j][1];
-      ps[1] += s[j][2] + s[j][3];
-    }
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = exp2f(fmaf(s[j][0], LOG2E, -ml2[0]));
+        s[j][1] = exp2f(fmaf(s[j][1], LOG2E, -ml2[0]));
+        s[j][2] = exp2f(fmaf(s[j][2], LOG2E, -ml2[1]));
+        s[j][3] = exp2f(fmaf(s[j][3], LOG2E, -ml2[1]));
+        ps[0] += s[j][0] + s[j][1];
+        ps[1] += s[j][2] + s[j][3];
+      }
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      float v = ps[hf];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      den[hf] += v;
-    }
-    // O += P V: key k-steps of 16 = two key tiles; V fragments through ldmatrix.trans (V is stored key-major)
+      for (int hf = 0; hf < 2; ++hf) {
+        float v = ps[hf];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        den[hf] += v;
+      }
+      // O += P V: key k-steps of 16 = two key tiles; V fragments through ldmatrix.trans (V is stored key-major)
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      uint32_t ph[4], pl[4];
-      split_pack2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
-      split_pack2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
-      split_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
-      split_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ph[4], pl[4];
+        split_pack2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+        split_pack2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+        split_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+        split_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
-      for (int ep = 0; ep < 2; ++ep) {
-        uint32_t vh[4], vl[4];
-        const uint32_t off = f32_swz(kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4));
-        ptx::ldmatrix_x4_trans(vh0 + off, vh[0], vh[1], vh[2], vh[3]);
-        ptx::ldmatrix_x4_trans(vl0 + off, vl[0], vl[1], vl[2], vl[3]);
+        for (int ep = 0; ep < 2; ++ep) {
+          uint32_t vh[4], vl[4];
+          const uint32_t off = f32_swz(64 * hb + kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4));
+          ptx::ldmatrix_x4_trans(vh0 + off, vh[0], vh[1], vh[2], vh[3]);
+          ptx::ldmatrix_x4_trans(vl0 + off, vl[0], vl[1], vl[2], vl[3]);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          ptx::mma_bf16_16816(o[2 * ep + q], pl[0], pl[1], pl[2], pl[3], vh[2 * q], vh[2 * q + 1]);
-          ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vl[2 * q], vl[2 * q + 1]);
-          ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vh[2 * q], vh[2 * q + 1]);
+          for (int q = 0; q < 2; ++q) {
+            ptx::mma_bf16_16816(o[2 * ep + q], pl[0], pl[1], pl[2], pl[3], vh[2 * q], vh[2 * q + 1]);
+            ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vl[2 * q], vl[2 * q + 1]);
+            ptx::mma_bf16_16816(o[2 * ep + q], ph[0], ph[1], ph[2], ph[3], vh[2 * q], vh[2 * q + 1]);
+          }
         }
       }
     }

@@ -48,7 +48,7 @@ constexpr int CV_TOTAL = 16384;   // the two per-column epilogue vectors of ever
 #define BIOM3_QKV_EPI_WARPS 8
 #endif
 __host__ __device__ constexpr int epi_warps(int epi) {
-  return (epi >= 3 && epi <= 6) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);
+  return (epi >= 3 && epi <= 6) ? 8 : (epi == 1 ? BIOM3_QKV_EPI_WARPS : BIOM3_BF16_EPI_WARPS);   // 7: like 2
 }
 constexpr uint32_t EPI_WARP0 = 2;     // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
 
@@ -68,7 +68,11 @@ enum Epi : int {
                             // Epilogue 5 keeps one chunk of residual in registers (16 x 16-byte loads per lane), which with the
                             // ~1.7 us loaded HBM latency of this kernel pinned it at 4.4 TB/s (ncu: 45 % of the stall samples on
                             // the first use of the prefetched registers).
+  EPI_BIAS_GELU_SPLIT = 7,  // fp32-class mode FF1: gelu_erf(acc + bias[n]) with the exact erf, stored as the [hi | lo] bf16 split
+                            // the next split3 GEMM reads: hi at column n, lo at column N + n of a [M][2N] matrix (tmap_c).
+                            // Replaces an fp32 store + a separate bias / GELU / split pass (1 GB of HBM traffic per layer).
 };
+// (7, below the enum: fp32-class mode)
 #ifndef BIOM3_RESID_SLOTS
 #define BIOM3_RESID_SLOTS 3
 #endif
@@ -123,10 +127,10 @@ inline void fill_shifts(Params& p, int bn) {
 // Staging and vector space follow the epilogue (EPI), so that the kernels that need less of them can afford a deeper ring.
 __host__ __device__ constexpr bool epi_is_f32(int epi) { return epi >= 3 && epi <= 5; }
 __host__ __device__ constexpr int epi_stg_bytes(int epi) {
-  return epi == 6 ? epi_warps(epi) * RESID_SLOTS * RESID_SLOT_BYTES : epi_warps(epi) * (epi_is_f32(epi) ? 4096 : 2048);
+  return epi == 6 ? epi_warps(epi) * RESID_SLOTS * RESID_SLOT_BYTES : epi_warps(epi) * ((epi_is_f32(epi) || epi == 7) ? 4096 : 2048);
 }
 // 1: the scale / shift vectors of the bf16 epilogues; 6: bias (+ conditioning) of the warp's 128 columns, double buffered
-__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2) ? CV_TOTAL : (epi == 6 ? 8 * 1024 : 0); }
+__host__ __device__ constexpr int epi_cv_bytes(int epi) { return (epi == 1 || epi == 2 || epi == 7) ? CV_TOTAL : (epi == 6 ? 8 * 1024 : 0); }
 
 template <int BN, int STAGES, bool CG2, int EPI>
 struct SmemLayout {
@@ -675,7 +679,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // Per-column epilogue vectors (x = acc * rstd + (-mean * rstd) * cs[n] + ct[n]; cs/ct = folded-LayerNorm
         // s/t, or 0/bias) are staged once per tile in warp-private smem BEFORE the accumulator wait: with ~225 KB of
         // the SM's 256 KB carved out as shared memory there is next to no L1 left for them.
-        constexpr bool kHasVec = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR);
+        constexpr bool kHasVec = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_HEADMAJOR || EPI == EPI_BIAS_GELU_SPLIT);
         float mean = 0.f, rstd = 1.f;
         const bool use_vec = kHasVec && (p.ln_stats != nullptr || p.bias != nullptr);
         const uint32_t cvs = cvs0 + (pipe ? (it & 1) * CV_BYTES : 0);
@@ -760,6 +764,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
           }
+          if constexpr (EPI == EPI_BIAS_GELU_SPLIT) {
+            // exact erf form (torch's default nn.GELU), then the second staging block takes the lo halves
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752440f));
+            if (lane == 0) ptx::tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hw[e] = ptx::pack_bf16x2(v[8 * i + 2 * e], v[8 * i + 2 * e + 1]);
+                lw[e] = ptx::pack_bf16x2(v[8 * i + 2 * e] - __uint_as_float(hw[e] << 16), v[8 * i + 2 * e + 1] - __uint_as_float(hw[e] & 0xffff0000u));
+              }
+              const uint32_t off = lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
+              st_shared_v4(stg + off, hw[0], hw[1], hw[2], hw[3]);
+              st_shared_v4(stg + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (ptx::elect_one()) {
+              ptx::tma_store_2d(&tmap_c, stg, nbase + c * 32, rbase);
+              ptx::tma_store_2d(&tmap_c, stg + 2048, p.N + nbase + c * 32, rbase);
+              ptx::tma_store_commit();
+            }
+            __syncwarp();
+          } else {
           // the previous chunk's TMA store must have finished READING the staging block before it is rewritten
           if (lane == 0) ptx::tma_store_wait_read();
           __syncwarp();
@@ -778,6 +809,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tma_store_commit();
           }
           __syncwarp();
+          }
         }
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][3] = clock64();
       }

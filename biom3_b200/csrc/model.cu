@@ -128,6 +128,7 @@ constexpr int gemm_stages() {
   // epilogue 6 spends 96 KB on its residual slots; it serves the K = 512 out-projection, whose mainloop is far from
   // binding (3 stages measured equal to 5 for that GEMM in round 1)
   if (CG2 && BN == 256 && EPI == gemm::EPI_BIAS_RESID_SPLIT_TMA) return BIOM3_RESID_STAGES;
+  if (CG2 && BN == 256 && EPI == gemm::EPI_BIAS_GELU_SPLIT) return 4;      // two staging blocks per epilogue warp
   if (CG2 && BN == 256) return 5;
   return CG2 ? 7 : (BN == 256 ? 3 : 5);
 }
@@ -193,6 +194,7 @@ cudaError_t init_kernel_attributes_impl() {
   SET_GEMM(gemm::EPI_STORE_BF16)
   SET_GEMM(gemm::EPI_STORE_F32)
   SET_GEMM1(256, gemm::EPI_BIAS_RESID_SPLIT_TMA, true)      // pair tiling only
+  SET_GEMM(gemm::EPI_BIAS_GELU_SPLIT)
 #undef SET_GEMM1
 #undef SET_GEMM
   e = cudaFuncSetAttribute(attn::local_attention_kernel<attn::LOCAL_NST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -324,6 +326,9 @@ struct biom3_model {
   int launches_per_step = 0;
   // fp32-class mode (biom3_set_precision(m, 1) before finalize): split [hi | lo] weights and fp32 activations
   int precision = 0;
+  bool f32_fused_gelu = true;                   // BIOM3_F32_FUSED_GELU=0: fp32 hidden activation + a separate bias / GELU / split pass
+  CUtensorMap tm_st_hid2{};                     // TMA-store map of hid2 [M][8D] (gemm::EPI_BIAS_GELU_SPLIT)
+  bool f32_attn_mma = true;                     // BIOM3_F32_ATTN_MMA=0: the CUDA-core fp32 attention kernels of round 1
   bf16 *Wqkv2 = nullptr, *Wo2 = nullptr, *W1s = nullptr, *W2s = nullptr;       // [N][2K] per layer, stacked
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // [depth][D]
   bf16 *a2 = nullptr, *hid2 = nullptr;                                            // [M][2D], [M][8D]
@@ -506,7 +511,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_QKV, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_wqkv2[iw], m->tm_st_hid, p, m->num_sms, st));
       if (H - NL > 0)
         LAUNCH(C_LINEAR, f32p::linear_attention_f32_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
-      if (NL > 0)
+      if (NL > 0 && m->f32_attn_mma)
+        LAUNCH(C_LOCAL, f32p::local_attention_f32_mma_kernel<<<dim3(L / attn::WIN, NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
+      else if (NL > 0)
         LAUNCH(C_LOCAL, f32p::local_attention_f32_kernel<<<dim3(L / attn::WIN, NL, B), 128, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
       gemm::Params r{};
       r.L = L; r.H = H; r.Bsz = B; r.M = M; r.split3 = 1;
@@ -515,8 +522,15 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       LAUNCH(C_LN, f32p::ln_split_kernel<<<row_blocks, 256, 0, st>>>(m->u, m->ln2_g + size_t(j) * D, m->ln2_b + size_t(j) * D,
                                                                     m->a2, M, D));
       p.N = 4 * D; p.K = D; p.b_row_offset = j * 4 * D; p.out = m->hid32;
-      LAUNCH(C_FF1, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_w1s[iw], m->tm_st_hid, p, m->num_sms, st));
-      LAUNCH(C_OTHER, f32p::bias_gelu_split_kernel<<<ew_blocks, 256, 0, st>>>(m->hid32, m->b1 + size_t(j) * 4 * D, m->hid2, size_t(M), 4 * D));
+      if (m->f32_fused_gelu) {
+        // bias + exact-erf GELU + [hi | lo] split in the GEMM epilogue: no fp32 hidden activation in HBM
+        p.bias = m->b1 + size_t(j) * 4 * D;
+        LAUNCH(C_FF1, launch_gemm<gemm::EPI_BIAS_GELU_SPLIT>(m->bn_wide, pw, m->tm_a2, m->tm_w1s[iw], m->tm_st_hid2, p, m->num_sms, st));
+        p.bias = nullptr;
+      } else {
+        LAUNCH(C_FF1, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_w1s[iw], m->tm_st_hid, p, m->num_sms, st));
+        LAUNCH(C_OTHER, f32p::bias_gelu_split_kernel<<<ew_blocks, 256, 0, st>>>(m->hid32, m->b1 + size_t(j) * 4 * D, m->hid2, size_t(M), 4 * D));
+      }
       r.N = D; r.K = 4 * D; r.b_row_offset = j * D; r.bias = m->b2 + size_t(j) * D;
       r.cond = (j + 1 < depth) ? m->cvec + size_t(j + 1) * D : nullptr;
       r.cond_stride = JD;
@@ -664,6 +678,8 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_RESID_TMA")) m->resid_tma = atoi(e);
+  if (const char* e = getenv("BIOM3_F32_ATTN_MMA")) m->f32_attn_mma = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_F32_FUSED_GELU")) m->f32_fused_gelu = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
@@ -886,6 +902,7 @@ int biom3_finalize_weights(biom3_model* m) {
     TRY(dev_alloc(m, &m->hid32, M * 4 * D));
     TRY(make_tmap(&m->tm_a2, m->a2, M, 2 * D, 128));
     TRY(make_tmap(&m->tm_hid2, m->hid2, M, 8 * D, 128));
+    TRY(make_store_tmap(&m->tm_st_hid2, m->hid2, M, 8 * D));
     for (int i = 0; i < 2; ++i) {
       const uint32_t box = i ? 256 : 128;
       TRY(make_tmap(&m->tm_wqkv2[i], m->Wqkv2, depth * 3 * D, 2 * D, box));
@@ -933,7 +950,7 @@ int biom3_finalize_weights(biom3_model* m) {
   }
 #undef TRY
   m->finalized = true;
-  m->launches_per_step = 2 + int(depth) * (m->precision == 1 ? 9 : 6) + 2 - (c.local_heads == 0 ? int(depth) : 0) -
+  m->launches_per_step = 2 + int(depth) * (m->precision == 1 ? (m->f32_fused_gelu ? 8 : 9) : 6) + 2 - (c.local_heads == 0 ? int(depth) : 0) -
                          (c.heads == c.local_heads ? int(depth) : 0);
   return BIOM3_OK;
 }
@@ -1316,6 +1333,13 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
       p.out_bf16 = reinterpret_cast<bf16*>(out);
       p.out = reinterpret_cast<bf16*>(out) + size_t(M) * N;
       launch_gemm<gemm::EPI_BIAS_RESID_SPLIT>(block_n, pair != 0, ta, tb, tc, p, sms, st); break;
+    case gemm::EPI_BIAS_GELU_SPLIT: {       // out = bf16 [M][2N]: gelu_erf(A W^T + bias) as hi (columns [0, N)) and lo (columns [N, 2N))
+      if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
+      CUtensorMap ts;
+      if ((r = make_store_tmap(&ts, out, M, 2 * uint64_t(N)))) return r;
+      launch_gemm<gemm::EPI_BIAS_GELU_SPLIT>(block_n, pair != 0, ta, tb, ts, p, sms, st);
+      break;
+    }
     case gemm::EPI_BIAS_RESID_SPLIT_TMA: {  // same planes, TMA-fed residual ring (pair tiling only)
       if (!bias) return fail(BIOM3_ERR_INVALID, "bias required");
       if (!pair) return fail(BIOM3_ERR_INVALID, "epilogue 6 needs pair tiling");

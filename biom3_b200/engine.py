@@ -234,7 +234,7 @@ def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ep
     if out is None:
         if epi in (5, 6):
             raise ValueError('epilogues 5 and 6 update `out` in place: bf16 [2, M, N] (hi plane, lo plane)')
-        out = torch.empty(M, N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
+        out = torch.empty(M, 2 * N if epi == 7 else N, device=A.device, dtype=torch.float32 if epi in (3, 4) else torch.bfloat16)
     with torch.cuda.device(A.device):
         _lib.check(lib.biom3_gemm_test(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, epi, block_n, int(pair) | (2 if split3 else 0),
                                        C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))

@@ -112,7 +112,8 @@ int biom3_unmask(const int64_t* tok, const int64_t* path, int64_t* state, int B,
  * A device bf16 [M][K]; W device bf16 [N][K]; epi: 0 bf16 out, 2 bias+gelu bf16 out,
  * 3 fp32 in-place residual (+bias), 4 fp32 out, 5 in-place residual stored split (out = bf16 [2][M][N]: hi plane
  * bf16(R), lo plane bf16(R - hi)), 6 the same update through TMA-fed residual slots (pair tiling only; bit-identical
- * to 5).  block_n: 256.  pair bit 0: CTA-pair (cta_group::2) tiling, 256 x 256 tiles
+ * to 5), 7 gelu_erf(A W^T + bias) (exact erf) stored as the [hi | lo] bf16 split of the fp32-class mode (out = bf16
+ * [M][2N]).  block_n: 256.  pair bit 0: CTA-pair (cta_group::2) tiling, 256 x 256 tiles
  * (needs M % 256 == 0; otherwise 128 x 256 tiles, one CTA each); pair bit 1: fp32-class K schedule, A and W are
  * [hi | lo] bf16 halves of width 2K and the result is hi.hi + hi.lo + lo.hi.  With BIOM3_GEMM_TRACE=1 in the
  * environment CTA 0 records its clock64 timeline (biom3_debug_trace(1, ...)). */

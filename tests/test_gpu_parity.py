@@ -529,6 +529,24 @@ def test_gemm_split3_matches_fp32_product():
         assert rel_err(out, ref) < 2e-5, (bn, pair)
 
 
+@pytest.mark.parametrize('pair', [False, True])
+def test_gemm_gelu_split_epilogue(pair):
+    """Epilogue 7 (fp32-class FF1): bias + exact-erf GELU on the fp32 accumulator, stored as hi | lo bf16 halves whose sum
+    carries 16 significant bits."""
+    from biom3_b200 import engine
+    g = torch.Generator().manual_seed(13)
+    M, N, K = 1024, 512, 256
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = torch.nn.functional.gelu(A.float() @ W.float().t() + bias)
+    out = engine.gemm_test(A, W, bias, 7, 256, pair=pair)
+    assert out.shape == (M, 2 * N)
+    got = out[:, :N].float() + out[:, N:].float()
+    assert rel_err(got, ref) < 2e-5
+    assert torch.equal(out[:, :N], got.bfloat16()) or rel_err(out[:, :N].float(), ref) < 4e-3
+
+
 @pytest.mark.parametrize('name', ['gpu_small_b3', 'gpu_resume_b2', 'full_forward_b2'])
 def test_fp32_mode_forward_vs_reference_fixture(name):
     from biom3_b200.engine import Engine
