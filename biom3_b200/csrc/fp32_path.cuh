@@ -336,6 +336,247 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
   }
 }
 
+// Linear attention of the fp32-class mode on the tensor cores (round 2; the CUDA-core kernel below is kept as the unit-test
+// reference).  Same input and output as linear_attention_f32_kernel, grid (H - NL, B), 256 threads, LINF_SMEM_BYTES of
+// dynamic shared memory.  The softmaxes are fp32 and thread-per-token (each thread owns one token's 32 features); the two
+// contractions (exp(k)^T v over the tokens, softmax(q) ctx over the features) are three-product bf16 splits on mma.sync
+// with fp32 accumulators, like local_attention_f32_mma_kernel.
+//   pass 1   per-feature maximum of k over the sequence (lane = feature, warps stride over the tokens)
+//   pass 2   256 tokens at a time: thread = token computes exp(k - max) and splits it and v into (hi, lo) bf16 rows of its
+//            warp's 32-row slice of the tiles; the warp then multiplies its own 32 tokens in (only __syncwarp between the
+//            two), denominators through the same A fragments against a ones operand; partial ctx per warp -> reduced in
+//            shared memory -> ctx^T / Z * q_scale as (hi, lo) bf16
+//   pass 3   thread = token softmaxes its q row, splits it into the warp's tile slice; the warp multiplies by ctx
+constexpr int LINF_TOK = 256;
+constexpr int LINF_SMEM_BYTES = 4 * LINF_TOK * 64 + 128;
+constexpr uint32_t ONES_BF16X2 = 0x3F803F80u;
+
+__global__ void __launch_bounds__(256)
+linear_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
+                                int NL, float q_scale) {
+  extern __shared__ uint8_t linf_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(linf_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sEh = tiles;                           // exp(k) (pass 2) / softmax(q) (pass 3), hi; [256 tokens][64 bytes], swizzled
+  uint8_t* sEl = tiles + LINF_TOK * 64;
+  uint8_t* sVh = tiles + 2 * LINF_TOK * 64;
+  uint8_t* sVl = tiles + 3 * LINF_TOK * 64;
+  __shared__ float red[8][DH];
+  __shared__ float kmax[DH], zsum[DH];
+  __shared__ __align__(128) uint8_t sCh[DH * 64], sCl[DH * 64];   // ctx^T [e][d] bf16 (hi, lo), swizzled rows
+  const int h = NL + blockIdx.x, b = blockIdx.y;
+  const int D = H * DH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float* base = qkv + size_t(b) * L * 3 * D + h * DH;       // + n*3D (+ D for k, + 2D for v)
+  // pass 1
+  {
+    float m = -INFINITY;
+    for (int n = warp; n < L; n += 8) m = fmaxf(m, base[size_t(n) * 3 * D + D + lane]);
+    red[warp][lane] = m;
+    __syncthreads();
+    if (warp == 0) {
+      float mm = red[0][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i][lane]);
+      kmax[lane] = mm * LOG2E;
+    }
+    __syncthreads();
+  }
+  const int r0 = warp * 32;                       // this warp's rows of the tiles
+  const uint32_t eh0 = ptx::smem_u32(sEh), el0 = ptx::smem_u32(sEl), vh0 = ptx::smem_u32(sVh), vl0 = ptx::smem_u32(sVl);
+  // pass 2
+  float acc[2][4][4], accd[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      accd[i][j] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+    }
+  for (int n0 = 0; n0 < L; n0 += LINF_TOK) {
+    const int n = n0 + tid;
+    const bool live = n < L;
+    const float* row = base + size_t(live ? n : 0) * 3 * D;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                 // 8 features per step: one 16-byte piece of each bf16 row
+      float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, v0 = k0, v1 = k0;
+      float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        k0 = *reinterpret_cast<const float4*>(row + D + 8 * c);
+        k1 = *reinterpret_cast<const float4*>(row + D + 8 * c + 4);
+        v0 = *reinterpret_cast<const float4*>(row + 2 * D + 8 * c);
+        v1 = *reinterpret_cast<const float4*>(row + 2 * D + 8 * c + 4);
+        const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = exp2f(fmaf(kk[i], LOG2E, -kmax[8 * c + i]));
+      }
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_pack2(e[2 * i], e[2 * i + 1], hw[i], lw[i]);
+      const uint32_t off = f32_swz(tid, c);
+      *reinterpret_cast<uint4*>(sEh + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(sEl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      split_pack2(v0.x, v0.y, hw[0], lw[0]);
+      split_pack2(v0.z, v0.w, hw[1], lw[1]);
+      split_pack2(v1.x, v1.y, hw[2], lw[2]);
+      split_pack2(v1.z, v1.w, hw[3], lw[3]);
+      *reinterpret_cast<uint4*>(sVh + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(sVl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    __syncwarp();
+    uint32_t ah[2][2][4], al[2][2][4];             // [k-step][m-tile(d)][a0..a3]: exp(k)^T fragments
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t off = f32_swz(r0 + ks * 16 + (lane & 7) + 8 * (lane >> 4), 2 * mt + ((lane >> 3) & 1));
+        ptx::ldmatrix_x4_trans(eh0 + off, ah[ks][mt][0], ah[ks][mt][1], ah[ks][mt][2], ah[ks][mt][3]);
+        ptx::ldmatrix_x4_trans(el0 + off, al[ks][mt][0], al[ks][mt][1], al[ks][mt][2], al[ks][mt][3]);
+      }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int ep = 0; ep < 2; ++ep) {
+        uint32_t vh[4], vl[4];
+        const uint32_t off = f32_swz(r0 + ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ep + (lane >> 4));
+        ptx::ldmatrix_x4_trans(vh0 + off, vh[0], vh[1], vh[2], vh[3]);
+        ptx::ldmatrix_x4_trans(vl0 + off, vl[0], vl[1], vl[2], vl[3]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            ptx::mma_bf16_16816(acc[mt][2 * ep + q], al[ks][mt][0], al[ks][mt][1], al[ks][mt][2], al[ks][mt][3], vh[2 * q], vh[2 * q + 1]);
+            ptx::mma_bf16_16816(acc[mt][2 * ep + q], ah[ks][mt][0], ah[ks][mt][1], ah[ks][mt][2], ah[ks][mt][3], vl[2 * q], vl[2 * q + 1]);
+            ptx::mma_bf16_16816(acc[mt][2 * ep + q], ah[ks][mt][0], ah[ks][mt][1], ah[ks][mt][2], ah[ks][mt][3], vh[2 * q], vh[2 * q + 1]);
+          }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        ptx::mma_bf16_16816(accd[mt], al[ks][mt][0], al[ks][mt][1], al[ks][mt][2], al[ks][mt][3], ONES_BF16X2, ONES_BF16X2);
+        ptx::mma_bf16_16816(accd[mt], ah[ks][mt][0], ah[ks][mt][1], ah[ks][mt][2], ah[ks][mt][3], ONES_BF16X2, ONES_BF16X2);
+      }
+    }
+    __syncwarp();
+  }
+  // per-warp partials -> shared (aliasing the tiles), reduced over the 8 warps
+  __syncthreads();
+  float* part = reinterpret_cast<float*>(tiles);                 // [8][32 d][32 e]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int d = 16 * mt + 8 * hf + g;
+      if (t == 0) red[warp][d] = accd[mt][2 * hf];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* dst = part + (size_t(warp) * DH + d) * DH + 8 * nt + 2 * t;
+        dst[0] = acc[mt][nt][2 * hf];
+        dst[1] = acc[mt][nt][2 * hf + 1];
+      }
+    }
+  __syncthreads();
+  if (tid < DH) {
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z += red[i][tid];
+    zsum[tid] = q_scale / z;
+  }
+  __syncthreads();
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sum += part[(size_t(wv) * DH + d) * DH + e];
+    sum *= zsum[d];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
+    const uint32_t off = f32_swz(e, d >> 3) + (d & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(sCh + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(sCl + off) = __float2bfloat16_rn(sum - __bfloat162float(hi));
+  }
+  __syncthreads();
+  // pass 3
+  uint32_t ch[4][4], cl[4][4];                     // ctx as B fragments: [n-tile(e)][b0 ks0, b1 ks0, b0 ks1, b1 ks1]
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const uint32_t off = f32_swz(8 * nt + (lane & 7), lane >> 3);
+    ptx::ldmatrix_x4(ptx::smem_u32(sCh) + off, ch[nt][0], ch[nt][1], ch[nt][2], ch[nt][3]);
+    ptx::ldmatrix_x4(ptx::smem_u32(sCl) + off, cl[nt][0], cl[nt][1], cl[nt][2], cl[nt][3]);
+  }
+  for (int n0 = 0; n0 < L; n0 += LINF_TOK) {
+    const int n = n0 + tid;
+    const bool live = n < L;
+    const float* row = base + size_t(live ? n : 0) * 3 * D;
+    float qv[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 x = live ? *reinterpret_cast<const float4*>(row + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qv[4 * c] = x.x; qv[4 * c + 1] = x.y; qv[4 * c + 2] = x.z; qv[4 * c + 3] = x.w;
+    }
+    float qm = qv[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) qm = fmaxf(qm, qv[i]);
+    float qs = 0.f;
+    const float qml = qm * LOG2E;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      qv[i] = exp2f(fmaf(qv[i], LOG2E, -qml));
+      qs += qv[i];
+    }
+    const float qi = 1.0f / qs;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_pack2(qv[8 * c + 2 * i] * qi, qv[8 * c + 2 * i + 1] * qi, hw[i], lw[i]);
+      const uint32_t off = f32_swz(tid, c);
+      *reinterpret_cast<uint4*>(sEh + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(sEl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {               // 16 tokens each
+      uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t off = f32_swz(r0 + mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4));
+        ptx::ldmatrix_x4(eh0 + off, qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3]);
+        ptx::ldmatrix_x4(el0 + off, ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
+      }
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          ptx::mma_bf16_16816(o[nt], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], ch[nt][2 * ks], ch[nt][2 * ks + 1]);
+          ptx::mma_bf16_16816(o[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], cl[nt][2 * ks], cl[nt][2 * ks + 1]);
+          ptx::mma_bf16_16816(o[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], ch[nt][2 * ks], ch[nt][2 * ks + 1]);
+        }
+      }
+      const int tok0 = n0 + r0 + mt * 16 + g;
+      __nv_bfloat16* d0 = att2 + (size_t(b) * L + tok0) * 2 * D + h * DH + 2 * t;
+      __nv_bfloat16* d1 = d0 + size_t(8) * 2 * D;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t hi, lo;
+        if (tok0 < L) {
+          split_pack2(o[nt][0], o[nt][1], hi, lo);
+          *reinterpret_cast<uint32_t*>(d0 + 8 * nt) = hi;
+          *reinterpret_cast<uint32_t*>(d0 + 8 * nt + D) = lo;
+        }
+        if (tok0 + 8 < L) {
+          split_pack2(o[nt][2], o[nt][3], hi, lo);
+          *reinterpret_cast<uint32_t*>(d1 + 8 * nt) = hi;
+          *reinterpret_cast<uint32_t*>(d1 + 8 * nt + D) = lo;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Linear attention, fp32, heads [NL, H): q = softmax_d(q) * dh^-0.5, k = softmax_n(k), ctx = k^T v, out = q ctx.
 // grid (H - NL, B), 256 threads.  Three passes over the head's [L][32] k / v / q columns (L2 resident).
 __global__ void __launch_bounds__(256)

@@ -206,6 +206,8 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(f32p::linear_attention_f32_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LINF_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::sample_all_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -509,7 +511,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
                                                                     m->a2, M, D));
       p.N = 3 * D; p.K = D; p.b_row_offset = j * 3 * D; p.out = m->qkv32; p.reverse = 0;
       LAUNCH(C_QKV, launch_gemm<gemm::EPI_STORE_F32>(m->bn_wide, pw, m->tm_a2, m->tm_wqkv2[iw], m->tm_st_hid, p, m->num_sms, st));
-      if (H - NL > 0)
+      if (H - NL > 0 && m->f32_attn_mma)
+        LAUNCH(C_LINEAR, f32p::linear_attention_f32_mma_kernel<<<dim3(H - NL, B), 256, f32p::LINF_SMEM_BYTES, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
+      else if (H - NL > 0)
         LAUNCH(C_LINEAR, f32p::linear_attention_f32_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
       if (NL > 0 && m->f32_attn_mma)
         LAUNCH(C_LOCAL, f32p::local_attention_f32_mma_kernel<<<dim3(L / attn::WIN, NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
