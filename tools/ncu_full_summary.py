@@ -40,7 +40,7 @@ def label(name):
         return 'linear_attention'
     if 'gemm_bf16_tcgen05' in name:
         epi = name.split('<')[1].split(',')[2].strip()
-        return {'1': 'gemm_qkv', '2': 'gemm_ff1', '5': 'gemm_resid'}.get(epi, 'gemm_epi' + epi)
+        return {'1': 'gemm_qkv', '2': 'gemm_ff1', '5': 'gemm_resid', '6': 'gemm_resid'}.get(epi, 'gemm_epi' + epi)
     return name.split('(')[0].split('::')[-1]
 
 
@@ -48,7 +48,7 @@ lines, traffic, n_resid = [], {}, 0
 for r in rows[2:]:
     name = r[col['Kernel Name']]
     lab = label(name)
-    if lab == 'gemm_resid':                      # launch order inside a layer: out-proj then FF2
+    if lab == 'gemm_resid':                      # launch order inside a layer: out-proj (epilogue 6 or 5) then FF2 (epilogue 5)
         lab = 'gemm_out' if n_resid % 2 == 0 else 'gemm_ff2'
         n_resid += 1
     rd, wr = val(r, 'dram__bytes_read.sum'), val(r, 'dram__bytes_write.sum')
