@@ -125,6 +125,57 @@ def test_forward_small_vs_oracle():
     assert rel_err(got, orc(x, t, z)) < LOGIT_TOL
 
 
+SWEEP = {
+    # every valid corner of biom3_create's checks that the stage3 / SMALL shapes do not touch
+    'all_linear': dict(SMALL, transformer_local_heads=0),
+    'all_local': dict(SMALL, transformer_local_heads=8),
+    'three_windows_odd_batch': dict(SMALL, diffusion_steps=384),            # B * L % 256 != 0: single-CTA GEMM tiles, epilogue 5
+    'dim768_depth3': dict(SMALL, transformer_dim=768, transformer_heads=24, transformer_local_heads=12, transformer_depth=3),
+    'dim1024': dict(SMALL, transformer_dim=1024, transformer_heads=32, transformer_local_heads=16, transformer_depth=1),
+    'classes21_emb100': dict(SMALL, num_classes=21, text_emb_dim=100),       # sgemm K tail, smaller vocabulary
+}
+
+
+@pytest.mark.parametrize('name', sorted(SWEEP))
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_config_sweep_forward_and_decode_vs_oracle(name, precision):
+    """Shapes other than the two the rest of the suite uses: logits vs the oracle, then a 12-step decode with explicit
+    noise vs the oracle's sampler (identity, or a flip only where the oracle's own race margin is below the tolerance)."""
+    from biom3_b200.engine import Engine
+    from oracle.model import OracleModel
+    from oracle import sampler as osamp
+    over = SWEEP[name]
+    B = 3
+    args = synthetic.stage3_args(**over)
+    L, C, E = args.diffusion_steps, args.num_classes, args.text_emb_dim
+    sd = synthetic.random_state_dict(args, seed=31, perturb_norm=True)
+    eng = Engine(args, sd, torch.device('cuda'), B, precision=precision)
+    orc = OracleModel(args, sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, C, (B, L), generator=g)
+    t = torch.tensor([0, L // 2, L - 1])
+    z = synthetic.synthetic_z_c(B, E, seed=4)
+    got = eng.forward(x.cuda(), t.cuda(), z.cuda()).cpu()
+    ref = orc(x, t, z)
+    assert got.shape == (B, C, L)
+    assert rel_err(got, ref) < (LOGIT_TOL if precision == 'bf16' else 1e-4), name
+    T = 12
+    path = synthetic.synthetic_paths(B, L, seed=6)
+    noise = synthetic.synthetic_noise(T, B, L, C, seed=7)
+    margins = []
+
+    def hook(i, logits):
+        p = torch.softmax(logits, 1).permute(0, 2, 1).reshape(B * L, C) / noise[i]
+        top2 = p.topk(2, -1).values
+        margins.append(((top2[:, 0] - top2[:, 1]) / top2[:, 0]).reshape(B, L).numpy())
+
+    states, _ = osamp.decode(orc, torch.zeros(B, L), torch.zeros(B).long(), z, path, noise, L, max_iters=T, logits_hook=hook)
+    _, traj = eng.decode(z.cuda(), path.cuda(), num_steps=T, noise=noise.cuda(), want_traj=True)
+    _assert_traj(traj.cpu().numpy().astype(np.int64), np.stack(states)[:, :, 0], margins if precision == 'bf16' else None)
+    eng.check_inputs()
+    eng.close()
+
+
 def test_out_of_range_inputs_are_flagged_not_dereferenced():
     """The reference raises for a token id >= num_classes (nn.Embedding); here the load kernels clamp and record such a
     value, and a time index / path entry outside [0, L) likewise; Engine.check_inputs() raises, once, and clean calls stay
