@@ -180,10 +180,11 @@ local_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restr
 // split on mma.sync m16n8k16 with fp32 accumulators: x = hi + lo, hi = bf16(x), lo = bf16(x - hi), and
 // a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (what the tcgen05 GEMMs of this mode do, Params::split3); the softmax itself
 // (scores, maxima, exponentials, sums, the output accumulator) stays fp32.
-//   grid (L/128, NL, B), 256 threads: one query window; warp w owns query rows 16 w .. 16 w + 15 (Q fragments in registers)
+//   grid (L/128, NL, B), 256 threads, LAF_SMEM_BYTES of dynamic shared memory: one query window; warp w owns query rows 16 w .. 16 w + 15 (Q fragments in registers)
 //   per key window (w - 1, w, w + 1 where they exist): K and V converted to (hi, lo) bf16 tiles in shared memory (64-byte
 //   rows, 16-byte pieces XOR-swizzled for ldmatrix); per block of 64 keys S = Q K^T (48 MMAs per warp), online softmax,
 //   P split in registers (the accumulator fragments of two key tiles are the A fragment of one k-step), O += P V.
+constexpr int LAF_SMEM_BYTES = 4 * WIN * 64 + 2 * WIN * DH * 4 + 128;      // four bf16 tiles + raw fp32 K and V rows + alignment slack
 __device__ __forceinline__ uint32_t f32_swz(int row, int chunk) { return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -194,7 +195,13 @@ __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint
 __global__ void __launch_bounds__(256, 2)
 local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L,
                                float scale) {
-  __shared__ __align__(128) uint8_t sKh[WIN * 64], sKl[WIN * 64], sVh[WIN * 64], sVl[WIN * 64];
+  extern __shared__ uint8_t laf_raw[];
+  uint8_t* const laf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(laf_raw) + 127) & ~uintptr_t(127));
+  uint8_t* const sKh = laf;                         // (hi, lo) bf16 tiles of the current key window, 8 KB each
+  uint8_t* const sKl = laf + WIN * 64;
+  uint8_t* const sVh = laf + 2 * WIN * 64;
+  uint8_t* const sVl = laf + 3 * WIN * 64;
+  uint8_t* const sRaw = laf + 4 * WIN * 64;         // fp32 K and V rows of the NEXT key window (cp.async), 16 KB each
   const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * DH;
   const int nw = L / WIN;
@@ -221,14 +228,26 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
   for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float mx[2] = {-INFINITY, -INFINITY}, den[2] = {0.f, 0.f};      // rows g, g + 8
   const uint32_t kh0 = ptx::smem_u32(sKh), kl0 = ptx::smem_u32(sKl), vh0 = ptx::smem_u32(sVh), vl0 = ptx::smem_u32(sVl);
-  for (int kw = w - 1; kw <= w + 1; ++kw) {
-    if (kw < 0 || kw >= nw) continue;
-    __syncthreads();
-    // K, V of the key window: fp32 -> (hi, lo) bf16 tiles
+  // The fp32 rows of a key window travel global -> shared with cp.async while the previous window is being multiplied;
+  // each thread then converts the pieces it fetched itself into the (hi, lo) tiles.
+  const int kw_lo = max(w - 1, 0), kw_hi = min(w + 1, nw - 1);
+  auto fetch = [&](int kw) {
     for (int i = tid; i < WIN * DH / 4; i += 256) {
       const int r = i >> 3, c4 = i & 7;                             // row, float4 index within the 32 features
       const float* src = qkv + (size_t(b) * L + size_t(kw) * WIN + r) * 3 * D + h * DH + 4 * c4;
-      const float4 kk = *reinterpret_cast<const float4*>(src + D), vv = *reinterpret_cast<const float4*>(src + 2 * D);
+      ptx::cp_async_16(ptx::smem_u32(sRaw) + i * 16, src + D);
+      ptx::cp_async_16(ptx::smem_u32(sRaw) + WIN * DH * 4 + i * 16, src + 2 * D);
+    }
+    ptx::cp_async_commit();
+  };
+  fetch(kw_lo);
+  for (int kw = kw_lo; kw <= kw_hi; ++kw) {
+    ptx::cp_async_wait<0>();
+    __syncthreads();                                                // everyone is done with the previous window's tiles
+    for (int i = tid; i < WIN * DH / 4; i += 256) {
+      const int r = i >> 3, c4 = i & 7;
+      const float4 kk = *reinterpret_cast<const float4*>(sRaw + i * 16);
+      const float4 vv = *reinterpret_cast<const float4*>(sRaw + WIN * DH * 4 + i * 16);
       const uint32_t off = f32_swz(r, c4 >> 1) + (c4 & 1) * 8;
       uint32_t h0, l0, h1, l1;
       split_pack2(kk.x, kk.y, h0, l0);
@@ -240,6 +259,7 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
       *reinterpret_cast<uint2*>(sVh + off) = make_uint2(h0, h1);
       *reinterpret_cast<uint2*>(sVl + off) = make_uint2(l0, l1);
     }
+    if (kw < kw_hi) fetch(kw + 1);                                  // this thread's raw pieces are consumed: refill them
     __syncthreads();
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {                                  // two blocks of 64 keys (half the score registers of 128)

@@ -206,6 +206,8 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(f32p::local_attention_f32_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LAF_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(f32p::linear_attention_f32_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LINF_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_MAX);
@@ -516,7 +518,7 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
       else if (H - NL > 0)
         LAUNCH(C_LINEAR, f32p::linear_attention_f32_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
       if (NL > 0 && m->f32_attn_mma)
-        LAUNCH(C_LOCAL, f32p::local_attention_f32_mma_kernel<<<dim3(L / attn::WIN, NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
+        LAUNCH(C_LOCAL, f32p::local_attention_f32_mma_kernel<<<dim3(L / attn::WIN, NL, B), 256, f32p::LAF_SMEM_BYTES, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
       else if (NL > 0)
         LAUNCH(C_LOCAL, f32p::local_attention_f32_kernel<<<dim3(L / attn::WIN, NL, B), 128, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
       gemm::Params r{};
