@@ -580,6 +580,33 @@ def test_gemm_split3_matches_fp32_product():
         assert rel_err(out, ref) < 2e-5, (bn, pair)
 
 
+def test_fp32_mode_round2_kernels_agree_with_round1_kernels(monkeypatch):
+    """fp32-class mode: the tensor-core attention kernels (three-product bf16 splits on mma.sync) and the GELU / split
+    epilogue of FF1 against the CUDA-core fp32 kernels and the separate GELU pass they replaced (kept behind
+    BIOM3_F32_ATTN_MMA=0 / BIOM3_F32_FUSED_GELU=0): same logits to 2e-5 at a shape with both kinds of heads, three
+    windows (look-around on both sides) and a sequence that is not a multiple of the 256-token pass of the linear kernel."""
+    from biom3_b200.engine import Engine
+    over = dict(SMALL, diffusion_steps=384, transformer_depth=3)
+    B = 3
+    args = synthetic.stage3_args(**over)
+    sd = synthetic.random_state_dict(args, seed=17, perturb_norm=True)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randint(0, 29, (B, 384), generator=g).cuda()
+    t = torch.tensor([1, 200, 383]).cuda()
+    z = synthetic.synthetic_z_c(B, 64, seed=4).cuda()
+    out = {}
+    for mma, fused in (('1', '1'), ('0', '1'), ('1', '0'), ('0', '0')):
+        monkeypatch.setenv('BIOM3_F32_ATTN_MMA', mma)
+        monkeypatch.setenv('BIOM3_F32_FUSED_GELU', fused)
+        eng = Engine(args, sd, torch.device('cuda'), B, precision='fp32')
+        out[mma, fused] = eng.forward(x, t, z).cpu()
+        eng.close()
+    ref = out['0', '0']
+    for k, v in out.items():
+        assert rel_err(v, ref) < 2e-5, k
+    assert torch.equal(out['0', '1'], ref)            # the fused epilogue evaluates the same expression on the same accumulator
+
+
 @pytest.mark.parametrize('pair', [False, True])
 def test_gemm_gelu_split_epilogue(pair):
     """Epilogue 7 (fp32-class FF1): bias + exact-erf GELU on the fp32 accumulator, stored as hi | lo bf16 halves whose sum
