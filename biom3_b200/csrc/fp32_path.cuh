@@ -356,6 +356,212 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
   }
 }
 
+// The same attention on tcgen05 (round 2, default): mma.sync runs at about an eighth of the tcgen05 rate on this part and
+// bounded the kernel above (19 M m16n8k16 per layer).  One CTA of 128 threads per query window, thread = query row = TMEM
+// lane; up to four CTAs per SM overlap each other's phases (128 TMEM columns, 48 KB of shared memory each):
+//   * the CTA converts the Q rows (scaled like the reference scales q) and, per key window, the K and V rows from fp32
+//     (coalesced float4 loads, 8 threads per row) to (hi, lo) bf16 rows of shared-memory tiles in the 64-byte-swizzled layout the MMA descriptors expect
+//     (what TMA writes in the bf16 kernel, attention.cuh); fence.proxy.async publishes them to the tensor core
+//   * one elected thread issues, per block of 64 keys, S = Ql Kh^T + Qh Kl^T + Qh Kh^T (six 128 x 64 x 16 MMAs into 64 TMEM
+//     columns) and, after the softmax, O += Pl Vh + Ph Vl + Ph Vh (twelve 128 x 32 x 16 MMAs, P read from TMEM, V as
+//     stored, MN-major); tcgen05 operations of one thread execute in issue order, which orders S of the next block
+//     behind the P V reads of this one
+//   * softmax per row in fp32 against a lazily rescaled reference maximum (as in the bf16 kernel); P is split into bf16
+//     hi (TMEM columns 0-31 of the S slot) and lo (columns 32-63): the split overwrites the scores in place
+constexpr int LAT_SMEM_BYTES = 6 * WIN * 64 + 1024;     // Qh, Ql, Kh, Kl, Vh, Vl tiles + alignment slack
+
+// fp32 rows [128][32] at `src` (row stride `ld` floats) -> (hi, lo) bf16 tiles, 128 threads: thread i + 128 j takes the j-th
+// float4 round, 8 threads per row, so every warp load covers four full 128-byte rows
+__device__ __forceinline__ void split_tile_128(const float* __restrict__ src, size_t ld, float mul, uint8_t* th, uint8_t* tl, int tid) {
+  float4 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = tid + 128 * j;
+    v[j] = *reinterpret_cast<const float4*>(src + size_t(i >> 3) * ld + 4 * (i & 7));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = tid + 128 * j, r = i >> 3, c4 = i & 7;
+    uint32_t h0, l0, h1, l1;
+    split_pack2(v[j].x * mul, v[j].y * mul, h0, l0);
+    split_pack2(v[j].z * mul, v[j].w * mul, h1, l1);
+    const uint32_t off = f32_swz(r, c4 >> 1) + (c4 & 1) * 8;
+    *reinterpret_cast<uint2*>(th + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(tl + off) = make_uint2(l0, l1);
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(128)
+local_attention_f32_tc_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L, float scale) {
+  extern __shared__ uint8_t lat_raw[];
+  uint8_t* const sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lat_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* const sQh = sm;
+  uint8_t* const sQl = sm + WIN * 64;
+  uint8_t* const sKh = sm + 2 * WIN * 64;
+  uint8_t* const sKl = sm + 3 * WIN * 64;
+  uint8_t* const sVh = sm + 4 * WIN * 64;
+  uint8_t* const sVl = sm + 5 * WIN * 64;
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * DH;
+  const int nw = L / WIN;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  constexpr float LOG2E = 1.4426950408889634f;
+  constexpr float LAZY_LOG2 = 8.0f;
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  if (tid == 0) {
+    ptx::mbar_init(&bar_s, 1);
+    ptx::mbar_init(&bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, 128);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_s = tmem + ((uint32_t(warp) * 32u) << 16);          // this warp's lanes: S / P at columns 0-63
+  const uint32_t t_o = t_s + 64;                                          // O at columns 64-95
+  const size_t qrow = size_t(b) * L + size_t(w) * WIN + tid;
+  split_tile_128(qkv + (size_t(b) * L + size_t(w) * WIN) * 3 * D + h * DH, size_t(3) * D, scale, sQh, sQl, tid);
+  const uint32_t qh_lo = attn::local_desc_lo(ptx::smem_u32(sQh)), ql_lo = attn::local_desc_lo(ptx::smem_u32(sQl));
+  const uint32_t kh_lo = attn::local_desc_lo(ptx::smem_u32(sKh)), kl_lo = attn::local_desc_lo(ptx::smem_u32(sKl));
+  const uint32_t vh_lo = attn::local_desc_lo(ptx::smem_u32(sVh)), vl_lo = attn::local_desc_lo(ptx::smem_u32(sVl));
+  auto issue_s = [&](int sb) {                         // one thread: S = Ql Kh^T + Qh Kl^T + Qh Kh^T for keys 64 sb ..
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ptx::umma_bf16(tmem, attn::local_desc(ql_lo + 2 * ks), attn::local_desc(kh_lo + sb * 256 + 2 * ks), IDESC_S, ks != 0);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ptx::umma_bf16(tmem, attn::local_desc(qh_lo + 2 * ks), attn::local_desc(kl_lo + sb * 256 + 2 * ks), IDESC_S, 1);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ptx::umma_bf16(tmem, attn::local_desc(qh_lo + 2 * ks), attn::local_desc(kh_lo + sb * 256 + 2 * ks), IDESC_S, 1);
+    ptx::umma_commit(&bar_s);
+  };
+  float m_ref = 0.f, rs = 0.f;
+  uint32_t ph_s = 0, ph_o = 0;
+  int blocks_done = 0;                                 // P V blocks issued so far for this item
+  const int kw_lo = max(w - 1, 0), kw_hi = min(w + 1, nw - 1);
+  for (int kw = kw_lo; kw <= kw_hi; ++kw) {
+    // the previous window's MMAs must be done with the K / V tiles before they are rewritten
+    if (blocks_done > 0) {
+      ptx::mbar_wait(&bar_o, ph_o ^ 1);                // the last commit's phase (ph_o was flipped when it was issued)
+      ptx::tc_fence_after();
+    }
+    const float* kbase = qkv + (size_t(b) * L + size_t(kw) * WIN) * 3 * D + D + h * DH;
+    split_tile_128(kbase, size_t(3) * D, 1.0f, sKh, sKl, tid);
+    split_tile_128(kbase + D, size_t(3) * D, 1.0f, sVh, sVl, tid);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) issue_s(0);
+      __syncwarp();
+    }
+    for (int sb = 0; sb < 2; ++sb) {
+      ptx::mbar_wait(&bar_s, ph_s);
+      ph_s ^= 1;
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32(t_s, r0);
+      ptx::tmem_ld_32x32(t_s + 32, r1);
+      ptx::tmem_ld_wait();
+      float bm = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) bm = fmaxf(bm, fmaxf(__uint_as_float(r0[k]), __uint_as_float(r1[k])));
+      if (blocks_done == 0) {
+        m_ref = bm;
+        rs = 0.f;
+      } else {
+        const bool need = (bm - m_ref) * LOG2E > LAZY_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          // every P V issued so far must have landed in O
+          ptx::mbar_wait(&bar_o, ph_o ^ 1);
+          ptx::tc_fence_after();
+          const float f = need ? exp2f((m_ref - bm) * LOG2E) : 1.f;
+          uint32_t ro[32];
+          ptx::tmem_ld_32x32(t_o, ro);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
+          ptx::tmem_st_32x32(t_o, ro);
+          ptx::tmem_st_wait();
+          rs *= f;
+          if (need) m_ref = bm;
+        }
+      }
+      const float ml = m_ref * LOG2E;
+      uint32_t ph[32], pl[32];                         // P hi / lo as bf16 pairs: 64 keys -> 32 + 32 columns
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * k]), LOG2E, -ml)), p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * k + 1]), LOG2E, -ml));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * k]), LOG2E, -ml)), p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * k + 1]), LOG2E, -ml));
+        sum += (p0 + p1) + (p2 + p3);
+        split_pack2(p0, p1, ph[k], pl[k]);
+        split_pack2(p2, p3, ph[16 + k], pl[16 + k]);
+      }
+      rs += sum;
+      ptx::tmem_st_32x32(t_s, ph);
+      ptx::tmem_st_32x32(t_s + 32, pl);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          // O (+)= Pl Vh + Ph Vl + Ph Vh over the block's 64 keys (four k-steps of 16)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16_ts(tmem + 64, tmem + 32 + ks * 8, attn::local_desc(vh_lo + sb * 256 + ks * 64), IDESC_O, (blocks_done | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16_ts(tmem + 64, tmem + ks * 8, attn::local_desc(vl_lo + sb * 256 + ks * 64), IDESC_O, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16_ts(tmem + 64, tmem + ks * 8, attn::local_desc(vh_lo + sb * 256 + ks * 64), IDESC_O, 1);
+          ptx::umma_commit(&bar_o);
+          if (sb == 0) issue_s(1);                     // in issue order behind the P V reads of the S / P columns
+        }
+        __syncwarp();
+      }
+      ph_o ^= 1;
+      ++blocks_done;
+    }
+  }
+  // output: O / row sum, split, this thread's row
+  ptx::mbar_wait(&bar_o, ph_o ^ 1);
+  ptx::tc_fence_after();
+  {
+    uint32_t ro[32];
+    ptx::tmem_ld_32x32(t_o, ro);
+    ptx::tmem_ld_wait();
+    const float inv = 1.0f / rs;
+    __nv_bfloat16* dst = att2 + qrow * 2 * D + h * DH;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        split_pack2(__uint_as_float(ro[8 * c + 2 * i]) * inv, __uint_as_float(ro[8 * c + 2 * i + 1]) * inv, hw[i], lw[i]);
+      *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(dst + D + 8 * c) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 128);
+}
+
 // Linear attention of the fp32-class mode on the tensor cores (round 2; the CUDA-core kernel below is kept as the unit-test
 // reference).  Same input and output as linear_attention_f32_kernel, grid (H - NL, B), 256 threads, LINF_SMEM_BYTES of
 // dynamic shared memory.  The softmaxes are fp32 and thread-per-token (each thread owns one token's 32 features); the two

@@ -206,6 +206,8 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(f32p::local_attention_f32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LAT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(f32p::local_attention_f32_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LAF_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(f32p::linear_attention_f32_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LINF_SMEM_BYTES);
@@ -332,7 +334,8 @@ struct biom3_model {
   int precision = 0;
   bool f32_fused_gelu = true;                   // BIOM3_F32_FUSED_GELU=0: fp32 hidden activation + a separate bias / GELU / split pass
   CUtensorMap tm_st_hid2{};                     // TMA-store map of hid2 [M][8D] (gemm::EPI_BIAS_GELU_SPLIT)
-  bool f32_attn_mma = true;                     // BIOM3_F32_ATTN_MMA=0: the CUDA-core fp32 attention kernels of round 1
+  int f32_attn_mma = 2;                         // BIOM3_F32_ATTN_MMA: 2 = windowed attention on tcgen05 + linear on mma.sync, 1 = both on mma.sync,
+                                                // 0 = the CUDA-core fp32 attention kernels of round 1
   bf16 *Wqkv2 = nullptr, *Wo2 = nullptr, *W1s = nullptr, *W2s = nullptr;       // [N][2K] per layer, stacked
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // [depth][D]
   bf16 *a2 = nullptr, *hid2 = nullptr;                                            // [M][2D], [M][8D]
@@ -517,7 +520,9 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
         LAUNCH(C_LINEAR, f32p::linear_attention_f32_mma_kernel<<<dim3(H - NL, B), 256, f32p::LINF_SMEM_BYTES, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
       else if (H - NL > 0)
         LAUNCH(C_LINEAR, f32p::linear_attention_f32_kernel<<<dim3(H - NL, B), 256, 0, st>>>(m->qkv32, m->a2, B, H, L, NL, q_scale));
-      if (NL > 0 && m->f32_attn_mma)
+      if (NL > 0 && m->f32_attn_mma >= 2)
+        LAUNCH(C_LOCAL, f32p::local_attention_f32_tc_kernel<<<dim3(L / attn::WIN, NL, B), 128, f32p::LAT_SMEM_BYTES, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
+      else if (NL > 0 && m->f32_attn_mma)
         LAUNCH(C_LOCAL, f32p::local_attention_f32_mma_kernel<<<dim3(L / attn::WIN, NL, B), 256, f32p::LAF_SMEM_BYTES, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
       else if (NL > 0)
         LAUNCH(C_LOCAL, f32p::local_attention_f32_kernel<<<dim3(L / attn::WIN, NL, B), 128, 0, st>>>(m->qkv32, m->a2, B, H, L, q_scale));
@@ -684,7 +689,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_RESID_TMA")) m->resid_tma = atoi(e);
-  if (const char* e = getenv("BIOM3_F32_ATTN_MMA")) m->f32_attn_mma = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_F32_ATTN_MMA")) m->f32_attn_mma = atoi(e);
   if (const char* e = getenv("BIOM3_F32_FUSED_GELU")) m->f32_fused_gelu = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;

@@ -595,7 +595,7 @@ def test_fp32_mode_round2_kernels_agree_with_round1_kernels(monkeypatch):
     t = torch.tensor([1, 200, 383]).cuda()
     z = synthetic.synthetic_z_c(B, 64, seed=4).cuda()
     out = {}
-    for mma, fused in (('1', '1'), ('0', '1'), ('1', '0'), ('0', '0')):
+    for mma, fused in (('2', '1'), ('1', '1'), ('0', '1'), ('1', '0'), ('0', '0')):
         monkeypatch.setenv('BIOM3_F32_ATTN_MMA', mma)
         monkeypatch.setenv('BIOM3_F32_FUSED_GELU', fused)
         eng = Engine(args, sd, torch.device('cuda'), B, precision='fp32')
