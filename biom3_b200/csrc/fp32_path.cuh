@@ -368,6 +368,9 @@ local_attention_f32_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __r
 //     behind the P V reads of this one
 //   * softmax per row in fp32 against a lazily rescaled reference maximum (as in the bf16 kernel); P is split into bf16
 //     hi (TMEM columns 0-31 of the S slot) and lo (columns 32-63): the split overwrites the scores in place
+#ifndef BIOM3_F32_TC_CTAS
+#define BIOM3_F32_TC_CTAS 3      // CTAs per SM the register budget is cut for (4 measured equal: the kernel is bound by its serial phases, not by occupancy)
+#endif
 constexpr int LAT_SMEM_BYTES = 6 * WIN * 64 + 1024;     // Qh, Ql, Kh, Kl, Vh, Vl tiles + alignment slack
 
 // fp32 rows [128][32] at `src` (row stride `ld` floats) -> (hi, lo) bf16 tiles, 128 threads: thread i + 128 j takes the j-th
@@ -397,7 +400,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BIOM3_F32_TC_CTAS)
 local_attention_f32_tc_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ att2, int B, int H, int L, float scale) {
   extern __shared__ uint8_t lat_raw[];
   uint8_t* const sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lat_raw) + 1023) & ~uintptr_t(1023));
