@@ -657,4 +657,309 @@ local_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
   if (warp == 1) ptx::tmem_dealloc(tmem_slot, 512);
 }
 
+// ================================================================================================
+// The same attention with THREE streams per CTA (round 2 experiment, BIOM3_ATTN3=1): three softmax warps per SM
+// sub-partition instead of two, so that the MUFU pipe has a third warp's exponentials to run while the other two are in
+// the MUFU-free part of their blocks (the two-stream kernel keeps it 2/3 busy).  Four warps per SMSP cap a thread at 128
+// registers, which is what the softmax warps need, so the CTA has exactly 16 warps:
+//   warp 0        TMA producer for all three streams (non-blocking: serves whichever stream has a free buffer)
+//   warps 1..3    one issuer per stream: S one block ahead of P V (two S / P slots), both from the same thread
+//   warps 4..15   softmax, four per stream (warp id % 4 = TMEM lane quarter)
+// Per stream: TMEM 160 columns (S / P slots at 0 and 64, one O buffer at 128), shared memory 2 Q tiles + 3 K/V stages.
+// With a single O buffer the output of an item is read right after its last block (the wait for the last P V is covered
+// by the other two streams).
+// ================================================================================================
+constexpr int L3_NST = 3;
+constexpr int L3_THREADS = 16 * 32;
+constexpr int L3_STREAM_TILES = 2 + 2 * L3_NST;
+constexpr int L3_SMEM_BYTES = 3 * L3_STREAM_TILES * TC_TILE + 1024;
+struct L3Bars {
+  uint64_t q_full[2], q_free[2], kv_full[L3_NST], kv_free[L3_NST], s_full[2], p_ready[2], s_free[2], o_full, o_free;
+};
+struct L3Cursor {                       // position of an issuer in its stream's block sequence
+  int n, kt, sb, g;
+  uint32_t st, st_ph;
+  bool valid;
+  LocalItem it;
+};
+
+__global__ void __launch_bounds__(L3_THREADS, 1)
+local_attention3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
+                        int NL, float scale_log2e, int reverse) {
+  const int nw = L / WIN;
+  const int total = nw * B * NL, nlb = NL * B;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  extern __shared__ uint8_t local3_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(local3_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ L3Bars bars[3];
+  __shared__ uint32_t tmem_slot;
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_qkv);
+    for (int s2 = 0; s2 < 3; ++s2) {
+      L3Bars& x = bars[s2];
+      for (int k = 0; k < 2; ++k) {
+        ptx::mbar_init(&x.q_full[k], 1);
+        ptx::mbar_init(&x.q_free[k], 1);
+        ptx::mbar_init(&x.s_full[k], 1);
+        ptx::mbar_init(&x.p_ready[k], 4);
+        ptx::mbar_init(&x.s_free[k], 1);
+      }
+      for (int k = 0; k < L3_NST; ++k) {
+        ptx::mbar_init(&x.kv_full[k], 1);
+        ptx::mbar_init(&x.kv_free[k], 1);
+      }
+      ptx::mbar_init(&x.o_full, 1);
+      ptx::mbar_init(&x.o_free, 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  ptx::pdl_sync();
+
+  // the n-th item of stream s: flat index blockIdx.x + (s + 3 n) gridDim.x, walked window-major
+  auto item = [&](int s, int n, LocalItem& it) -> bool {
+    const int f = int(blockIdx.x) + (s + 3 * n) * int(gridDim.x);
+    if (f >= total) return false;
+    const int ff = reverse ? total - 1 - f : f;
+    it.w = ff / nlb;
+    const int r = ff - it.w * nlb;
+    it.b = r / NL;
+    it.h = r - it.b * NL;
+    it.w_lo = max(it.w - 1, 0);
+    it.nkt = min(it.w + 1, nw - 1) - it.w_lo + 1;
+    return true;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer, three streams, non-blocking
+    const int plane = B * H * L;
+    int n[3] = {0, 0, 0}, kt[3] = {-1, -1, -1};
+    uint32_t st[3] = {0, 0, 0}, st_ph[3] = {0, 0, 0};
+    bool live[3];
+    LocalItem it[3];
+    int left = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      live[s] = item(s, 0, it[s]);
+      left += live[s] ? 1 : 0;
+    }
+    while (left > 0) {
+      bool progress = false;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (!live[s]) continue;
+        L3Bars& bar = bars[s];
+        uint8_t* sQ = smem + s * L3_STREAM_TILES * TC_TILE;
+        uint8_t* sKV = sQ + 2 * TC_TILE;
+        const int rq = (it[s].b * H + it[s].h) * L;
+        if (kt[s] < 0) {
+          const int qb = n[s] & 1;
+          if (!ptx::mbar_try_wait(&bar.q_free[qb], ((n[s] >> 1) & 1) ^ 1)) continue;
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
+            ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + it[s].w * WIN);
+          }
+          __syncwarp();
+          kt[s] = 0;
+          progress = true;
+        } else {
+          if (!ptx::mbar_try_wait(&bar.kv_free[st[s]], st_ph[s] ^ 1)) continue;
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&bar.kv_full[st[s]], 2 * TC_TILE);
+            ptx::tma_load_2d(sKV + (2 * st[s]) * TC_TILE, &tm_qkv, &bar.kv_full[st[s]], 0, plane + rq + (it[s].w_lo + kt[s]) * WIN);
+            ptx::tma_load_2d(sKV + (2 * st[s] + 1) * TC_TILE, &tm_qkv, &bar.kv_full[st[s]], 0, 2 * plane + rq + (it[s].w_lo + kt[s]) * WIN);
+          }
+          __syncwarp();
+          if (++st[s] == L3_NST) { st[s] = 0; st_ph[s] ^= 1; }
+          progress = true;
+          if (++kt[s] == it[s].nkt) {
+            kt[s] = -1;
+            ++n[s];
+            live[s] = item(s, n[s], it[s]);
+            if (!live[s]) --left;
+          }
+        }
+      }
+      if (!progress) __nanosleep(64);
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ issuer of stream warp - 1: S one block ahead of P V
+    const int s = warp - 1;
+    L3Bars& bar = bars[s];
+    const uint32_t tmem = tmem0 + s * 160;
+    uint8_t* sQ = smem + s * L3_STREAM_TILES * TC_TILE;
+    uint8_t* sKV = sQ + 2 * TC_TILE;
+    constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t q_lo0 = local_desc_lo(ptx::smem_u32(sQ)), kv_lo0 = local_desc_lo(ptx::smem_u32(sKV));
+    auto start = [&](L3Cursor& c) {
+      c.n = 0; c.kt = 0; c.sb = 0; c.g = 0; c.st = 0; c.st_ph = 0;
+      c.valid = item(s, 0, c.it);
+    };
+    auto advance = [&](L3Cursor& c) {
+      ++c.g;
+      if (c.sb == 0) { c.sb = 1; return; }
+      c.sb = 0;
+      if (++c.st == L3_NST) { c.st = 0; c.st_ph ^= 1; }
+      if (++c.kt == c.it.nkt) {
+        c.kt = 0;
+        ++c.n;
+        c.valid = item(s, c.n, c.it);
+      }
+    };
+    auto issue_s = [&](const L3Cursor& c) {
+      const int qb = c.n & 1;
+      const uint32_t slot = c.g & 1;
+      if (c.kt == 0 && c.sb == 0) ptx::mbar_wait_parked(&bar.q_full[qb], (c.n >> 1) & 1);
+      if (c.sb == 0) ptx::mbar_wait_parked(&bar.kv_full[c.st], c.st_ph);
+      ptx::mbar_wait_parked(&bar.s_free[slot], ((c.g >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t q_lo = q_lo0 + qb * (TC_TILE >> 4);
+      const uint32_t k_lo = kv_lo0 + c.st * (2 * TC_TILE >> 4);
+      const bool last_s = c.kt == c.it.nkt - 1 && c.sb == 1;
+      if (ptx::elect_one()) {
+        ptx::umma_bf16(tmem + slot * 64, local_desc(q_lo), local_desc(k_lo + c.sb * 256), IDESC_S, 0);
+        ptx::umma_bf16(tmem + slot * 64, local_desc(q_lo + 2), local_desc(k_lo + c.sb * 256 + 2), IDESC_S, 1);
+        ptx::umma_commit(&bar.s_full[slot]);
+        if (last_s) ptx::umma_commit(&bar.q_free[qb]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](const L3Cursor& c) {
+      const uint32_t slot = c.g & 1;
+      const bool first = c.kt == 0 && c.sb == 0, last = c.kt == c.it.nkt - 1 && c.sb == 1;
+      if (first) ptx::mbar_wait_parked(&bar.o_free, (c.n & 1) ^ 1);       // the previous item's output has been read
+      ptx::mbar_wait_parked(&bar.p_ready[slot], (c.g >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t v_lo = kv_lo0 + c.st * (2 * TC_TILE >> 4) + (TC_TILE >> 4);
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_bf16_ts(tmem + 128, tmem + slot * 64 + ks * 8, local_desc(v_lo + c.sb * 256 + ks * 64), IDESC_O, (first ? ks : 1) != 0);
+        ptx::umma_commit(&bar.s_free[slot]);
+        if (c.sb == 1) ptx::umma_commit(&bar.kv_free[c.st]);
+        if (last) ptx::umma_commit(&bar.o_full);
+      }
+      __syncwarp();
+    };
+    L3Cursor cs, cp;
+    start(cs);
+    start(cp);
+    if (cs.valid) {
+      issue_s(cs);
+      advance(cs);
+    }
+    while (cp.valid) {
+      if (cs.valid) {
+        issue_s(cs);
+        advance(cs);
+      }
+      issue_pv(cp);
+      advance(cp);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output: stream (warp - 4) / 4, quarter warp % 4
+    const int s = (warp - 4) >> 2;
+    L3Bars& bar = bars[s];
+    const uint32_t tmem = tmem0 + s * 160;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t(quarter) * 32u) << 16);
+    const int D = H * DH;
+    constexpr float LAZY_LOG2 = 8.0f;
+    float m_ref = 0.f, rs = 0.f;
+    LocalItem it;
+    int g = 0;
+    for (int n = 0; item(s, n, it); ++n) {
+      const int nblk = 2 * it.nkt;
+      for (int blk = 0; blk < nblk; ++blk, ++g) {
+        const uint32_t slot = g & 1, slot_ph = (g >> 1) & 1;
+        const uint32_t t_s = lane_base + slot * 64;
+        ptx::mbar_wait(&bar.s_full[slot], slot_ph);
+        ptx::tc_fence_after();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(t_s, r0);
+        ptx::tmem_ld_32x32(t_s + 32, r1);
+        ptx::tmem_ld_wait();
+        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          b0 = fmaxf(b0, __uint_as_float(r0[2 * k]));
+          b1 = fmaxf(b1, __uint_as_float(r0[2 * k + 1]));
+          b2 = fmaxf(b2, __uint_as_float(r1[2 * k]));
+          b3 = fmaxf(b3, __uint_as_float(r1[2 * k + 1]));
+        }
+        const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+        if (blk == 0) {
+          m_ref = bm;
+          rs = 0.f;
+        } else {
+          const bool need = (bm - m_ref) * scale_log2e > LAZY_LOG2;
+          if (__any_sync(0xffffffffu, need)) {
+            // every P V issued so far must have landed in O: P V (g - 1)'s commit completes s_free of its slot
+            ptx::mbar_wait(&bar.s_free[slot ^ 1], ((g - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            const float f = need ? fast_ex2((m_ref - bm) * scale_log2e) : 1.f;
+            uint32_t ro[32];
+            ptx::tmem_ld_32x32(lane_base + 128, ro);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ro[k] = __float_as_uint(__uint_as_float(ro[k]) * f);
+            ptx::tmem_st_32x32(lane_base + 128, ro);
+            ptx::tmem_st_wait();
+            rs *= f;
+            if (need) m_ref = bm;
+          }
+        }
+        const float ms = m_ref * scale_log2e;
+        uint32_t pk[32];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_ex2(fmaf(__uint_as_float(r0[2 * k]), scale_log2e, -ms));
+          const float p1 = fast_ex2(fmaf(__uint_as_float(r0[2 * k + 1]), scale_log2e, -ms));
+          const float p2 = fast_ex2(fmaf(__uint_as_float(r1[2 * k]), scale_log2e, -ms));
+          const float p3 = fast_ex2(fmaf(__uint_as_float(r1[2 * k + 1]), scale_log2e, -ms));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[k] = ptx::pack_bf16x2(p0, p1);
+          pk[16 + k] = ptx::pack_bf16x2(p2, p3);
+        }
+        rs += (s0 + s1) + (s2 + s3);
+        ptx::tmem_st_32x32(t_s, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.p_ready[slot]);
+      }
+      // output of this item (single O buffer): the last P V has been issued as soon as the fourth warp arrived above
+      ptx::mbar_wait(&bar.o_full, n & 1);
+      ptx::tc_fence_after();
+      uint32_t ro[32];
+      ptx::tmem_ld_32x32(lane_base + 128, ro);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.o_free);
+      const float inv = 1.f / rs;
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t(it.b) * L + size_t(it.w) * WIN + row) * D + it.h * DH);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[k] = make_uint4(ptx::pack_bf16x2(__uint_as_float(ro[8 * k]) * inv, __uint_as_float(ro[8 * k + 1]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 2]) * inv, __uint_as_float(ro[8 * k + 3]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 4]) * inv, __uint_as_float(ro[8 * k + 5]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(ro[8 * k + 6]) * inv, __uint_as_float(ro[8 * k + 7]) * inv));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem0, 512);
+}
+
 }  // namespace attn

@@ -203,6 +203,8 @@ cudaError_t init_kernel_attributes_impl() {
   e = cudaFuncSetAttribute(attn::local_attention_kernel<attn::LOCAL_NST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LocalCfg<attn::LOCAL_NST>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::local_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::L3_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -237,9 +239,15 @@ cudaError_t init_kernel_attributes() {
 }
 
 // windowed attention (attention.cuh): persistent, one CTA per SM; trace = 1 records CTA 0's clock64 timeline
+int g_attn3 = 0;                   // BIOM3_ATTN3=1: the three-stream windowed-attention kernel (attention.cuh, round-2 experiment)
 void launch_local(const CUtensorMap& tm, bf16* out, int B, int H, int L, int NL, float scale_log2e, int reverse, int num_sms,
                   int trace, cudaStream_t st) {
   const int grid = std::min(num_sms, (L / attn::WIN) * NL * B);
+  if (g_attn3 && !trace) {
+    launch_k(attn::local_attention3_kernel, dim3(grid), dim3(attn::L3_THREADS), size_t(attn::L3_SMEM_BYTES), st, tm, out, B, H, L, NL,
+             scale_log2e, reverse);
+    return;
+  }
   constexpr size_t smem = attn::LocalCfg<attn::LOCAL_NST>::SMEM_BYTES;
   if (trace)
     launch_k(attn::local_attention_kernel<attn::LOCAL_NST, 1>, dim3(grid), dim3(attn::LOCAL_THREADS), smem, st, tm, out, B, H, L, NL,
@@ -689,6 +697,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_SPLIT_RESID")) m->split_resid = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_SERPENTINE")) m->serpentine = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_RESID_TMA")) m->resid_tma = atoi(e);
+  if (const char* e = getenv("BIOM3_ATTN3")) g_attn3 = atoi(e);
   if (const char* e = getenv("BIOM3_F32_ATTN_MMA")) m->f32_attn_mma = atoi(e);
   if (const char* e = getenv("BIOM3_F32_FUSED_GELU")) m->f32_fused_gelu = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
@@ -1281,6 +1290,7 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
     return fail(BIOM3_ERR_INVALID, "bad attention_test argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CU_OK(init_kernel_attributes());
+  if (const char* e = getenv("BIOM3_ATTN3")) g_attn3 = atoi(e);
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(attn::DH));
   const float q_scale = 1.0f / sqrtf(float(attn::DH));
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
