@@ -539,13 +539,15 @@ def test_batch_of_one_decode_matches_oracle():
 @pytest.mark.parametrize('B,H,L,NL,amp', [(1, 2, 128, 1, 1.5), (2, 4, 256, 2, 1.5), (2, 16, 1024, 8, 1.5),
                                           (2, 4, 512, 2, 4.0), (3, 4, 1024, 3, 6.0), (5, 8, 384, 8, 1.0)])
 @pytest.mark.parametrize('variant', [0, 1])
-def test_attention_kernels_vs_fp32_reference(B, H, L, NL, amp, variant):
+@pytest.mark.parametrize('streams', [3, 2])
+def test_attention_kernels_vs_fp32_reference(B, H, L, NL, amp, variant, streams, monkeypatch):
     """Heads < NL: the tcgen05 windowed-softmax kernel (two streams per CTA, split S / PV issuers, P kept in TMEM, lazily
     rescaled online softmax; variant 1 = the same kernel with its clock64 timeline recording on); heads >= NL: linear
     attention.  amp >= 4 gives peaked rows whose block maxima jump by more than 2^8, which exercises the rescale path.
     Same bf16 inputs, fp32 reference."""
     from biom3_b200 import engine
     from oracle.upstream_blocks import LocalAttention, linear_attention
+    monkeypatch.setenv('BIOM3_ATTN3', '1' if streams == 3 else '0')      # three-stream kernel (default) / two-stream kernel
     g = torch.Generator().manual_seed(B * 100 + L)
     qkv = (torch.randn(3, B, H, L, 32, generator=g) * amp).bfloat16()
     q, k, v = (t.float() for t in qkv)
