@@ -669,7 +669,8 @@ local_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
 // With a single O buffer the output of an item is read right after its last block (the wait for the last P V is covered
 // by the other two streams).  81.5 us against 87.7 us isolated at B = 64, 1.43 against 1.59 ms per step; the three warps of
 // an SMSP still settle into lockstep (an initial stagger of the streams changes nothing), two K/V stages instead of three:
-// +1 %.
+// +1 %.  A four-stream form (20 warps, 96 registers: the softmax in two halves of 32 keys with the scores read from TMEM
+// twice, one S / P slot per stream, one controller warp per stream polling with mbarrier.test_wait) ran at 95 us.
 // ================================================================================================
 constexpr int L3_NST = 3;
 constexpr int L3_THREADS = 16 * 32;
@@ -763,7 +764,7 @@ local_attention3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
         const int rq = (it[s].b * H + it[s].h) * L;
         if (kt[s] < 0) {
           const int qb = n[s] & 1;
-          if (!ptx::mbar_try_wait(&bar.q_free[qb], ((n[s] >> 1) & 1) ^ 1)) continue;
+          if (!ptx::mbar_test_wait(&bar.q_free[qb], ((n[s] >> 1) & 1) ^ 1)) continue;
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&bar.q_full[qb], TC_TILE);
             ptx::tma_load_2d(sQ + qb * TC_TILE, &tm_qkv, &bar.q_full[qb], 0, rq + it[s].w * WIN);
@@ -772,7 +773,7 @@ local_attention3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
           kt[s] = 0;
           progress = true;
         } else {
-          if (!ptx::mbar_try_wait(&bar.kv_free[st[s]], st_ph[s] ^ 1)) continue;
+          if (!ptx::mbar_test_wait(&bar.kv_free[st[s]], st_ph[s] ^ 1)) continue;
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&bar.kv_full[st[s]], 2 * TC_TILE);
             ptx::tma_load_2d(sKV + (2 * st[s]) * TC_TILE, &tm_qkv, &bar.kv_full[st[s]], 0, plane + rq + (it[s].w_lo + kt[s]) * WIN);
