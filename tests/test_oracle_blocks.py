@@ -77,3 +77,31 @@ def test_categorical_draw_equals_torch_multinomial():
         probs=torch.softmax(logits, 1).permute(0, 2, 1)).sample(), -1)
     q = osamp.reference_noise_stream(7, 1, 2, 64, 29)[0]
     assert torch.equal(osamp.sample_tokens(logits, q), ref)
+
+
+def test_reference_call_site_keywords_are_the_oracle_constructor_parameters():
+    """The reference builds every block with `LinearAttentionTransformer(emb_dim, 1, max_seq_len, heads=..., ...)`
+    (/root/reference/Stage3_source/cond_diff_transformer_layer.py:123-143).  Every keyword that call passes must be a
+    parameter of the oracle's stand-in (which asserts the hot-path value of the options the sampling config leaves at
+    their defaults), and the call must pass nothing that would select a different upstream code path
+    (`exact_windowsize`, `autopad`, `shared_qk`, `look_backward` / `look_forward`, `bucket_size` are never given, so
+    upstream's defaults apply).  Runs where the reference tree exists; the GPU box has no copy."""
+    import ast
+    import inspect
+    import os
+
+    import pytest
+    path = '/root/reference/Stage3_source/cond_diff_transformer_layer.py'
+    if not os.path.exists(path):
+        pytest.skip('reference tree not present')
+    tree = ast.parse(open(path).read())
+    calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, 'id', None) == 'LinearAttentionTransformer']
+    assert len(calls) == 1
+    call = calls[0]
+    assert len(call.args) == 3 and isinstance(call.args[1], ast.Constant) and call.args[1].value == 1      # depth 1 per block
+    passed = {k.arg for k in call.keywords}
+    params = set(inspect.signature(ub.LinearAttentionTransformer.__init__).parameters) - {'self'}
+    assert passed <= params, passed - params
+    assert not passed & {'exact_windowsize', 'autopad', 'shared_qk', 'look_backward', 'look_forward', 'bucket_size',
+                         'receives_context', 'pkm_layers', 'shift_tokens'}
+    assert {'heads', 'n_local_attn_heads', 'local_attn_window_size', 'ff_glu', 'reversible', 'causal'} <= passed
