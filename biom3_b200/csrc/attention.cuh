@@ -67,6 +67,9 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
   return make_float2(__bfloat162float(b.x), __bfloat162float(b.y));
 }
 
+// QSOFT = false (the decode's form): q arrives already softmaxed over its features (the QKV GEMM epilogue did it from the
+// fp32 accumulator, gemm::Params::qkv_chunk kind 1); phase B is then load -> MMA -> store.
+template <bool QSOFT>
 __global__ void __launch_bounds__(128)
 linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int H, int L,
                         int NL, float q_scale, int reverse) {
@@ -241,6 +244,7 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         ptx::ldmatrix_x4(cur + swz(mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)), qa[ks][0],
                          qa[ks][1], qa[ks][2], qa[ks][3]);
       // rows g (regs 0, 2) and g + 8 (regs 1, 3): softmax over the 32 features held by the quad
+      if constexpr (QSOFT) {
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float2 x[4];
@@ -265,6 +269,7 @@ linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         qa[0][hf + 2] = ptx::pack_bf16x2(x[1].x * inv, x[1].y * inv);
         qa[1][hf] = ptx::pack_bf16x2(x[2].x * inv, x[2].y * inv);
         qa[1][hf + 2] = ptx::pack_bf16x2(x[3].x * inv, x[3].y * inv);
+      }
       }
       float o[4][4];
 #pragma unroll

@@ -82,6 +82,8 @@ constexpr int RESID_SLOTS = BIOM3_RESID_SLOTS;
 #endif
 constexpr int RESID_SLOT_BYTES = 4096;   // 32 rows x 64 bytes, hi block then lo block
 
+constexpr int QKV_MAX_CHUNKS = 256;   // 3 * dim / 32 <= 256
+
 struct Params {
   int M, N, K;
   int b_row_offset;        // first row of this layer's weight inside the stacked weight tensor map
@@ -94,6 +96,12 @@ struct Params {
   int L;                   // tokens per sample (rows per batch entry)
   int H;                   // heads (EPI_QKV_HEADMAJOR)
   int Bsz;                 // batch (EPI_QKV_HEADMAJOR)
+  // EPI_QKV_HEADMAJOR: what the i-th 32-column chunk of the output is (a chunk of a row IS one head of one token):
+  // bits 0-11 head, 12-13 which (0 q, 1 k, 2 v), 14-15 kind.  Kind 1: stored as softmax over the head's 32 features, taken
+  // from the fp32 accumulator (q of a linear-attention head).  The host permutes the weight rows so that the chunks with
+  // extra work are spread evenly over the column tiles (biom3_model::qkv_chunk); the identity order with kind 0 is the
+  // plain head-major store.
+  unsigned short qkv_chunk[QKV_MAX_CHUNKS];
   // consumer side of the folded LayerNorm (bf16-output epilogues): x = rstd*(acc - mean*ln_s[n]) + ln_t[n]
   const float* ln_stats;   // [M][ln_parts][2] partial (sum, sumsq) over the K features, or nullptr
   const float* ln_s;       // [N]
@@ -728,12 +736,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const float nm = -mean * rstd;
         int tma_c0 = nbase, tma_c1 = rbase;                // TMA-store coordinates (column, row) of chunk 0
         if constexpr (EPI == EPI_QKV_HEADMAJOR) {
-          const int D = p.N / 3;
           tma_c0 = 0;
-          int which, hrem;
-          if (p.d_shift >= 0) { which = nbase >> p.d_shift; hrem = nbase & (D - 1); }
-          else { which = nbase / D; hrem = nbase % D; }
-          tma_c1 = ((which * p.Bsz + bidx) * p.H + (hrem >> 5)) * p.L + row_l(rbase);
+          tma_c1 = row_l(rbase);                           // row inside the (which, sample, head) plane; the plane is per chunk
         }
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) g_gemm_trace[1][it][0] = clock64();
         ptx::mbar_wait_parked(&acc_full[as], aphase);
@@ -763,6 +767,25 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf_half(use_vec ? v[i] : 0.5f * v[i]);
+          }
+          [[maybe_unused]] uint32_t chunk_desc = 0;
+          if constexpr (EPI == EPI_QKV_HEADMAJOR) {
+            chunk_desc = p.qkv_chunk[(nbase >> 5) + c];
+            if ((chunk_desc >> 14) == 1) {                 // q of a linear-attention head: softmax over its 32 features
+              float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+              for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+              const float ml = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * 1.4426950408889634f;
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[i]) : "f"(fmaf(v[i], 1.4426950408889634f, -ml)));
+                s4[i & 3] += v[i];
+              }
+              const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= inv;
+            }
           }
           if constexpr (EPI == EPI_BIAS_GELU_SPLIT) {
             // exact erf form (torch's default nn.GELU), then the second staging block takes the lo halves
@@ -804,8 +827,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::fence_proxy_async();
           __syncwarp();
           if (ptx::elect_one()) {
-            ptx::tma_store_2d(&tmap_c, stg, tma_c0 + (EPI == EPI_QKV_HEADMAJOR ? 0 : c * 32),
-                              tma_c1 + (EPI == EPI_QKV_HEADMAJOR ? c * p.L : 0));
+            if constexpr (EPI == EPI_QKV_HEADMAJOR)
+              ptx::tma_store_2d(&tmap_c, stg, 0, ((int((chunk_desc >> 12) & 3) * p.Bsz + bidx) * p.H + int(chunk_desc & 0xfff)) * p.L + tma_c1);
+            else
+              ptx::tma_store_2d(&tmap_c, stg, tma_c0 + c * 32, tma_c1);
             ptx::tma_store_commit();
           }
           __syncwarp();

@@ -205,8 +205,9 @@ cudaError_t init_kernel_attributes_impl() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn::local_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::L3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn::linear_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           attn::LIN_SMEM_BYTES);
+  e = cudaFuncSetAttribute(attn::linear_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::LIN_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn::linear_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::LIN_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(f32p::local_attention_f32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32p::LAT_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -315,6 +316,8 @@ struct biom3_model {
   // rows the sampler consumes are carried through out-proj / MLP / head (k::gather_rows_kernel).  BIOM3_COMPACT=0
   // computes every row like the reference does.
   bool compact_last = true;
+  unsigned short qkv_chunk[gemm::QKV_MAX_CHUNKS] = {};   // gemm::Params::qkv_chunk: output order of the QKV GEMM, set by finalize
+  bool qsoft_epi = true;        // softmax(q) of the linear-attention heads in the QKV GEMM epilogue (BIOM3_QSOFT_EPI=0: in the attention kernel)
   int compact_rows_max = 0;                     // rows allocated for the compact buffers (multiple of 256), 0 = none
   int last_compact_rows = 0;                    // rows the last run_step() carried through the last layer's MLP (0 = all)
   bf16 *att_c = nullptr, *a_c = nullptr, *ulo_c = nullptr, *hid_c = nullptr;
@@ -450,6 +453,58 @@ int upload_folded(biom3_model* m, const std::string& g_key, const std::string& b
   return BIOM3_OK;
 }
 
+// Output order of the QKV GEMM in 32-column chunks (one chunk = one head of q, k or v).  With the q softmax of the
+// linear-attention heads done in the GEMM epilogue (qsoft_epi) those chunks cost the epilogue warps about twice the plain
+// ones; in the natural order they fill a whole 256-column tile (heads NL.. of q are columns 256-511 at the stage3 shape)
+// whose epilogue then outlasts the next tile's mainloop (profiles/r02_ab_qk_epilogue_unpermuted.jsonl: QKV +0.13 ms per
+// step, all of the linear-attention kernel's gain).  The weight rows are permuted so that they are spread evenly
+// (profiles/r02_ab_qk_epilogue.jsonl: QKV unchanged, step -0.07 ms); gemm::Params::qkv_chunk tells the epilogue what
+// each chunk is and where it goes, so the qkv layout in memory does not change.
+void build_qkv_chunk_order(biom3_model* m) {
+  const int H = m->cfg.heads, NL = m->cfg.local_heads;
+  std::vector<unsigned short> heavy, light;
+  for (int which = 0; which < 3; ++which)
+    for (int h = 0; h < H; ++h) {
+      int kind = 0;
+      if (m->precision == 0 && h >= NL && which == 0 && m->qsoft_epi) kind = 1;
+      (kind ? heavy : light).push_back((unsigned short)(h | (which << 12) | (kind << 14)));
+    }
+  const size_t n = size_t(3) * H, nh = heavy.size();
+  size_t ih = 0, il = 0;
+  for (size_t i = 0; i < n; ++i)
+    m->qkv_chunk[i] = ((i + 1) * nh / n > i * nh / n) ? heavy[ih++] : light[il++];
+}
+
+// rows of layer j's stacked [q | k | v] weight (and its folded-LayerNorm vectors) from the natural order into qkv_chunk's
+int permute_qkv_chunks(biom3_model* m, size_t j) {
+  const size_t D = m->cfg.dim, H = m->cfg.heads, n = 3 * H;
+  bool identity = true;
+  for (size_t i = 0; i < n; ++i) identity = identity && size_t(((m->qkv_chunk[i] >> 12) & 3) * H + (m->qkv_chunk[i] & 0xfff)) == i;
+  if (identity) return BIOM3_OK;
+  bf16* w = m->Wqkv + j * 3 * D * D;
+  float* vec[2] = {m->ln_s_qkv + j * 3 * D, m->ln_t_qkv + j * 3 * D};
+  bf16* wtmp = nullptr;
+  float* vtmp = nullptr;
+  CU_OK(cudaMalloc(&wtmp, 3 * D * D * sizeof(bf16)));
+  CU_OK(cudaMalloc(&vtmp, 3 * D * sizeof(float)));
+  CU_OK(cudaMemcpy(wtmp, w, 3 * D * D * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  for (size_t i = 0; i < n; ++i) {
+    const size_t src = size_t((m->qkv_chunk[i] >> 12) & 3) * H + (m->qkv_chunk[i] & 0xfff);
+    CU_OK(cudaMemcpy(w + i * 32 * D, wtmp + src * 32 * D, 32 * D * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  }
+  for (float* v : vec) {
+    CU_OK(cudaMemcpy(vtmp, v, 3 * D * sizeof(float), cudaMemcpyDeviceToDevice));
+    for (size_t i = 0; i < n; ++i) {
+      const size_t src = size_t((m->qkv_chunk[i] >> 12) & 3) * H + (m->qkv_chunk[i] & 0xfff);
+      CU_OK(cudaMemcpy(v + i * 32, vtmp + src * 32, 32 * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+  }
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaFree(wtmp));
+  CU_OK(cudaFree(vtmp));
+  return BIOM3_OK;
+}
+
 // C = act(A W^T + b), fp32 (conditioning MLPs only)
 void sgemm(const float* A, const float* W, const float* b, float* C, int M, int N, int K, int act, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
@@ -564,12 +619,18 @@ cudaError_t run_step(biom3_model* m, int B, int group, const int* t_per_sample, 
     p.ln_stats = m->stats; p.ln_parts = m->ln_parts;
     p.ln_s = m->ln_s_qkv + size_t(j) * 3 * D; p.ln_t = m->ln_t_qkv + size_t(j) * 3 * D;
     p.reverse = next_dir();
+    memcpy(p.qkv_chunk, m->qkv_chunk, sizeof(p.qkv_chunk));
     LAUNCH(C_QKV, launch_gemm<gemm::EPI_QKV_HEADMAJOR>(m->bn_wide, pw, m->tm_a, m->tm_wqkv[iw], m->tm_st_qkv, p, m->num_sms, st));
     const int adir = next_dir();                // both attention kernels read the same QKV output
     // the two attention kernels read the same QKV output and write disjoint column ranges of `att`
-    if (H - NL > 0)
-      LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), st, m->qkv, m->att, B, H, L, NL,
-                                                                                       q_scale, adir));
+    if (H - NL > 0) {
+      if (m->qsoft_epi)
+        LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel<false>, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), st, m->qkv,
+                                  m->att, B, H, L, NL, q_scale, adir));
+      else
+        LAUNCH(C_LINEAR, launch_k(attn::linear_attention_kernel<true>, dim3(H - NL, B), dim3(128), size_t(attn::LIN_SMEM_BYTES), st, m->qkv,
+                                  m->att, B, H, L, NL, q_scale, adir));
+    }
     if (NL > 0)
       LAUNCH(C_LOCAL, launch_local(m->tm_qkv_attn, m->att, B, H, L, NL, scale_log2e, adir, m->num_sms, 0, st));
     // u += att . Wo^T + bo ; also emits bf16(u) and its row statistics for the next folded LayerNorm
@@ -671,6 +732,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (c.n_blocks != 1) return fail(BIOM3_ERR_INVALID, "transformer_blocks must be 1");
   if (c.heads <= 0 || c.dim != c.heads * attn::DH)
     return fail(BIOM3_ERR_INVALID, "transformer_dim / transformer_heads must be 32");
+  if (3 * c.heads > gemm::QKV_MAX_CHUNKS) return fail(BIOM3_ERR_INVALID, "transformer_heads must be <= 85");
   if (c.dim % 256 != 0 || c.dim > 1024) return fail(BIOM3_ERR_INVALID, "transformer_dim must be a multiple of 256, <= 1024");
   if (c.local_window != attn::WIN) return fail(BIOM3_ERR_INVALID, "transformer_local_size must be 128");
   if (c.seq_len <= 0 || c.seq_len % c.local_window != 0)
@@ -701,6 +763,7 @@ int biom3_create(const biom3_config* cfg, int device, int max_batch, biom3_model
   if (const char* e = getenv("BIOM3_F32_ATTN_MMA")) m->f32_attn_mma = atoi(e);
   if (const char* e = getenv("BIOM3_F32_FUSED_GELU")) m->f32_fused_gelu = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_COMPACT")) m->compact_last = atoi(e) != 0;
+  if (const char* e = getenv("BIOM3_QSOFT_EPI")) m->qsoft_epi = atoi(e) != 0;
   if (const char* e = getenv("BIOM3_FWD_GRAPH")) m->fwd_graph = atoi(e) != 0;
   CU_OK(init_kernel_attributes());
   CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
@@ -818,6 +881,7 @@ int biom3_finalize_weights(biom3_model* m) {
   TRY(upload_f32(m, T + "y_mlp.0.bias", 4 * D, m->y_b0));
   TRY(upload_f32(m, T + "y_mlp.2.weight", D * depth * 4 * D, m->y_w2));
   TRY(upload_f32(m, T + "y_mlp.2.bias", D * depth, m->y_b2));
+  build_qkv_chunk_order(m);
   for (size_t j = 0; j < depth; ++j) {
     const std::string P = T + "transformer_blocks.0." + std::to_string(j) + ".layers.layers.0.";
     // Folded LayerNorms: W' = gamma (.) W in bf16, s_n = sum_k bf16(W'_nk), t_n = sum_k beta_k W_nk (+ bias)
@@ -827,6 +891,7 @@ int biom3_finalize_weights(biom3_model* m) {
                       m->Wqkv + (j * 3 + 1) * D * D, m->ln_s_qkv + (j * 3 + 1) * D, m->ln_t_qkv + (j * 3 + 1) * D));
     TRY(upload_folded(m, P + "0.norm.weight", P + "0.norm.bias", P + "0.fn.to_v.weight", "", D, D,
                       m->Wqkv + (j * 3 + 2) * D * D, m->ln_s_qkv + (j * 3 + 2) * D, m->ln_t_qkv + (j * 3 + 2) * D));
+    TRY(permute_qkv_chunks(m, j));
     TRY(upload_bf16(m, P + "0.fn.to_out.weight", D * D, m->Wo + j * D * D));
     TRY(upload_f32(m, P + "0.fn.to_out.bias", D, m->bo + j * D));
     TRY(upload_folded(m, P + "1.norm.weight", P + "1.norm.bias", P + "1.fn.fn.w1.weight", P + "1.fn.fn.w1.bias", 4 * D, D,
@@ -1302,10 +1367,12 @@ int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    launch_local(tm, o, B, H, L, NL, scale_log2e, 0, sms, variant == 1, st);
+    launch_local(tm, o, B, H, L, NL, scale_log2e, 0, sms, (variant & 1) != 0, st);
   }
-  if (H - NL > 0)
-    attn::linear_attention_kernel<<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
+  if (H - NL > 0) {                      // variant bit 1: the caller's q of the linear heads is already softmaxed over its features
+    if (variant & 2) attn::linear_attention_kernel<false><<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
+    else attn::linear_attention_kernel<true><<<dim3(H - NL, B), 128, attn::LIN_SMEM_BYTES, st>>>(q, o, B, H, L, NL, q_scale, 0);
+  }
   CU_OK(cudaGetLastError());
   return BIOM3_OK;
 }

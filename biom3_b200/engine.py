@@ -242,8 +242,9 @@ def gemm_test(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ep
 
 
 def attention_test(qkv: torch.Tensor, NL: int, variant: int = 0) -> torch.Tensor:
-    """Unit-test hook: qkv bf16 [3, B, H, L, 32] (cuda) -> attention output bf16 [B*L, H*32]; variant 1 also records
-    the local-attention kernel's clock64 timeline (biom3_debug_trace)."""
+    """Unit-test hook: qkv bf16 [3, B, H, L, 32] (cuda) -> attention output bf16 [B*L, H*32]; variant bit 0 also records
+    the local-attention kernel's clock64 timeline (biom3_debug_trace), bit 1: q of the linear heads is already
+    softmax(q) over the features (the form the QKV GEMM epilogue writes in the decode)."""
     lib = _lib.load()
     _, B, H, L, dh = qkv.shape
     assert dh == 32 and qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous()

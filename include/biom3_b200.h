@@ -121,8 +121,9 @@ int biom3_gemm_test(const void* A, const void* W, const float* bias, void* out, 
                     int block_n, int pair, void* stream);
 
 /* Unit-test hook for the attention kernels: qkv device bf16 [3][B][H][L][32] -> out device bf16 [B*L][H*32].
- * Heads [0, NL) windowed softmax (tcgen05 kernel; variant 1 = the same kernel recording CTA 0's clock64 timeline,
- * biom3_debug_trace(0, ...)), heads [NL, H) linear attention. */
+ * Heads [0, NL) windowed softmax (tcgen05 kernel; variant bit 0 = the same kernel recording CTA 0's clock64 timeline,
+ * biom3_debug_trace(0, ...)), heads [NL, H) linear attention (variant bit 1: q of those heads is already softmax(q) over
+ * the features -- the form the QKV GEMM epilogue writes in the decode). */
 int biom3_attention_test(const void* qkv, void* out, int B, int H, int L, int NL, int variant, void* stream);
 
 /* Per-kernel device timings (ms) of the last biom3_profile_step() call; for bench.py's roofline. */

@@ -560,6 +560,58 @@ def test_attention_kernels_vs_fp32_reference(B, H, L, NL, amp, variant, streams,
         assert rel_err(out[:, NL * 32:], ref[:, NL * 32:]) < 8e-3
 
 
+@pytest.mark.parametrize('B,H,L,NL,amp', [(2, 4, 256, 2, 1.5), (2, 16, 1024, 8, 1.5), (3, 4, 1024, 0, 6.0)])
+def test_linear_attention_with_q_prepared_by_the_qkv_epilogue(B, H, L, NL, amp):
+    """The decode's form of the linear-attention kernel (variant bit 1): q of the linear heads arrives as softmax over the
+    head's features, the way the QKV GEMM epilogue writes it; the kernel's second phase is then load -> MMA -> store.
+    Against the fp32 reference of the whole op on the raw q."""
+    from biom3_b200 import engine
+    from oracle.upstream_blocks import LocalAttention, linear_attention
+    g = torch.Generator().manual_seed(B * 100 + L + 1)
+    raw = torch.randn(3, B, H, L, 32, generator=g) * amp
+    q, k, v = (t.bfloat16().float() for t in raw)
+    fed = raw.clone()
+    fed[0, :, NL:] = torch.softmax(raw[0, :, NL:], -1)            # what the epilogue stores: softmax of the fp32 q
+    ref_lin = linear_attention(raw[0, :, NL:], k[:, NL:], v[:, NL:])
+    out = engine.attention_test(fed.bfloat16().cuda(), NL, 2).float().cpu()
+    got_lin = out[:, NL * 32:].reshape(B, L, H - NL, 32).transpose(1, 2)
+    assert rel_err(got_lin, ref_lin) < 8e-3
+    if NL:
+        lo = LocalAttention(128)(q[:, :NL], k[:, :NL], v[:, :NL]).transpose(1, 2).reshape(B * L, NL * 32)
+        assert rel_err(out[:, :NL * 32], lo) < 8e-3
+
+
+def test_qkv_epilogue_softmaxes_q_of_the_linear_heads(monkeypatch):
+    """BIOM3_QSOFT_EPI=1 (default): the QKV GEMM epilogue stores softmax(q) for heads >= NL (weight rows permuted so that
+    those chunks are spread over the column tiles, the qkv layout in memory unchanged) and leaves everything else as it
+    was; the logits agree with the in-kernel form (BIOM3_QSOFT_EPI=0) and with the oracle."""
+    B, L = 3, 256                                # 768 rows: CTA-pair tiles; the odd-row test covers single-CTA tiles
+    H, NL = 8, 4
+    g = torch.Generator().manual_seed(21)
+    x = torch.randint(0, 29, (B, L), generator=g)
+    t = torch.tensor([0, 100, 255])
+    z = synthetic.synthetic_z_c(B, 64, seed=4)
+    res = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('BIOM3_QSOFT_EPI', flag)
+        args, sd, eng, orc = make(dict(SMALL, transformer_depth=1), B)
+        logits = eng.forward(x.cuda(), t.cuda(), z.cuda()).float().cpu()
+        qkv = eng.debug_buffer('qkv', (3, B, H, L, 32), torch.bfloat16).float()      # the only layer's q, k, v
+        res[flag] = (logits, qkv)
+        assert rel_err(logits, orc(x, t, z)) < LOGIT_TOL
+        del eng
+    (l0, q0), (l1, q1) = res['0'], res['1']
+
+    def same(a, b):                                                      # same column, other position in the tile: one bf16 ulp at most
+        return bool(((a - b).abs() <= 2 ** -7 * a.abs() + 1e-6).all())
+    assert same(q0[1:], q1[1:])                                          # k, v untouched (their weight rows moved, nothing else)
+    assert same(q0[0, :, :NL], q1[0, :, :NL])                            # q of the windowed heads untouched
+    soft = torch.softmax(q0[0, :, NL:], -1)                              # from the bf16-rounded q: agrees to bf16 rounding
+    assert (q1[0, :, NL:].sum(-1) - 1).abs().max().item() < 2e-2
+    assert (q1[0, :, NL:] - soft).abs().max().item() < 2e-2 * soft.max().item() + 1e-3
+    assert rel_err(l1, l0) < 5e-3
+
+
 # ---------------------------------------------------------------- fp32-class mode (biom3_set_precision(m, 1))
 FP32_TOL = 1e-4          # BASELINE.json north_star: logits within 1e-4 relative in fp32
 
