@@ -105,3 +105,56 @@ def test_reference_call_site_keywords_are_the_oracle_constructor_parameters():
     assert not passed & {'exact_windowsize', 'autopad', 'shared_qk', 'look_backward', 'look_forward', 'bucket_size',
                          'receives_context', 'pkm_layers', 'shift_tokens'}
     assert {'heads', 'n_local_attn_heads', 'local_attn_window_size', 'ff_glu', 'reversible', 'causal'} <= passed
+
+
+def test_whole_block_equals_a_float64_numpy_rederivation():
+    """One LinearAttentionTransformer(depth=1) block, re-derived token by token in float64 numpy from the published
+    definition (pre-norm, heads [0, nl) windowed softmax over windows w-1..w+1, heads [nl, h) linear attention, head-major
+    concatenation, to_out, residual; pre-norm, w1 -> exact GELU -> w2, residual), without any of the oracle's reshapes,
+    bucketing or einsum strings: catches a head split / concatenation order or residual wiring the two parts of the oracle
+    would share."""
+    import numpy as np
+    torch.manual_seed(5)
+    dim, heads, nl, W, n = 64, 4, 2, 16, 48
+    blk = ub.LinearAttentionTransformer(dim, 1, n, heads=heads, n_local_attn_heads=nl, local_attn_window_size=W)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(0.05 * torch.randn_like(p))                     # LayerNorm off its defaults, biases non-zero
+    x = torch.randn(2, n, dim)
+    got = blk(x).detach().double().numpy()
+    sd = {k: v.detach().double().numpy() for k, v in blk.state_dict().items()}
+    A, F_ = 'layers.layers.0.0.', 'layers.layers.0.1.'
+    dh = dim // heads
+
+    def ln(v, g, b):
+        mu = v.mean()
+        return (v - mu) / math.sqrt(((v - mu) ** 2).mean() + 1e-5) * g + b
+
+    def erf_gelu(v):
+        return np.array([0.5 * t * (1.0 + math.erf(t / math.sqrt(2.0))) for t in v])
+
+    for b in range(x.shape[0]):
+        u = x[b].double().numpy()
+        y = np.stack([ln(u[i], sd[A + 'norm.weight'], sd[A + 'norm.bias']) for i in range(n)])
+        q, k, v = (y @ sd[A + f'fn.to_{c}.weight'].T for c in 'qkv')
+        att = np.zeros((n, dim))
+        for h in range(heads):
+            cols = slice(h * dh, (h + 1) * dh)
+            qh, kh, vh = q[:, cols], k[:, cols], v[:, cols]
+            if h < nl:
+                for i in range(n):
+                    keys = [j for j in range(n) if abs(j // W - i // W) <= 1]
+                    s = np.array([qh[i] @ kh[j] for j in keys]) * dh ** -0.5
+                    pr = np.exp(s - s.max())
+                    att[i, cols] = (pr / pr.sum()) @ vh[keys]
+            else:
+                ek = np.exp(kh - kh.max(0))
+                ctx = (ek / ek.sum(0)).T @ vh                       # [d, e]: softmax over the tokens, per feature
+                for i in range(n):
+                    eq = np.exp(qh[i] - qh[i].max())
+                    att[i, cols] = (eq / eq.sum() * dh ** -0.5) @ ctx
+        u = u + att @ sd[A + 'fn.to_out.weight'].T + sd[A + 'fn.to_out.bias']
+        y = np.stack([ln(u[i], sd[F_ + 'norm.weight'], sd[F_ + 'norm.bias']) for i in range(n)])
+        hid = np.stack([erf_gelu(r) for r in y @ sd[F_ + 'fn.fn.w1.weight'].T + sd[F_ + 'fn.fn.w1.bias']])
+        u = u + hid @ sd[F_ + 'fn.fn.w2.weight'].T + sd[F_ + 'fn.fn.w2.bias']
+        assert np.abs(got[b] - u).max() < 5e-5 * max(1.0, np.abs(u).max())
